@@ -1,0 +1,260 @@
+/*
+ * pcdn_fanout.h — C ABI of the B200-native broker fan-out engine.
+ *
+ * This is the drop-in boundary for ONE hot path of EspressoSystems/Push-CDN: cdn-broker's
+ * broadcast + direct-message routing and per-recipient replication with the cdn-proto
+ * `u32 big-endian length ‖ raw bytes` framing fused in.  The reference (100 % safe Rust, no FFI)
+ * has no plugin interface; the seam is cut where SURVEY.md §8(b) puts it.  Every entry point
+ * below names the reference function it replaces (paths relative to the reference repo root).
+ *
+ * Threading: all calls on one engine are serialised internally by a mutex (mirrors the single
+ * `parking_lot::RwLock<Connections>` of cdn-broker/src/lib.rs:98).  State calls issued before a
+ * flush/submit are visible to that batch, later ones are not (R12).
+ *
+ * Errors: every function returns 0 (PCDN_OK) or a negative PCDN_E* code; a human-readable message
+ * for the calling thread is available from pcdn_last_error().  Nothing throws or aborts across
+ * the ABI.  Unknown recipient / no subscribers is success with 0 deliveries (reference:
+ * cdn-broker/src/tasks/broker/handler.rs:210 silently drops).
+ *
+ * There is NO CPU data path behind this ABI: with `device < 0` the engine is a host-only state
+ * mirror (used by CPU unit tests of the table logic) and every data call fails with PCDN_ENODEV.
+ */
+#ifndef PCDN_FANOUT_H
+#define PCDN_FANOUT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCDN_ABI_VERSION 1u
+
+/* ---- status codes ------------------------------------------------------------------------- */
+enum {
+  PCDN_OK = 0,
+  PCDN_EINVAL = -1,    /* bad argument                                                          */
+  PCDN_ENOMEM = -2,    /* host or device allocation failed                                      */
+  PCDN_ENODEV = -3,    /* no CUDA device / host-only engine asked to route                      */
+  PCDN_ECUDA = -4,     /* a CUDA runtime call failed (message has the cudaError string)         */
+  PCDN_ENOSPC = -5,    /* a fixed-capacity table is full (conns, keys, batch arena, entries)    */
+  PCDN_EKEYLEN = -6,   /* key longer than config.max_key_len                                    */
+  PCDN_EPARSE = -7,    /* frame is not a valid cdn-proto message (=> caller disconnects peer)   */
+  PCDN_EPRUNE = -8,    /* Topic::prune left no valid topic (=> caller disconnects peer)         */
+  PCDN_EKIND = -9,     /* message kind not allowed on this connection type (=> disconnect)      */
+  PCDN_ENOENT = -10,   /* unknown batch id / connection                                         */
+  PCDN_EAGAIN = -11,   /* all batch slots in flight: poll + release one first                   */
+  PCDN_E2BIG = -12     /* batch exceeded max_batch_deliveries on the device; nothing was packed */
+};
+
+/* ---- vocabulary --------------------------------------------------------------------------- */
+typedef struct pcdn_engine pcdn_engine; /* opaque */
+typedef uint32_t pcdn_conn;            /* dense connection id; users and peer brokers share it */
+#define PCDN_CONN_NONE 0xFFFFFFFFu
+
+/* capnp union tags of cdn-proto/schema/messages.capnp (messages_capnp.rs:277,292) */
+enum {
+  PCDN_KIND_DIRECT = 3,
+  PCDN_KIND_BROADCAST = 4,
+  PCDN_KIND_SUBSCRIBE = 5,
+  PCDN_KIND_UNSUBSCRIBE = 6,
+  PCDN_KIND_USER_SYNC = 7,
+  PCDN_KIND_TOPIC_SYNC = 8
+};
+
+/* pcdn_msg.flags — `to_users_only` / `to_user_only` of handler.rs:197,240 (R4) */
+enum { PCDN_TO_USERS_ONLY = 1 };
+
+/* Output records are 32-byte aligned inside a connection's ring; one record = one framed
+ * delivery: u32 BE length ‖ raw bytes ‖ pad.  32 B = one DRAM sector, so two records never share
+ * a sector and no store of the pack kernel is a partial-sector write. */
+#define PCDN_RECORD_ALIGN 32u
+
+typedef struct pcdn_config {
+  uint32_t struct_size;         /* = sizeof(pcdn_config); ABI guard                             */
+  int32_t device;               /* CUDA ordinal; < 0 = host-only state mirror (no data path)    */
+  uint32_t max_conns;           /* capacity of the dense connection-id space (users + brokers)  */
+  uint32_t max_topics;          /* rows of the subscription bitmap; 256 = wire-exact (Topic=u8) */
+  uint32_t max_keys;            /* direct-map capacity (entries of the cuckoo table)            */
+  uint32_t max_key_len;         /* longest user public key in bytes (prod BLS-BN254 G2 = 128)   */
+  uint64_t ring_bytes_per_conn; /* output ring per connection, multiple of 32                   */
+  uint32_t max_batch_msgs;      /* messages per batch                                           */
+  uint32_t max_batch_bcast;     /* broadcast messages per batch (sizes the match matrix)        */
+  uint64_t max_batch_bytes;     /* bytes of frames per batch (device arena + pinned staging)    */
+  uint64_t max_batch_deliveries;/* capacity of the scatter list per batch                       */
+  uint32_t batch_slots;         /* batches in flight (>=1)                                      */
+  uint32_t n_valid_topics;      /* Topic::prune validity: topic t is valid iff t < this (def.rs:25-49); 0 = all */
+  uint64_t hash_seed;           /* keys the direct-map hash (0 = default)                       */
+  void* stream;                 /* optional cudaStream_t to run on (e.g. torch's); NULL = own   */
+  const char* identity;         /* this broker's BrokerIdentifier string "public/private"       */
+  uint32_t pack_variant;        /* 0 = default; see DESIGN.md (kernel selection for profiling)  */
+  uint32_t reserved;
+} pcdn_config;
+
+/* One routed message.  `raw` is the inbound frame body and is forwarded verbatim (R1). */
+typedef struct pcdn_msg {
+  uint8_t kind;  /* PCDN_KIND_BROADCAST or PCDN_KIND_DIRECT                                     */
+  uint8_t flags; /* PCDN_TO_USERS_ONLY                                                          */
+  uint16_t n_topics;
+  const uint16_t* topics;   /* broadcast: already pruned (R6)                                   */
+  const uint8_t* recipient; /* direct: recipient public key                                     */
+  uint32_t recipient_len;
+  uint32_t raw_len;
+  const uint8_t* raw;
+} pcdn_msg;
+
+/* A contiguous run of records in one connection's ring.  The host walks it as the reference's
+ * writer task walks its queue (cdn-proto/src/connection/protocols/mod.rs:156-186): at `p` read
+ * L = BE32(p), write the 4+L bytes to the socket, advance p by round_up(4+L, 32). */
+typedef struct pcdn_span {
+  pcdn_conn conn;
+  uint32_t ring_off;  /* byte offset of the first record inside the connection's ring          */
+  uint32_t len;       /* bytes covered (multiple of 32), padding included                      */
+  uint32_t n_records; /* deliveries in this run                                                */
+} pcdn_span;
+
+typedef struct pcdn_batch_result {
+  uint64_t batch_id;
+  uint32_t n_msgs;
+  uint32_t n_spans;
+  const pcdn_span* spans;          /* engine-owned pinned host memory, valid until release      */
+  uint64_t n_deliveries;           /* records written                                           */
+  uint64_t bytes_out;              /* sum of 4+L over deliveries (what BYTES_SENT would add, protocols/mod.rs:388) */
+  uint32_t n_overflow;             /* connections whose ring was full: their deliveries from the overflow point on were dropped; the host must remove them (R13 analogue) */
+  const pcdn_conn* overflow_conns; /* engine-owned                                              */
+  uint32_t n_direct_dropped;       /* direct messages with no route (handler.rs:210,224)        */
+  uint32_t status;                 /* 0 or PCDN_E2BIG (as positive number)                      */
+} pcdn_batch_result;
+
+/* Device-resident batch (inputs already in HBM; used by bench `value` and the NCCL ingest path).
+ * Frame slot layout in `arena`: each message owns a 16-byte aligned slot; the raw bytes start at
+ * slot+4 (the first 4 bytes are the hole the pack kernel fills with the BE length).  */
+typedef struct pcdn_device_batch {
+  uint32_t n_msgs;
+  uint32_t n_bcast;              /* number of broadcast messages among them                    */
+  const void* arena;             /* device: frame slots                                        */
+  uint64_t arena_bytes;
+  const uint8_t* kind;           /* device [n_msgs]                                            */
+  const uint8_t* flags;          /* device [n_msgs]                                            */
+  const uint32_t* slot_off16;    /* device [n_msgs] slot offset in arena, units of 16 B        */
+  const uint32_t* raw_len;       /* device [n_msgs]                                            */
+  const uint32_t* aux_off;       /* device [n_msgs] broadcast: index into `topics`; direct: byte offset of the recipient key in arena (4-byte aligned) */
+  const uint32_t* aux_len;       /* device [n_msgs] broadcast: topic count; direct: key length */
+  const uint16_t* topics;        /* device: concatenated topic lists                           */
+  uint32_t n_topics_total;
+  const uint32_t* bcast_index;   /* device [n_bcast]: batch index of the j-th broadcast, ascending */
+} pcdn_device_batch;
+
+typedef struct pcdn_stats {
+  uint64_t batches, msgs, deliveries, bytes_out;
+  double ms_match;   /* accumulated device time (CUDA events on the engine stream), when PCDN timing is on */
+  double ms_plan;
+  double ms_direct;
+  double ms_pack;
+  double ms_total;
+  uint64_t timed_batches;
+} pcdn_stats;
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+uint32_t pcdn_abi_version(void);
+void pcdn_config_default(pcdn_config* cfg);
+int pcdn_create(const pcdn_config* cfg, pcdn_engine** out);
+void pcdn_destroy(pcdn_engine* e);
+const char* pcdn_last_error(void);
+
+/* ---- state in: Connections::* (cdn-broker/src/connections/mod.rs) ------------------------- */
+/* Connections::add_user mod.rs:278-304 — kicks an existing user with the same key, registers the
+ * connection, direct_map[key]=self, subscribes to `topics`.  Returns the dense connection id.   */
+int pcdn_add_user(pcdn_engine* e, const uint8_t* key, uint32_t key_len, const uint16_t* topics,
+                  uint32_t n_topics, pcdn_conn* out_conn);
+/* Connections::remove_user mod.rs:330-351 */
+int pcdn_remove_user(pcdn_engine* e, const uint8_t* key, uint32_t key_len);
+/* Connections::subscribe_user_to mod.rs:365 / unsubscribe_user_from :383 (RelationalMap R10)   */
+int pcdn_subscribe_user_to(pcdn_engine* e, const uint8_t* key, uint32_t key_len,
+                           const uint16_t* topics, uint32_t n);
+int pcdn_unsubscribe_user_from(pcdn_engine* e, const uint8_t* key, uint32_t key_len,
+                               const uint16_t* topics, uint32_t n);
+/* Connections::add_broker mod.rs:252-274 / remove_broker :308-324 */
+int pcdn_add_broker(pcdn_engine* e, const char* identifier, pcdn_conn* out_conn);
+int pcdn_remove_broker(pcdn_engine* e, const char* identifier);
+/* Connections::subscribe_broker_to mod.rs:354 / unsubscribe_broker_from :372 */
+int pcdn_subscribe_broker_to(pcdn_engine* e, const char* identifier, const uint16_t* topics,
+                             uint32_t n);
+int pcdn_unsubscribe_broker_from(pcdn_engine* e, const char* identifier, const uint16_t* topics,
+                                 uint32_t n);
+/* Connections::apply_user_sync mod.rs:154-162 = VersionedMap::merge (versioned_map.rs:193-269)
+ * of a remote DirectMap followed by remove_user of every changed key.  One entry per key of the
+ * remote map; owner == NULL is a tombstone.  `remote_identity` is the remote map's conflict id. */
+typedef struct pcdn_user_sync_entry {
+  const uint8_t* key;
+  uint32_t key_len;
+  uint64_t version;
+  const char* owner; /* BrokerIdentifier string or NULL (tombstone) */
+} pcdn_user_sync_entry;
+int pcdn_apply_user_sync(pcdn_engine* e, const char* remote_identity,
+                         const pcdn_user_sync_entry* entries, uint32_t n);
+/* Bulk form of add_user for table loads (keys are fixed-stride); same semantics, one lock.      */
+int pcdn_add_users_bulk(pcdn_engine* e, const uint8_t* keys, uint32_t key_len, uint32_t key_stride,
+                        uint32_t n_users, const uint16_t* topics, const uint32_t* topic_offsets,
+                        pcdn_conn* out_conns /* optional */);
+
+/* ---- data in: the two routing functions of cdn-broker/src/tasks/broker/handler.rs ---------- */
+/* Inner::handle_broadcast_message handler.rs:240-272 — appended to the open batch.              */
+int pcdn_handle_broadcast_message(pcdn_engine* e, const uint16_t* topics, uint32_t n_topics,
+                                  const uint8_t* raw, uint32_t raw_len, int to_users_only);
+/* Inner::handle_direct_message handler.rs:197-237 */
+int pcdn_handle_direct_message(pcdn_engine* e, const uint8_t* recipient, uint32_t recipient_len,
+                               const uint8_t* raw, uint32_t raw_len, int to_user_only);
+/* One iteration of Inner::user_receive_loop (cdn-broker/src/tasks/user/handler.rs:104-161):
+ * Message::deserialize (cdn-proto/src/message.rs:212) → Topic::prune (def.rs:36-49) → dispatch.
+ * Broadcast/Direct are appended to the open batch; Subscribe/Unsubscribe update the tables (the
+ * open batch is flushed first so earlier messages do not see the change, R12).  A negative return
+ * (PCDN_EPARSE/EPRUNE/EKIND) means the reference loop would have ended: the caller removes the user. */
+int pcdn_user_receive(pcdn_engine* e, const uint8_t* sender_key, uint32_t key_len,
+                      const uint8_t* raw, uint32_t raw_len);
+/* One iteration of Inner::broker_receive_loop (tasks/broker/handler.rs:130-192), Direct and
+ * Broadcast only (to_user(s)_only = true, no prune); other kinds return 1 = "not routed here". */
+int pcdn_broker_receive(pcdn_engine* e, const char* identifier, const uint8_t* raw,
+                        uint32_t raw_len);
+/* Close the open batch and launch it.  *batch_id = 0 when the batch was empty. */
+int pcdn_flush(pcdn_engine* e, uint64_t* batch_id);
+/* Submit an explicit ordered batch (R9: batch order = per-connection delivery order). */
+int pcdn_submit(pcdn_engine* e, const pcdn_msg* msgs, uint32_t n, uint64_t* batch_id);
+/* Same, inputs already resident in HBM (no host copy, no host parse). */
+int pcdn_submit_device(pcdn_engine* e, const pcdn_device_batch* batch, uint64_t* batch_id);
+
+/* ---- data out: replaces Connection::send_message_raw + the per-connection writer task
+ *      (cdn-proto/src/connection/protocols/mod.rs:239-251,156-186,354-394) -------------------- */
+/* Wait for (block != 0) or test a batch; fills *out (span table is in pinned host memory). */
+int pcdn_poll(pcdn_engine* e, uint64_t batch_id, pcdn_batch_result* out, int block);
+/* Copy `len` ring bytes of a connection to host memory (what a socket writer would send). */
+int pcdn_read(pcdn_engine* e, pcdn_conn conn, uint32_t ring_off, uint32_t len, void* dst);
+/* The host has written every span of the batch: free its ring space and its slot.  This is the
+ * analogue of dropping the last `Bytes` clone (limiter/pool.rs:44-52).  In order, oldest first. */
+int pcdn_release_batch(pcdn_engine* e, uint64_t batch_id);
+
+/* ---- introspection (tests, metrics: cdn-proto/src/connection/metrics.rs:12-28) ------------- */
+int pcdn_get_stats(pcdn_engine* e, pcdn_stats* out);
+int pcdn_set_timing(pcdn_engine* e, int on);
+/* device pointer + geometry of the rings (zero-copy verification / GPUDirect hand-off) */
+int pcdn_ring_info(pcdn_engine* e, void** dev_base, uint64_t* ring_bytes, uint32_t* max_conns);
+/* number of connected users (Connections::num_users mod.rs:127) and brokers */
+int pcdn_num_users(pcdn_engine* e, uint32_t* users, uint32_t* brokers);
+/* Connections::get_interested_by_topic mod.rs:94-124 evaluated on the HOST MIRROR of the tables
+ * (state-logic tests without a GPU).  Writes up to cap conn ids; returns the count via *n.       */
+int pcdn_debug_interested(pcdn_engine* e, const uint16_t* topics, uint32_t n_topics,
+                          int to_users_only, pcdn_conn* out, uint32_t cap, uint32_t* n);
+/* Host-mirror route of a key, as the direct kernel would resolve it: 0 = none (drop),
+ * 1 = local user (*conn), 2 = remote broker (*conn = that broker's conn or PCDN_CONN_NONE).     */
+int pcdn_debug_route(pcdn_engine* e, const uint8_t* key, uint32_t key_len, int* kind,
+                     pcdn_conn* conn);
+/* Parse helper exported for tests: Message::deserialize restricted to the routed kinds.  Returns
+ * the kind (>=0) or PCDN_EPARSE.  topics_out (cap 256) / recipient span are filled when relevant. */
+int pcdn_parse_frame(const uint8_t* raw, uint32_t raw_len, uint16_t* topics_out,
+                     uint32_t* n_topics, uint32_t* field_off, uint32_t* field_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCDN_FANOUT_H */
