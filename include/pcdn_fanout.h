@@ -226,6 +226,9 @@ int pcdn_submit_device(pcdn_engine* e, const pcdn_device_batch* batch, uint64_t*
 
 /* ---- data out: replaces Connection::send_message_raw + the per-connection writer task
  *      (cdn-proto/src/connection/protocols/mod.rs:239-251,156-186,354-394) -------------------- */
+/* Oldest batch that was launched and not yet released (0 = none).  State calls and full batches
+ * launch the open batch implicitly, so a host drains with: while (next_batch) { poll; write; release }. */
+int pcdn_next_batch(pcdn_engine* e, uint64_t* batch_id);
 /* Wait for (block != 0) or test a batch; fills *out (span table is in pinned host memory). */
 int pcdn_poll(pcdn_engine* e, uint64_t batch_id, pcdn_batch_result* out, int block);
 /* Copy `len` ring bytes of a connection to host memory (what a socket writer would send). */

@@ -1,0 +1,426 @@
+"""push-cdn_b200 — B200-native fan-out engine for Push-CDN's cdn-broker hot path.
+
+This Python module is a thin ctypes binding over the C ABI (``include/pcdn_fanout.h``) of
+``libpcdn_fanout.so`` (CUDA, sm_100a).  It mirrors the names of the reference's broker API
+(`Connections::*`, `Inner::handle_broadcast_message`, `Inner::handle_direct_message`,
+`user_receive_loop` / `broker_receive_loop` — cdn-broker/src/{connections/mod.rs,
+tasks/broker/handler.rs, tasks/user/handler.rs}) so that tests read like the reference's own.
+
+There is no Python or CPU implementation of the data path here: if the shared library is missing or
+no CUDA device is present, constructing a routing ``Engine`` raises.
+(The directory name has a hyphen; import it through ``__graft_entry__.load_package()`` which
+registers it as ``push_cdn_b200``.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libpcdn_fanout.so")
+INCLUDE = os.path.join(_ROOT, "include")
+
+SOURCES = ["engine.cu", "kernels.cu", "host_state.cpp", "frame_parse.cpp"]
+HEADERS = ["kernels.cuh", "host_state.h", "frame_parse.h", "hash.h"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+KIND_DIRECT, KIND_BROADCAST, KIND_SUBSCRIBE, KIND_UNSUBSCRIBE = 3, 4, 5, 6
+TO_USERS_ONLY = 1
+RECORD_ALIGN = 32
+CONN_NONE = 0xFFFFFFFF
+
+ERRORS = {
+    -1: "PCDN_EINVAL", -2: "PCDN_ENOMEM", -3: "PCDN_ENODEV", -4: "PCDN_ECUDA", -5: "PCDN_ENOSPC",
+    -6: "PCDN_EKEYLEN", -7: "PCDN_EPARSE", -8: "PCDN_EPRUNE", -9: "PCDN_EKIND", -10: "PCDN_ENOENT",
+    -11: "PCDN_EAGAIN", -12: "PCDN_E2BIG",
+}
+
+
+class PcdnError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(INCLUDE, "pcdn_fanout.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into the in-tree shared library (nvcc cross-compiles
+    without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.exists(nvcc):
+        nvcc = "nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.check_call(cmd, cwd=CSRC)
+    return LIB_PATH
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("device", C.c_int32), ("max_conns", C.c_uint32), ("max_topics", C.c_uint32),
+        ("max_keys", C.c_uint32), ("max_key_len", C.c_uint32), ("ring_bytes_per_conn", C.c_uint64),
+        ("max_batch_msgs", C.c_uint32), ("max_batch_bcast", C.c_uint32), ("max_batch_bytes", C.c_uint64),
+        ("max_batch_deliveries", C.c_uint64), ("batch_slots", C.c_uint32), ("n_valid_topics", C.c_uint32),
+        ("hash_seed", C.c_uint64), ("stream", C.c_void_p), ("identity", C.c_char_p), ("pack_variant", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+
+class Msg(C.Structure):
+    _fields_ = [
+        ("kind", C.c_uint8), ("flags", C.c_uint8), ("n_topics", C.c_uint16), ("topics", C.POINTER(C.c_uint16)),
+        ("recipient", C.c_char_p), ("recipient_len", C.c_uint32), ("raw_len", C.c_uint32), ("raw", C.c_char_p),
+    ]
+
+
+class Span(C.Structure):
+    _fields_ = [("conn", C.c_uint32), ("ring_off", C.c_uint32), ("len", C.c_uint32), ("n_records", C.c_uint32)]
+
+
+class BatchResult(C.Structure):
+    _fields_ = [
+        ("batch_id", C.c_uint64), ("n_msgs", C.c_uint32), ("n_spans", C.c_uint32), ("spans", C.POINTER(Span)),
+        ("n_deliveries", C.c_uint64), ("bytes_out", C.c_uint64), ("n_overflow", C.c_uint32),
+        ("overflow_conns", C.POINTER(C.c_uint32)), ("n_direct_dropped", C.c_uint32), ("status", C.c_uint32),
+    ]
+
+
+class DeviceBatch(C.Structure):
+    _fields_ = [
+        ("n_msgs", C.c_uint32), ("n_bcast", C.c_uint32), ("arena", C.c_void_p), ("arena_bytes", C.c_uint64),
+        ("kind", C.c_void_p), ("flags", C.c_void_p), ("slot_off16", C.c_void_p), ("raw_len", C.c_void_p),
+        ("aux_off", C.c_void_p), ("aux_len", C.c_void_p), ("topics", C.c_void_p), ("n_topics_total", C.c_uint32),
+        ("bcast_index", C.c_void_p),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("batches", C.c_uint64), ("msgs", C.c_uint64), ("deliveries", C.c_uint64), ("bytes_out", C.c_uint64),
+        ("ms_match", C.c_double), ("ms_plan", C.c_double), ("ms_direct", C.c_double), ("ms_pack", C.c_double),
+        ("ms_total", C.c_double), ("timed_batches", C.c_uint64),
+    ]
+
+
+class UserSyncEntry(C.Structure):
+    _fields_ = [("key", C.c_char_p), ("key_len", C.c_uint32), ("version", C.c_uint64), ("owner", C.c_char_p)]
+
+
+# every symbol include/pcdn_fanout.h declares: name → (restype, argtypes)
+_vp, _u8p, _u16p, _u32, _u64, _ci, _cp = C.c_void_p, C.c_char_p, C.POINTER(C.c_uint16), C.c_uint32, C.c_uint64, C.c_int, C.c_char_p
+ABI = {
+    "pcdn_abi_version": (_u32, []),
+    "pcdn_config_default": (None, [C.POINTER(Config)]),
+    "pcdn_create": (_ci, [C.POINTER(Config), C.POINTER(_vp)]),
+    "pcdn_destroy": (None, [_vp]),
+    "pcdn_last_error": (_cp, []),
+    "pcdn_add_user": (_ci, [_vp, _u8p, _u32, _u16p, _u32, C.POINTER(_u32)]),
+    "pcdn_remove_user": (_ci, [_vp, _u8p, _u32]),
+    "pcdn_subscribe_user_to": (_ci, [_vp, _u8p, _u32, _u16p, _u32]),
+    "pcdn_unsubscribe_user_from": (_ci, [_vp, _u8p, _u32, _u16p, _u32]),
+    "pcdn_add_broker": (_ci, [_vp, _cp, C.POINTER(_u32)]),
+    "pcdn_remove_broker": (_ci, [_vp, _cp]),
+    "pcdn_subscribe_broker_to": (_ci, [_vp, _cp, _u16p, _u32]),
+    "pcdn_unsubscribe_broker_from": (_ci, [_vp, _cp, _u16p, _u32]),
+    "pcdn_apply_user_sync": (_ci, [_vp, _cp, C.POINTER(UserSyncEntry), _u32]),
+    "pcdn_add_users_bulk": (_ci, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
+    "pcdn_handle_broadcast_message": (_ci, [_vp, _u16p, _u32, _u8p, _u32, _ci]),
+    "pcdn_handle_direct_message": (_ci, [_vp, _u8p, _u32, _u8p, _u32, _ci]),
+    "pcdn_user_receive": (_ci, [_vp, _u8p, _u32, _u8p, _u32]),
+    "pcdn_broker_receive": (_ci, [_vp, _cp, _u8p, _u32]),
+    "pcdn_flush": (_ci, [_vp, C.POINTER(_u64)]),
+    "pcdn_submit": (_ci, [_vp, C.POINTER(Msg), _u32, C.POINTER(_u64)]),
+    "pcdn_submit_device": (_ci, [_vp, C.POINTER(DeviceBatch), C.POINTER(_u64)]),
+    "pcdn_next_batch": (_ci, [_vp, C.POINTER(_u64)]),
+    "pcdn_poll": (_ci, [_vp, _u64, C.POINTER(BatchResult), _ci]),
+    "pcdn_read": (_ci, [_vp, _u32, _u32, _u32, _vp]),
+    "pcdn_release_batch": (_ci, [_vp, _u64]),
+    "pcdn_get_stats": (_ci, [_vp, C.POINTER(Stats)]),
+    "pcdn_set_timing": (_ci, [_vp, _ci]),
+    "pcdn_ring_info": (_ci, [_vp, C.POINTER(_vp), C.POINTER(_u64), C.POINTER(_u32)]),
+    "pcdn_num_users": (_ci, [_vp, C.POINTER(_u32), C.POINTER(_u32)]),
+    "pcdn_debug_interested": (_ci, [_vp, _u16p, _u32, _ci, C.POINTER(_u32), _u32, C.POINTER(_u32)]),
+    "pcdn_debug_route": (_ci, [_vp, _u8p, _u32, C.POINTER(_ci), C.POINTER(_u32)]),
+    "pcdn_parse_frame": (_ci, [_u8p, _u32, _u16p, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA extension.  Raises if it is missing — there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(the product has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in ABI.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        assert L.pcdn_abi_version() == 1
+        _lib = L
+    return _lib
+
+
+def _t16(topics: Iterable[int]):
+    t = [int(x) for x in topics]
+    return (C.c_uint16 * max(1, len(t)))(*t), len(t)
+
+
+def parse_frame(raw: bytes):
+    """pcdn_parse_frame → (kind, topics list, (field_off, field_len)) or raises PcdnError(EPARSE)."""
+    L = lib()
+    t = (C.c_uint16 * 256)()
+    n, off, ln = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+    k = L.pcdn_parse_frame(raw, len(raw), t, C.byref(n), C.byref(off), C.byref(ln))
+    if k < 0:
+        raise PcdnError(k, L.pcdn_last_error().decode())
+    return k, [t[i] for i in range(n.value)], (off.value, ln.value)
+
+
+class Engine:
+    """One fan-out engine on one CUDA device (or a host-only state mirror with ``device=-1``)."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None, identity: str = "/", **kw):
+        self.L = lib()
+        cfg = Config()
+        self.L.pcdn_config_default(C.byref(cfg))
+        cfg.device = device
+        self._identity = identity.encode()
+        cfg.identity = self._identity
+        if stream is not None:
+            cfg.stream = stream
+        for k, v in kw.items():
+            if not hasattr(cfg, k):
+                raise TypeError(f"unknown config field {k}")
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        h = C.c_void_p()
+        self._chk(self.L.pcdn_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pcdn_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc: int) -> int:
+        if rc < 0:
+            raise PcdnError(rc, self.L.pcdn_last_error().decode())
+        return rc
+
+    # ---- state: Connections::* --------------------------------------------------------------
+    def add_user(self, key: bytes, topics: Iterable[int] = ()) -> int:
+        t, n = _t16(topics)
+        c = C.c_uint32()
+        self._chk(self.L.pcdn_add_user(self.h, key, len(key), t, n, C.byref(c)))
+        return c.value
+
+    def add_users_bulk(self, keys, key_len: int, topics=None, topic_offsets=None):
+        """keys: numpy uint8 [n, stride] (C-contiguous); topics/topic_offsets: CSR numpy arrays."""
+        import numpy as np
+
+        n, stride = keys.shape
+        out = np.empty(n, dtype=np.uint32)
+        tp = topics.ctypes.data if topics is not None else None
+        op = topic_offsets.ctypes.data if topic_offsets is not None else None
+        self._chk(self.L.pcdn_add_users_bulk(self.h, keys.ctypes.data, key_len, stride, n, tp, op, out.ctypes.data))
+        return out
+
+    def remove_user(self, key: bytes) -> None:
+        self._chk(self.L.pcdn_remove_user(self.h, key, len(key)))
+
+    def subscribe_user_to(self, key: bytes, topics: Iterable[int]) -> None:
+        t, n = _t16(topics)
+        self._chk(self.L.pcdn_subscribe_user_to(self.h, key, len(key), t, n))
+
+    def unsubscribe_user_from(self, key: bytes, topics: Iterable[int]) -> None:
+        t, n = _t16(topics)
+        self._chk(self.L.pcdn_unsubscribe_user_from(self.h, key, len(key), t, n))
+
+    def add_broker(self, ident: str) -> int:
+        c = C.c_uint32()
+        self._chk(self.L.pcdn_add_broker(self.h, ident.encode(), C.byref(c)))
+        return c.value
+
+    def remove_broker(self, ident: str) -> None:
+        self._chk(self.L.pcdn_remove_broker(self.h, ident.encode()))
+
+    def subscribe_broker_to(self, ident: str, topics: Iterable[int]) -> None:
+        t, n = _t16(topics)
+        self._chk(self.L.pcdn_subscribe_broker_to(self.h, ident.encode(), t, n))
+
+    def unsubscribe_broker_from(self, ident: str, topics: Iterable[int]) -> None:
+        t, n = _t16(topics)
+        self._chk(self.L.pcdn_unsubscribe_broker_from(self.h, ident.encode(), t, n))
+
+    def apply_user_sync(self, remote_identity: str, entries) -> None:
+        ents = list(entries)
+        arr = (UserSyncEntry * max(1, len(ents)))()
+        keep = []
+        for i, (key, version, owner) in enumerate(ents):
+            ob = None if owner is None else owner.encode()
+            keep.append((key, ob))
+            arr[i] = UserSyncEntry(key, len(key), version, ob)
+        self._chk(self.L.pcdn_apply_user_sync(self.h, remote_identity.encode(), arr, len(ents)))
+
+    # ---- data in ----------------------------------------------------------------------------
+    def handle_broadcast_message(self, topics: Iterable[int], raw: bytes, to_users_only: bool = False) -> None:
+        t, n = _t16(topics)
+        self._chk(self.L.pcdn_handle_broadcast_message(self.h, t, n, raw, len(raw), int(to_users_only)))
+
+    def handle_direct_message(self, recipient: bytes, raw: bytes, to_user_only: bool = False) -> None:
+        self._chk(self.L.pcdn_handle_direct_message(self.h, recipient, len(recipient), raw, len(raw), int(to_user_only)))
+
+    def user_receive(self, sender_key: bytes, raw: bytes) -> int:
+        """One iteration of user_receive_loop; negative = the loop would have ended (disconnect)."""
+        return self.L.pcdn_user_receive(self.h, sender_key, len(sender_key), raw, len(raw))
+
+    def broker_receive(self, ident: str, raw: bytes) -> int:
+        return self.L.pcdn_broker_receive(self.h, ident.encode(), raw, len(raw))
+
+    def flush(self) -> int:
+        b = C.c_uint64(0)
+        self._chk(self.L.pcdn_flush(self.h, C.byref(b)))
+        return b.value
+
+    def submit(self, msgs: Sequence[Tuple]) -> int:
+        """msgs: ('b', topics, raw, to_users_only) | ('d', recipient, raw, to_user_only)"""
+        arr = (Msg * max(1, len(msgs)))()
+        keep = []
+        for i, m in enumerate(msgs):
+            if m[0] == "b":
+                t, n = _t16(m[1])
+                keep.append(t)
+                arr[i] = Msg(KIND_BROADCAST, TO_USERS_ONLY if m[3] else 0, n, t, None, 0, len(m[2]), m[2])
+            else:
+                arr[i] = Msg(KIND_DIRECT, TO_USERS_ONLY if m[3] else 0, 0, None, m[1], len(m[1]), len(m[2]), m[2])
+        b = C.c_uint64(0)
+        self._chk(self.L.pcdn_submit(self.h, arr, len(msgs), C.byref(b)))
+        return b.value
+
+    def submit_device(self, db: DeviceBatch) -> int:
+        b = C.c_uint64(0)
+        self._chk(self.L.pcdn_submit_device(self.h, C.byref(db), C.byref(b)))
+        return b.value
+
+    # ---- data out ---------------------------------------------------------------------------
+    def next_batch(self) -> int:
+        b = C.c_uint64(0)
+        self._chk(self.L.pcdn_next_batch(self.h, C.byref(b)))
+        return b.value
+
+    def poll(self, batch_id: int, block: bool = True) -> Optional[BatchResult]:
+        r = BatchResult()
+        rc = self._chk(self.L.pcdn_poll(self.h, batch_id, C.byref(r), int(block)))
+        return None if rc == 1 else r
+
+    def read(self, conn: int, ring_off: int, length: int) -> bytes:
+        buf = C.create_string_buffer(max(1, length))
+        self._chk(self.L.pcdn_read(self.h, conn, ring_off, length, C.cast(buf, C.c_void_p)))
+        return buf.raw[:length]
+
+    def release_batch(self, batch_id: int) -> None:
+        self._chk(self.L.pcdn_release_batch(self.h, batch_id))
+
+    def spans(self, res: BatchResult) -> List[Tuple[int, int, int, int]]:
+        return [(res.spans[i].conn, res.spans[i].ring_off, res.spans[i].len, res.spans[i].n_records)
+                for i in range(res.n_spans)]
+
+    def collect_frames(self, res: BatchResult) -> Dict[int, List[bytes]]:
+        """What the per-connection writer tasks would put on the wire for this batch: walk every
+        span record by record (BE length prefix, 32-byte record stride) and return the raw frames
+        per connection in ring order.  A wrapped connection has two spans: the one that does not
+        start at offset 0 comes first."""
+        per: Dict[int, List[Tuple[int, int, int]]] = {}
+        for conn, off, ln, nrec in self.spans(res):
+            per.setdefault(conn, []).append((off, ln, nrec))
+        out: Dict[int, List[bytes]] = {}
+        for conn, pieces in per.items():
+            pieces.sort(key=lambda p: (p[0] == 0 and len(pieces) > 1, p[0]))
+            frames = []
+            for off, ln, nrec in pieces:
+                data = self.read(conn, off, ln)
+                p = 0
+                for _ in range(nrec):
+                    L = int.from_bytes(data[p:p + 4], "big")
+                    frames.append(data[p + 4:p + 4 + L])
+                    p += (4 + L + RECORD_ALIGN - 1) // RECORD_ALIGN * RECORD_ALIGN
+                assert p == ln, (conn, off, ln, nrec, p)
+            out[conn] = frames
+        return out
+
+    def drain(self) -> Dict[int, List[bytes]]:
+        """flush, then poll + collect + release every outstanding batch (oldest first)."""
+        self.flush()
+        out: Dict[int, List[bytes]] = {}
+        while True:
+            b = self.next_batch()
+            if not b:
+                return out
+            res = self.poll(b)
+            if res.status:
+                self.release_batch(b)
+                raise PcdnError(-int(res.status), "batch rejected on the device")
+            for conn, fr in self.collect_frames(res).items():
+                out.setdefault(conn, []).extend(fr)
+            self.last_result = res
+            self.release_batch(b)
+
+    # ---- introspection ----------------------------------------------------------------------
+    def stats(self) -> Stats:
+        s = Stats()
+        self._chk(self.L.pcdn_get_stats(self.h, C.byref(s)))
+        return s
+
+    def set_timing(self, on: bool) -> None:
+        self._chk(self.L.pcdn_set_timing(self.h, int(on)))
+
+    def ring_info(self) -> Tuple[int, int, int]:
+        p, rb, mc = C.c_void_p(), C.c_uint64(), C.c_uint32()
+        self._chk(self.L.pcdn_ring_info(self.h, C.byref(p), C.byref(rb), C.byref(mc)))
+        return (p.value or 0), rb.value, mc.value
+
+    def num_users(self) -> Tuple[int, int]:
+        u, b = C.c_uint32(), C.c_uint32()
+        self._chk(self.L.pcdn_num_users(self.h, C.byref(u), C.byref(b)))
+        return u.value, b.value
+
+    def debug_interested(self, topics: Iterable[int], to_users_only: bool = False) -> List[int]:
+        t, n = _t16(topics)
+        cap = self.cfg.max_conns
+        out = (C.c_uint32 * cap)()
+        k = C.c_uint32()
+        self._chk(self.L.pcdn_debug_interested(self.h, t, n, int(to_users_only), out, cap, C.byref(k)))
+        return sorted(out[i] for i in range(min(k.value, cap)))
+
+    def debug_route(self, key: bytes) -> Tuple[int, int]:
+        kind, conn = C.c_int(), C.c_uint32()
+        self._chk(self.L.pcdn_debug_route(self.h, key, len(key), C.byref(kind), C.byref(conn)))
+        return kind.value, (-1 if conn.value == CONN_NONE else conn.value)

@@ -1,0 +1,912 @@
+// engine.cu — host runtime of the fan-out engine and the C ABI (include/pcdn_fanout.h).
+//
+// One engine = one CUDA device, one stream, the routing tables (host mirror in host_state.*, device
+// copy in DevState), the per-connection output rings and a small pool of batch slots.  A batch is
+// staged in pinned memory while it is open, copied to the device on flush and routed by the kernel
+// pipeline of kernels.cuh; results (span table, counters) come back through pinned memory.
+// There is no CPU data path: without a device every routing call fails with PCDN_ENODEV.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "frame_parse.h"
+#include "host_state.h"
+#include "kernels.cuh"
+#include "pcdn_fanout.h"
+
+using namespace pcdn;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return fail(PCDN_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));             \
+  } while (0)
+
+template <class T>
+int dev_alloc(T** p, size_t n) {
+  *p = nullptr;
+  if (!n) n = 1;
+  cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+  if (e != cudaSuccess) return fail(PCDN_ENOMEM, std::string("cudaMalloc ") + std::to_string(n * sizeof(T)) + " B: " + cudaGetErrorString(e));
+  return 0;
+}
+template <class T>
+int pin_alloc(T** p, size_t n) {
+  *p = nullptr;
+  if (!n) n = 1;
+  cudaError_t e = cudaMallocHost((void**)p, n * sizeof(T));
+  if (e != cudaSuccess) return fail(PCDN_ENOMEM, std::string("cudaMallocHost ") + std::to_string(n * sizeof(T)) + " B: " + cudaGetErrorString(e));
+  return 0;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+enum SlotState { SLOT_FREE = 0, SLOT_OPEN = 1, SLOT_INFLIGHT = 2 };
+
+struct Slot {
+  int state = SLOT_FREE;
+  uint64_t batch_id = 0;
+  bool polled = false, device_input = false;
+  // host staging while open
+  uint8_t* h_arena = nullptr;   // pinned
+  size_t arena_used = 0;
+  std::vector<uint8_t> kind, flags;
+  std::vector<uint32_t> slot_off16, raw_len, aux_off, aux_len, bcast_index;
+  std::vector<uint16_t> topics;
+  uint32_t n_direct = 0;
+  uint8_t* h_desc = nullptr;    // pinned descriptor block
+  // device
+  uint8_t* d_arena = nullptr;
+  uint8_t* d_desc = nullptr;
+  Work w{};
+  BatchIn in{};
+  // results
+  BatchStats* h_stats = nullptr;  // pinned
+  Span* h_spans = nullptr;        // pinned
+  uint32_t* h_overflow = nullptr; // pinned
+  cudaEvent_t ev_done = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool timed = false;
+};
+
+}  // namespace
+
+struct pcdn_engine {
+  std::mutex mu;
+  pcdn_config cfg{};
+  std::string identity;
+  Geometry geo{};
+  std::unique_ptr<HostTables> tables;
+  std::unique_ptr<Connections> conns;
+  bool has_device = false;
+  int n_sms = 148;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  bool own_stream = false;
+  DevState dev{};
+  std::vector<Slot> slots;
+  int open_slot = -1;
+  uint64_t next_batch_id = 1;
+  std::vector<uint64_t> inflight;  // submit order
+  size_t desc_cap = 0, topics_cap = 0;
+  // journal device buffers
+  Upd32* j_u32 = nullptr; size_t j_u32_cap = 0;
+  UpdSlot* j_slot = nullptr; size_t j_slot_cap = 0;
+  uint32_t* j_kslot = nullptr; uint8_t* j_kbytes = nullptr; size_t j_key_cap = 0;
+  std::vector<Upd32> h_u32; std::vector<UpdSlot> h_slot; std::vector<uint32_t> h_kslot; std::vector<uint8_t> h_kbytes;
+  bool timing = false;
+  pcdn_stats stats{};
+  std::vector<void*> dev_allocs, pin_allocs;
+};
+
+namespace {
+
+int grow(pcdn_engine* e, void** p, size_t* cap, size_t need, size_t elem) {
+  if (need <= *cap) return 0;
+  size_t ncap = std::max(need, *cap * 2 + 1024);
+  if (*p) { cudaStreamSynchronize(e->stream); cudaFree(*p); *p = nullptr; }
+  cudaError_t err = cudaMalloc(p, ncap * elem);
+  if (err != cudaSuccess) { *cap = 0; return fail(PCDN_ENOMEM, std::string("journal cudaMalloc: ") + cudaGetErrorString(err)); }
+  *cap = ncap;
+  return 0;
+}
+
+// Upload changed table words/slots/keys and apply them on the engine stream (K4).  Stream order
+// gives R12: every earlier batch sees the old tables, every later batch the new ones.
+int flush_journal(pcdn_engine* e) {
+  HostTables& t = *e->tables;
+  if (!e->has_device) { t.clear_dirty(); return 0; }
+  const Geometry& g = e->geo;
+  bool any = !t.dirty_sub.empty() || !t.dirty_brk.empty() || !t.dirty_owner.empty() || !t.dirty_slots.empty() ||
+             !t.dirty_keys.empty();
+  if (!any) return 0;
+  cudaStream_t st = e->stream;
+  // keys first (slots reference them)
+  const bool full_keys = t.dirty_keys.size() > (size_t)g.max_keys / 16 + 64;
+  if (full_keys) CUDA_TRY(cudaMemcpyAsync(e->dev.keys, t.keys.data(), t.keys.size(), cudaMemcpyHostToDevice, st));
+  e->h_u32.clear(); e->h_slot.clear(); e->h_kslot.clear(); e->h_kbytes.clear();
+  bool full_sub = t.dirty_sub.size() > t.sub.size() / 16 + 64;
+  if (full_sub) CUDA_TRY(cudaMemcpyAsync(e->dev.sub, t.sub.data(), t.sub.size() * 4, cudaMemcpyHostToDevice, st));
+  else for (uint32_t i : t.dirty_sub) e->h_u32.push_back(Upd32{0, i, t.sub[i]});
+  for (uint32_t i : t.dirty_brk) e->h_u32.push_back(Upd32{1, i, t.brk[i]});
+  for (uint32_t i : t.dirty_owner) e->h_u32.push_back(Upd32{2, i, t.owner_conn[i]});
+  bool full_slots = t.dirty_slots.size() > t.cuckoo.size() / 16 + 64;
+  if (full_slots) CUDA_TRY(cudaMemcpyAsync(e->dev.cuckoo, t.cuckoo.data(), t.cuckoo.size() * sizeof(CuckooEntry), cudaMemcpyHostToDevice, st));
+  else for (uint32_t i : t.dirty_slots) e->h_slot.push_back(UpdSlot{i, t.cuckoo[i]});
+  if (!full_keys) for (uint32_t k : t.dirty_keys) {
+    e->h_kslot.push_back(k);
+    size_t at = e->h_kbytes.size();
+    e->h_kbytes.resize(at + g.key_stride);
+    std::memcpy(&e->h_kbytes[at], &t.keys[(size_t)k * g.key_stride], g.key_stride);
+  }
+  int rc;
+  if ((rc = grow(e, (void**)&e->j_u32, &e->j_u32_cap, e->h_u32.size(), sizeof(Upd32)))) return rc;
+  if ((rc = grow(e, (void**)&e->j_slot, &e->j_slot_cap, e->h_slot.size(), sizeof(UpdSlot)))) return rc;
+  if (e->h_kslot.size() > e->j_key_cap) {
+    size_t ncap = std::max(e->h_kslot.size(), e->j_key_cap * 2 + 256);
+    cudaStreamSynchronize(st);
+    if (e->j_kslot) cudaFree(e->j_kslot);
+    if (e->j_kbytes) cudaFree(e->j_kbytes);
+    e->j_kslot = nullptr; e->j_kbytes = nullptr; e->j_key_cap = 0;
+    CUDA_TRY(cudaMalloc((void**)&e->j_kslot, ncap * 4));
+    CUDA_TRY(cudaMalloc((void**)&e->j_kbytes, ncap * g.key_stride));
+    e->j_key_cap = ncap;
+  }
+  if (!e->h_u32.empty()) CUDA_TRY(cudaMemcpyAsync(e->j_u32, e->h_u32.data(), e->h_u32.size() * sizeof(Upd32), cudaMemcpyHostToDevice, st));
+  if (!e->h_slot.empty()) CUDA_TRY(cudaMemcpyAsync(e->j_slot, e->h_slot.data(), e->h_slot.size() * sizeof(UpdSlot), cudaMemcpyHostToDevice, st));
+  if (!e->h_kslot.empty()) {
+    CUDA_TRY(cudaMemcpyAsync(e->j_kslot, e->h_kslot.data(), e->h_kslot.size() * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->j_kbytes, e->h_kbytes.data(), e->h_kbytes.size(), cudaMemcpyHostToDevice, st));
+  }
+  launch_apply_updates(e->dev, e->j_u32, (uint32_t)e->h_u32.size(), e->j_slot, (uint32_t)e->h_slot.size(), e->j_kslot,
+                       e->j_kbytes, (uint32_t)e->h_kslot.size(), st);
+  CUDA_TRY(cudaGetLastError());
+  // pageable sources were consumed by the async copies (staged) — but the journal vectors are
+  // reused only after this point by the next flush, which is fine for staged copies.
+  CUDA_TRY(cudaStreamSynchronize(st));  // control-plane rate; keeps host vectors' lifetime trivial
+  t.clear_dirty();
+  return 0;
+}
+
+void slot_reset_open(Slot& s) {
+  s.arena_used = 0; s.n_direct = 0;
+  s.kind.clear(); s.flags.clear(); s.slot_off16.clear(); s.raw_len.clear(); s.aux_off.clear(); s.aux_len.clear();
+  s.bcast_index.clear(); s.topics.clear();
+  s.polled = false; s.device_input = false; s.timed = false;
+}
+
+int acquire_open_slot(pcdn_engine* e) {
+  if (e->open_slot >= 0) return 0;
+  for (size_t i = 0; i < e->slots.size(); i++)
+    if (e->slots[i].state == SLOT_FREE) {
+      e->open_slot = (int)i;
+      e->slots[i].state = SLOT_OPEN;
+      slot_reset_open(e->slots[i]);
+      return 0;
+    }
+  return fail(PCDN_EAGAIN, "all batch slots are in flight: poll and release a batch first");
+}
+
+// run the kernel pipeline for slot `s` whose BatchIn is ready on the device
+int launch_pipeline(pcdn_engine* e, Slot& s, uint32_t n_direct) {
+  cudaStream_t st = e->stream;
+  const bool has_direct = n_direct > 0;
+  s.timed = e->timing;
+  if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[0], st));
+  launch_batch_begin(e->dev, s.w, s.in, has_direct, st);
+  if (has_direct) launch_direct(e->dev, s.w, s.in, st);
+  if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[1], st));
+  launch_match(e->dev, s.w, s.in, st);
+  if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[2], st));
+  launch_plan(e->dev, s.w, s.in, st);
+  launch_offsets(e->dev, s.w, s.in, has_direct, st);
+  if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[3], st));
+  launch_pack(e->dev, s.w, s.in, e->cfg.pack_variant, e->n_sms, st);
+  if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[4], st));
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(s.h_stats, s.w.stats, sizeof(BatchStats), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(s.ev_done, st));
+  s.state = SLOT_INFLIGHT;
+  s.batch_id = e->next_batch_id++;
+  s.polled = false;
+  e->inflight.push_back(s.batch_id);
+  return 0;
+}
+
+// close the open batch: upload staging, launch
+int flush_open(pcdn_engine* e, uint64_t* batch_id) {
+  if (batch_id) *batch_id = 0;
+  if (e->open_slot < 0) return 0;
+  Slot& s = e->slots[e->open_slot];
+  const uint32_t n = (uint32_t)s.kind.size();
+  if (n == 0) { s.state = SLOT_FREE; e->open_slot = -1; return 0; }
+  if (!e->has_device) return fail(PCDN_ENODEV, "host-only engine cannot route messages");
+  int rc = flush_journal(e);
+  if (rc) return rc;
+  cudaStream_t st = e->stream;
+  // descriptor block layout (offsets 16-byte aligned)
+  size_t o_kind = 0, o_flags = align_up(o_kind + n, 16), o_slot = align_up(o_flags + n, 16);
+  size_t o_len = o_slot + (size_t)n * 4, o_aoff = o_len + (size_t)n * 4, o_alen = o_aoff + (size_t)n * 4;
+  size_t o_bidx = o_alen + (size_t)n * 4, o_top = align_up(o_bidx + s.bcast_index.size() * 4, 16);
+  size_t total = align_up(o_top + s.topics.size() * 2, 16);
+  if (total > e->desc_cap) return fail(PCDN_ENOSPC, "descriptor block overflow");
+  std::memcpy(s.h_desc + o_kind, s.kind.data(), n);
+  std::memcpy(s.h_desc + o_flags, s.flags.data(), n);
+  std::memcpy(s.h_desc + o_slot, s.slot_off16.data(), (size_t)n * 4);
+  std::memcpy(s.h_desc + o_len, s.raw_len.data(), (size_t)n * 4);
+  std::memcpy(s.h_desc + o_aoff, s.aux_off.data(), (size_t)n * 4);
+  std::memcpy(s.h_desc + o_alen, s.aux_len.data(), (size_t)n * 4);
+  if (!s.bcast_index.empty()) std::memcpy(s.h_desc + o_bidx, s.bcast_index.data(), s.bcast_index.size() * 4);
+  if (!s.topics.empty()) std::memcpy(s.h_desc + o_top, s.topics.data(), s.topics.size() * 2);
+  CUDA_TRY(cudaMemcpyAsync(s.d_arena, s.h_arena, align_up(s.arena_used, 16), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(s.d_desc, s.h_desc, total, cudaMemcpyHostToDevice, st));
+  s.in.n_msgs = n;
+  s.in.n_bcast = (uint32_t)s.bcast_index.size();
+  s.in.arena = s.d_arena;
+  s.in.kind = s.d_desc + o_kind;
+  s.in.flags = s.d_desc + o_flags;
+  s.in.slot_off16 = (const uint32_t*)(s.d_desc + o_slot);
+  s.in.raw_len = (const uint32_t*)(s.d_desc + o_len);
+  s.in.aux_off = (const uint32_t*)(s.d_desc + o_aoff);
+  s.in.aux_len = (const uint32_t*)(s.d_desc + o_alen);
+  s.in.bcast_index = (const uint32_t*)(s.d_desc + o_bidx);
+  s.in.topics = (const uint16_t*)(s.d_desc + o_top);
+  s.device_input = false;
+  rc = launch_pipeline(e, s, s.n_direct);
+  if (rc) return rc;
+  if (batch_id) *batch_id = s.batch_id;
+  e->open_slot = -1;
+  e->stats.batches++;
+  e->stats.msgs += n;
+  return 0;
+}
+
+// R12: a table mutation must not be visible to messages already handed to the engine
+int before_state_change(pcdn_engine* e) {
+  if (e->open_slot >= 0 && !e->slots[e->open_slot].kind.empty()) return flush_open(e, nullptr);
+  return 0;
+}
+
+// append one message to the open batch (flushing a full batch first)
+int append_msg(pcdn_engine* e, uint8_t kind, uint8_t flags, const uint16_t* topics, uint32_t n_topics,
+               const uint8_t* recipient, uint32_t recipient_len, const uint8_t* raw, uint32_t raw_len) {
+  if (!e->has_device) return fail(PCDN_ENODEV, "host-only engine cannot route messages");
+  if (raw_len > 0x1FFFFFFFu) return fail(PCDN_EINVAL, "message larger than MAX_MESSAGE_SIZE (cdn-proto/src/lib.rs:25)");
+  if (kind != PCDN_KIND_BROADCAST && kind != PCDN_KIND_DIRECT) return fail(PCDN_EINVAL, "kind must be broadcast or direct");
+  const pcdn_config& c = e->cfg;
+  const size_t slot_bytes = align_up(4 + (size_t)raw_len, 16);
+  size_t need = slot_bytes + (kind == PCDN_KIND_DIRECT ? align_up(recipient_len, 16) : 0);
+  if (need + 64 > c.max_batch_bytes) return fail(PCDN_ENOSPC, "message does not fit max_batch_bytes");
+  if (kind == PCDN_KIND_DIRECT && recipient_len > c.max_key_len) {
+    // longer than any key in the table: cannot match (bytewise identity, R8) → dropped silently,
+    // but batch order bookkeeping still wants the message; route it as "no recipient"
+    recipient_len = 0;
+  }
+  for (int attempt = 0; attempt < 2; attempt++) {
+    int rc = acquire_open_slot(e);
+    if (rc) return rc;
+    Slot& s = e->slots[e->open_slot];
+    bool full = s.kind.size() >= c.max_batch_msgs || s.arena_used + need + 64 > c.max_batch_bytes ||
+                (kind == PCDN_KIND_BROADCAST && s.bcast_index.size() >= c.max_batch_bcast) ||
+                s.topics.size() + n_topics > e->topics_cap;
+    if (!full) break;
+    if (attempt == 1) return fail(PCDN_ENOSPC, "message does not fit an empty batch");
+    if ((rc = flush_open(e, nullptr))) return rc;
+  }
+  Slot& s = e->slots[e->open_slot];
+  const uint32_t m = (uint32_t)s.kind.size();
+  const size_t off = s.arena_used;  // 16-byte aligned
+  uint8_t* dst = s.h_arena + off;
+  std::memset(dst, 0, 4);
+  if (raw_len) std::memcpy(dst + 4, raw, raw_len);
+  std::memset(dst + 4 + raw_len, 0, slot_bytes - 4 - raw_len);
+  s.arena_used += slot_bytes;
+  s.kind.push_back(kind);
+  s.flags.push_back(flags);
+  s.slot_off16.push_back((uint32_t)(off / 16));
+  s.raw_len.push_back(raw_len);
+  if (kind == PCDN_KIND_BROADCAST) {
+    s.aux_off.push_back((uint32_t)s.topics.size());
+    s.aux_len.push_back(n_topics);
+    for (uint32_t i = 0; i < n_topics; i++) s.topics.push_back(topics[i]);
+    s.bcast_index.push_back(m);
+  } else {
+    // recipient key: read it in place when it lies inside the frame at a 4-byte aligned offset
+    size_t koff;
+    if (recipient_len && recipient >= raw && recipient + recipient_len <= raw + raw_len &&
+        ((off + 4 + (size_t)(recipient - raw)) & 3) == 0) {
+      koff = off + 4 + (size_t)(recipient - raw);
+    } else {
+      koff = s.arena_used;
+      size_t kb = align_up(recipient_len, 16);
+      if (recipient_len) std::memcpy(s.h_arena + koff, recipient, recipient_len);
+      std::memset(s.h_arena + koff + recipient_len, 0, kb - recipient_len);
+      s.arena_used += kb;
+    }
+    s.aux_off.push_back((uint32_t)koff);
+    s.aux_len.push_back(recipient_len);
+    s.n_direct++;
+  }
+  return 0;
+}
+
+Slot* find_slot(pcdn_engine* e, uint64_t id) {
+  for (auto& s : e->slots)
+    if (s.state == SLOT_INFLIGHT && s.batch_id == id) return &s;
+  return nullptr;
+}
+
+void destroy_engine(pcdn_engine* e) {
+  if (e->has_device) {
+    cudaSetDevice(e->cfg.device);
+    cudaStreamSynchronize(e->stream);
+    for (auto& s : e->slots) {
+      if (s.ev_done) cudaEventDestroy(s.ev_done);
+      for (auto& ev : s.ev) if (ev) cudaEventDestroy(ev);
+    }
+    for (void* p : e->dev_allocs) cudaFree(p);
+    for (void* p : e->pin_allocs) cudaFreeHost(p);
+    if (e->j_u32) cudaFree(e->j_u32);
+    if (e->j_slot) cudaFree(e->j_slot);
+    if (e->j_kslot) cudaFree(e->j_kslot);
+    if (e->j_kbytes) cudaFree(e->j_kbytes);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+  }
+  delete e;
+}
+
+#define DEV_ALLOC(ptr, n)                                 \
+  do {                                                    \
+    int _rc = dev_alloc(&(ptr), (n));                     \
+    if (_rc) return _rc;                                  \
+    e->dev_allocs.push_back((void*)(ptr));                \
+  } while (0)
+#define PIN_ALLOC(ptr, n)                                 \
+  do {                                                    \
+    int _rc = pin_alloc(&(ptr), (n));                     \
+    if (_rc) return _rc;                                  \
+    e->pin_allocs.push_back((void*)(ptr));                \
+  } while (0)
+
+int init_device(pcdn_engine* e) {
+  const pcdn_config& c = e->cfg;
+  const Geometry& g = e->geo;
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if (err != cudaSuccess || ndev == 0)
+    return fail(PCDN_ENODEV, std::string("no CUDA device: ") + cudaGetErrorString(err));
+  if (c.device >= ndev) return fail(PCDN_ENODEV, "device ordinal out of range");
+  CUDA_TRY(cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, c.device));
+  e->n_sms = prop.multiProcessorCount;
+  if (c.stream) { e->stream = (cudaStream_t)c.stream; e->own_stream = false; }
+  else { CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true; }
+  CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  e->has_device = true;
+
+  DevState& d = e->dev;
+  d.N = g.N; d.W = g.W; d.T = g.T; d.nblk = g.W / kBlockWords;
+  d.bucket_mask = g.bucket_mask; d.key_stride = g.key_stride; d.seed = g.seed;
+  d.ring_bytes = c.ring_bytes_per_conn; d.ring_units = (uint32_t)(c.ring_bytes_per_conn / kUnit);
+  DEV_ALLOC(d.sub, (size_t)g.T * g.W);
+  DEV_ALLOC(d.brk, g.W);
+  DEV_ALLOC(d.owner_conn, g.max_owners);
+  DEV_ALLOC(d.cuckoo, (size_t)g.nbuckets * 4);
+  DEV_ALLOC(d.keys, (size_t)g.max_keys * g.key_stride);
+  DEV_ALLOC(d.ptail, g.N);
+  DEV_ALLOC(d.used, g.N);
+  DEV_ALLOC(d.rings, (size_t)g.max_conns * c.ring_bytes_per_conn);
+  CUDA_TRY(cudaMemsetAsync(d.sub, 0, (size_t)g.T * g.W * 4, e->stream));
+  CUDA_TRY(cudaMemsetAsync(d.brk, 0, (size_t)g.W * 4, e->stream));
+  CUDA_TRY(cudaMemsetAsync(d.owner_conn, 0xFF, (size_t)g.max_owners * 4, e->stream));
+  CUDA_TRY(cudaMemsetAsync(d.cuckoo, 0, (size_t)g.nbuckets * 4 * sizeof(CuckooEntry), e->stream));
+  CUDA_TRY(cudaMemsetAsync(d.keys, 0, (size_t)g.max_keys * g.key_stride, e->stream));
+  CUDA_TRY(cudaMemsetAsync(d.ptail, 0, (size_t)g.N * 4, e->stream));
+  CUDA_TRY(cudaMemsetAsync(d.used, 0, (size_t)g.N * 4, e->stream));
+
+  const uint32_t M = c.max_batch_msgs, MB = c.max_batch_bcast;
+  e->topics_cap = (size_t)M * 4 + 4096;
+  e->desc_cap = align_up((size_t)M * 2 + 64, 16) + (size_t)M * 20 + 64 + e->topics_cap * 2 + 64;
+  const size_t cap_fat = (size_t)c.max_batch_deliveries;
+  const size_t cap_thin = std::min<size_t>(c.max_batch_deliveries, (size_t)M * (kFatMin - 1));
+  const size_t ntiles = sort_tiles(M);
+  e->slots.resize(c.batch_slots);
+  for (Slot& s : e->slots) {
+    PIN_ALLOC(s.h_arena, c.max_batch_bytes + 64);
+    PIN_ALLOC(s.h_desc, e->desc_cap);
+    DEV_ALLOC(s.d_arena, c.max_batch_bytes + 64);
+    DEV_ALLOC(s.d_desc, e->desc_cap);
+    Work& w = s.w;
+    DEV_ALLOC(w.B, (size_t)MB * g.W);
+    DEV_ALLOC(w.wpre, (size_t)MB * g.W);
+    DEV_ALLOC(w.cnt, (size_t)MB * d.nblk);
+    DEV_ALLOC(w.base, (size_t)MB * d.nblk);
+    DEV_ALLOC(w.D, M);
+    DEV_ALLOC(w.dconn, M);
+    DEV_ALLOC(w.eb_fat, (size_t)M + 1);
+    DEV_ALLOC(w.eb_thin, (size_t)M + 1);
+    DEV_ALLOC(w.tbase, (size_t)M + 1);
+    DEV_ALLOC(w.scan_tmp, 3 * ((size_t)M / 256 + 2));
+    DEV_ALLOC(w.efat, cap_fat);
+    DEV_ALLOC(w.ethin, cap_thin);
+    w.cap_fat = (uint32_t)std::min<size_t>(cap_fat, 0xFFFFFFFFu);
+    w.cap_thin = (uint32_t)std::min<size_t>(cap_thin, 0xFFFFFFFFu);
+    for (int k = 0; k < 2; k++) { DEV_ALLOC(w.skey[k], M); DEV_ALLOC(w.sval[k], M); }
+    DEV_ALLOC(w.hist, 256 * ntiles);
+    DEV_ALLOC(w.hist_tmp, 256 * ntiles / 1024 + 2);
+    DEV_ALLOC(w.dstart, (size_t)g.N + 1);
+    DEV_ALLOC(w.dend, (size_t)g.N + 1);
+    DEV_ALLOC(w.batch_units, g.N);
+    DEV_ALLOC(w.spans, (size_t)2 * g.N);
+    DEV_ALLOC(w.overflow, g.N);
+    DEV_ALLOC(w.stats, 1);
+    PIN_ALLOC(s.h_stats, 1);
+    PIN_ALLOC(s.h_spans, (size_t)2 * g.max_conns);
+    PIN_ALLOC(s.h_overflow, g.max_conns);
+    CUDA_TRY(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    for (auto& ev : s.ev) CUDA_TRY(cudaEventCreate(&ev));
+  }
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================== C ABI
+#define LOCK std::lock_guard<std::mutex> _g(e->mu)
+#define GUARD_BEGIN try {
+#define GUARD_END                                                          \
+  } catch (const std::bad_alloc&) { return fail(PCDN_ENOMEM, "host allocation failed"); } \
+  catch (const std::exception& ex) { return fail(PCDN_EINVAL, ex.what()); }
+
+extern "C" {
+
+uint32_t pcdn_abi_version(void) { return PCDN_ABI_VERSION; }
+const char* pcdn_last_error(void) { return g_err.c_str(); }
+
+void pcdn_config_default(pcdn_config* c) {
+  std::memset(c, 0, sizeof(*c));
+  c->struct_size = sizeof(pcdn_config);
+  c->device = 0;
+  c->max_conns = 1 << 16;
+  c->max_topics = 256;
+  c->max_keys = 1 << 17;
+  c->max_key_len = 128;
+  c->ring_bytes_per_conn = 1 << 16;
+  c->max_batch_msgs = 4096;
+  c->max_batch_bcast = 1024;
+  c->max_batch_bytes = 64ull << 20;
+  c->max_batch_deliveries = 16ull << 20;
+  c->batch_slots = 4;
+  c->n_valid_topics = 0;
+  c->hash_seed = 0;
+  c->identity = "/";
+}
+
+int pcdn_create(const pcdn_config* cfg, pcdn_engine** out) {
+  GUARD_BEGIN
+  if (!cfg || !out) return fail(PCDN_EINVAL, "null argument");
+  if (cfg->struct_size != sizeof(pcdn_config)) return fail(PCDN_EINVAL, "pcdn_config.struct_size mismatch (ABI)");
+  if (!cfg->max_conns || !cfg->max_topics || cfg->max_topics > 65536 || !cfg->max_keys || !cfg->max_key_len ||
+      !cfg->max_batch_msgs || !cfg->batch_slots)
+    return fail(PCDN_EINVAL, "zero or out-of-range capacity in pcdn_config");
+  if (cfg->max_batch_bcast == 0 || cfg->max_batch_bcast > 65535) return fail(PCDN_EINVAL, "max_batch_bcast must be 1..65535");
+  if (cfg->ring_bytes_per_conn % PCDN_RECORD_ALIGN || cfg->ring_bytes_per_conn == 0 || cfg->ring_bytes_per_conn > (1ull << 31))
+    return fail(PCDN_EINVAL, "ring_bytes_per_conn must be a multiple of 32, at most 2 GiB");
+  if (cfg->max_key_len > 4096) return fail(PCDN_EINVAL, "max_key_len > 4096");
+  pcdn_engine* e = new pcdn_engine();
+  e->cfg = *cfg;
+  e->identity = cfg->identity ? cfg->identity : "/";
+  e->cfg.identity = e->identity.c_str();
+  Geometry& g = e->geo;
+  g.max_conns = cfg->max_conns;
+  g.N = (uint32_t)align_up(cfg->max_conns, 32 * kBlockWords);
+  g.W = g.N / 32;
+  g.T = cfg->max_topics;
+  g.max_keys = cfg->max_keys;
+  g.max_key_len = cfg->max_key_len;
+  g.key_stride = (uint32_t)align_up(cfg->max_key_len, 16);
+  uint32_t nb = 1;
+  while ((uint64_t)nb * 2 < cfg->max_keys) nb <<= 1;  // 4 slots per bucket → load factor <= 50 %
+  g.nbuckets = nb;
+  g.bucket_mask = nb - 1;
+  g.max_owners = 4096;
+  g.seed = cfg->hash_seed ? cfg->hash_seed : 0x243F6A8885A308D3ULL;
+  e->tables.reset(new HostTables(g));
+  e->conns.reset(new Connections(*e->tables, e->identity.c_str()));
+  if (cfg->device >= 0) {
+    int rc = init_device(e);
+    if (rc) { destroy_engine(e); return rc; }
+  }
+  *out = e;
+  return 0;
+  GUARD_END
+}
+
+void pcdn_destroy(pcdn_engine* e) {
+  if (e) destroy_engine(e);
+}
+
+// ---- state ------------------------------------------------------------------------------------
+int pcdn_add_user(pcdn_engine* e, const uint8_t* key, uint32_t key_len, const uint16_t* topics, uint32_t n,
+                  pcdn_conn* out_conn) {
+  GUARD_BEGIN
+  LOCK;
+  int rc = before_state_change(e);
+  if (rc) return rc;
+  rc = e->conns->add_user(std::string((const char*)key, key_len), topics, n, out_conn);
+  if (rc) return fail(rc, "add_user failed (capacity, key length or topic id)");
+  return 0;
+  GUARD_END
+}
+int pcdn_add_users_bulk(pcdn_engine* e, const uint8_t* keys, uint32_t key_len, uint32_t key_stride, uint32_t n_users,
+                        const uint16_t* topics, const uint32_t* topic_offsets, pcdn_conn* out_conns) {
+  GUARD_BEGIN
+  LOCK;
+  int rc = before_state_change(e);
+  if (rc) return rc;
+  for (uint32_t i = 0; i < n_users; i++) {
+    uint32_t conn;
+    const uint16_t* t = topics ? topics + topic_offsets[i] : nullptr;
+    uint32_t nt = topics ? topic_offsets[i + 1] - topic_offsets[i] : 0;
+    rc = e->conns->add_user(std::string((const char*)keys + (size_t)i * key_stride, key_len), t, nt, &conn);
+    if (rc) return fail(rc, "add_users_bulk failed at user " + std::to_string(i));
+    if (out_conns) out_conns[i] = conn;
+  }
+  return 0;
+  GUARD_END
+}
+int pcdn_remove_user(pcdn_engine* e, const uint8_t* key, uint32_t key_len) {
+  GUARD_BEGIN
+  LOCK;
+  int rc = before_state_change(e);
+  if (rc) return rc;
+  rc = e->conns->remove_user(std::string((const char*)key, key_len));
+  return rc ? fail(rc, "remove_user failed") : 0;
+  GUARD_END
+}
+int pcdn_subscribe_user_to(pcdn_engine* e, const uint8_t* key, uint32_t key_len, const uint16_t* topics, uint32_t n) {
+  GUARD_BEGIN
+  LOCK;
+  int rc = before_state_change(e);
+  if (rc) return rc;
+  rc = e->conns->subscribe_user_to(std::string((const char*)key, key_len), topics, n);
+  return rc ? fail(rc, "topic id out of range") : 0;
+  GUARD_END
+}
+int pcdn_unsubscribe_user_from(pcdn_engine* e, const uint8_t* key, uint32_t key_len, const uint16_t* topics, uint32_t n) {
+  GUARD_BEGIN
+  LOCK;
+  int rc = before_state_change(e);
+  if (rc) return rc;
+  return e->conns->unsubscribe_user_from(std::string((const char*)key, key_len), topics, n);
+  GUARD_END
+}
+int pcdn_add_broker(pcdn_engine* e, const char* identifier, pcdn_conn* out_conn) {
+  GUARD_BEGIN
+  LOCK;
+  int rc = before_state_change(e);
+  if (rc) return rc;
+  rc = e->conns->add_broker(identifier, out_conn);
+  return rc ? fail(rc, "add_broker failed") : 0;
+  GUARD_END
+}
+int pcdn_remove_broker(pcdn_engine* e, const char* identifier) {
+  GUARD_BEGIN
+  LOCK;
+  int rc = before_state_change(e);
+  if (rc) return rc;
+  return e->conns->remove_broker(identifier);
+  GUARD_END
+}
+int pcdn_subscribe_broker_to(pcdn_engine* e, const char* identifier, const uint16_t* topics, uint32_t n) {
+  GUARD_BEGIN
+  LOCK;
+  int rc = before_state_change(e);
+  if (rc) return rc;
+  rc = e->conns->subscribe_broker_to(identifier, topics, n);
+  return rc ? fail(rc, "topic id out of range") : 0;
+  GUARD_END
+}
+int pcdn_unsubscribe_broker_from(pcdn_engine* e, const char* identifier, const uint16_t* topics, uint32_t n) {
+  GUARD_BEGIN
+  LOCK;
+  int rc = before_state_change(e);
+  if (rc) return rc;
+  return e->conns->unsubscribe_broker_from(identifier, topics, n);
+  GUARD_END
+}
+int pcdn_apply_user_sync(pcdn_engine* e, const char* remote_identity, const pcdn_user_sync_entry* entries, uint32_t n) {
+  GUARD_BEGIN
+  LOCK;
+  int rc = before_state_change(e);
+  if (rc) return rc;
+  std::vector<UserSyncEntry> v;
+  v.reserve(n);
+  for (uint32_t i = 0; i < n; i++)
+    v.push_back(UserSyncEntry{std::string((const char*)entries[i].key, entries[i].key_len), entries[i].version,
+                              entries[i].owner != nullptr, entries[i].owner ? entries[i].owner : ""});
+  rc = e->conns->apply_user_sync(remote_identity, v);
+  return rc ? fail(rc, "apply_user_sync failed") : 0;
+  GUARD_END
+}
+
+// ---- data in ----------------------------------------------------------------------------------
+int pcdn_handle_broadcast_message(pcdn_engine* e, const uint16_t* topics, uint32_t n_topics, const uint8_t* raw,
+                                  uint32_t raw_len, int to_users_only) {
+  GUARD_BEGIN
+  LOCK;
+  return append_msg(e, PCDN_KIND_BROADCAST, to_users_only ? PCDN_TO_USERS_ONLY : 0, topics, n_topics, nullptr, 0, raw, raw_len);
+  GUARD_END
+}
+int pcdn_handle_direct_message(pcdn_engine* e, const uint8_t* recipient, uint32_t recipient_len, const uint8_t* raw,
+                               uint32_t raw_len, int to_user_only) {
+  GUARD_BEGIN
+  LOCK;
+  return append_msg(e, PCDN_KIND_DIRECT, to_user_only ? PCDN_TO_USERS_ONLY : 0, nullptr, 0, recipient, recipient_len, raw, raw_len);
+  GUARD_END
+}
+
+int pcdn_user_receive(pcdn_engine* e, const uint8_t* sender_key, uint32_t key_len, const uint8_t* raw, uint32_t raw_len) {
+  GUARD_BEGIN
+  LOCK;
+  ParsedFrame pf;
+  if (!parse_frame(raw, raw_len, &pf)) return fail(PCDN_EPARSE, "failed to deserialize message");
+  uint16_t topics[65536 / 8];
+  switch (pf.kind) {
+    case PCDN_KIND_DIRECT:
+      return append_msg(e, PCDN_KIND_DIRECT, 0, nullptr, 0, raw + pf.f0_off, pf.f0_len, raw, raw_len);
+    case PCDN_KIND_BROADCAST:
+    case PCDN_KIND_SUBSCRIBE:
+    case PCDN_KIND_UNSUBSCRIBE: {
+      if (pf.f0_len > sizeof(topics) / 2) return fail(PCDN_EPARSE, "topic list too long");
+      uint32_t n = prune_topics(raw + pf.f0_off, pf.f0_len, e->cfg.n_valid_topics, topics);
+      if (n == 0) return fail(PCDN_EPRUNE, "supplied no valid topics");
+      if (pf.kind == PCDN_KIND_BROADCAST) return append_msg(e, PCDN_KIND_BROADCAST, 0, topics, n, nullptr, 0, raw, raw_len);
+      int rc = before_state_change(e);
+      if (rc) return rc;
+      std::string key((const char*)sender_key, key_len);
+      rc = pf.kind == PCDN_KIND_SUBSCRIBE ? e->conns->subscribe_user_to(key, topics, n)
+                                          : e->conns->unsubscribe_user_from(key, topics, n);
+      return rc ? fail(rc, "topic id out of range") : 0;
+    }
+    default:
+      return fail(PCDN_EKIND, "invalid message received");
+  }
+  GUARD_END
+}
+
+int pcdn_broker_receive(pcdn_engine* e, const char* /*identifier*/, const uint8_t* raw, uint32_t raw_len) {
+  GUARD_BEGIN
+  LOCK;
+  ParsedFrame pf;
+  if (!parse_frame(raw, raw_len, &pf)) return fail(PCDN_EPARSE, "failed to deserialize message");
+  if (pf.kind == PCDN_KIND_DIRECT)
+    return append_msg(e, PCDN_KIND_DIRECT, PCDN_TO_USERS_ONLY, nullptr, 0, raw + pf.f0_off, pf.f0_len, raw, raw_len);
+  if (pf.kind == PCDN_KIND_BROADCAST) {
+    uint16_t topics[65536 / 8];
+    if (pf.f0_len > sizeof(topics) / 2) return fail(PCDN_EPARSE, "topic list too long");
+    for (uint32_t i = 0; i < pf.f0_len; i++) topics[i] = raw[pf.f0_off + i];  // broker-origin: no prune (handler.rs:157)
+    return append_msg(e, PCDN_KIND_BROADCAST, PCDN_TO_USERS_ONLY, topics, pf.f0_len, nullptr, 0, raw, raw_len);
+  }
+  return 1;
+  GUARD_END
+}
+
+int pcdn_flush(pcdn_engine* e, uint64_t* batch_id) {
+  GUARD_BEGIN
+  LOCK;
+  return flush_open(e, batch_id);
+  GUARD_END
+}
+
+int pcdn_submit(pcdn_engine* e, const pcdn_msg* msgs, uint32_t n, uint64_t* batch_id) {
+  GUARD_BEGIN
+  LOCK;
+  if (batch_id) *batch_id = 0;
+  int rc = flush_open(e, nullptr);  // keep explicit batches separate from the implicit open one
+  if (rc) return rc;
+  if (n > e->cfg.max_batch_msgs) return fail(PCDN_ENOSPC, "batch larger than max_batch_msgs");
+  for (uint32_t i = 0; i < n; i++) {
+    const pcdn_msg& m = msgs[i];
+    uint64_t before = e->next_batch_id;
+    rc = append_msg(e, m.kind, m.flags, m.topics, m.n_topics, m.recipient, m.recipient_len, m.raw, m.raw_len);
+    if (rc) return rc;
+    if (e->next_batch_id != before) return fail(PCDN_ENOSPC, "batch exceeded a per-batch capacity and was split");
+  }
+  return flush_open(e, batch_id);
+  GUARD_END
+}
+
+int pcdn_submit_device(pcdn_engine* e, const pcdn_device_batch* b, uint64_t* batch_id) {
+  GUARD_BEGIN
+  LOCK;
+  if (batch_id) *batch_id = 0;
+  if (!e->has_device) return fail(PCDN_ENODEV, "host-only engine cannot route messages");
+  if (!b || b->n_msgs == 0 || b->n_msgs > e->cfg.max_batch_msgs || b->n_bcast > e->cfg.max_batch_bcast ||
+      b->n_bcast > b->n_msgs)
+    return fail(PCDN_EINVAL, "device batch exceeds configured capacities");
+  int rc = flush_open(e, nullptr);
+  if (rc) return rc;
+  if ((rc = acquire_open_slot(e))) return rc;
+  Slot& s = e->slots[e->open_slot];
+  if ((rc = flush_journal(e))) { s.state = SLOT_FREE; e->open_slot = -1; return rc; }
+  s.in.n_msgs = b->n_msgs;
+  s.in.n_bcast = b->n_bcast;
+  s.in.arena = (const uint8_t*)b->arena;
+  s.in.kind = b->kind;
+  s.in.flags = b->flags;
+  s.in.slot_off16 = b->slot_off16;
+  s.in.raw_len = b->raw_len;
+  s.in.aux_off = b->aux_off;
+  s.in.aux_len = b->aux_len;
+  s.in.topics = b->topics;
+  s.in.bcast_index = b->bcast_index;
+  s.device_input = true;
+  rc = launch_pipeline(e, s, b->n_msgs - b->n_bcast);
+  if (rc) { s.state = SLOT_FREE; e->open_slot = -1; return rc; }
+  if (batch_id) *batch_id = s.batch_id;
+  e->open_slot = -1;
+  e->stats.batches++;
+  e->stats.msgs += b->n_msgs;
+  return 0;
+  GUARD_END
+}
+
+// ---- data out ---------------------------------------------------------------------------------
+int pcdn_next_batch(pcdn_engine* e, uint64_t* batch_id) {
+  LOCK;
+  *batch_id = e->inflight.empty() ? 0 : e->inflight.front();
+  return 0;
+}
+
+int pcdn_poll(pcdn_engine* e, uint64_t batch_id, pcdn_batch_result* out, int block) {
+  GUARD_BEGIN
+  LOCK;
+  Slot* s = find_slot(e, batch_id);
+  if (!s) return fail(PCDN_ENOENT, "unknown batch id");
+  if (!s->polled) {
+    if (block) CUDA_TRY(cudaEventSynchronize(s->ev_done));
+    else {
+      cudaError_t q = cudaEventQuery(s->ev_done);
+      if (q == cudaErrorNotReady) return 1;
+      CUDA_TRY(q);
+    }
+    const BatchStats& bs = *s->h_stats;
+    uint32_t nsp = std::min<uint32_t>(bs.n_spans, 2 * e->geo.max_conns);
+    uint32_t nov = std::min<uint32_t>(bs.n_overflow, e->geo.max_conns);
+    if (nsp) CUDA_TRY(cudaMemcpyAsync(s->h_spans, s->w.spans, (size_t)nsp * sizeof(Span), cudaMemcpyDeviceToHost, e->copy_stream));
+    if (nov) CUDA_TRY(cudaMemcpyAsync(s->h_overflow, s->w.overflow, (size_t)nov * 4, cudaMemcpyDeviceToHost, e->copy_stream));
+    if (nsp || nov) CUDA_TRY(cudaStreamSynchronize(e->copy_stream));
+    s->polled = true;
+    e->stats.deliveries += bs.n_deliveries;
+    e->stats.bytes_out += bs.bytes_out;
+    if (s->timed) {
+      float t[4] = {0, 0, 0, 0};
+      for (int i = 0; i < 4; i++) cudaEventElapsedTime(&t[i], s->ev[i], s->ev[i + 1]);
+      e->stats.ms_direct += t[0];
+      e->stats.ms_match += t[1];
+      e->stats.ms_plan += t[2];
+      e->stats.ms_pack += t[3];
+      e->stats.ms_total += t[0] + t[1] + t[2] + t[3];
+      e->stats.timed_batches++;
+    }
+  }
+  if (out) {
+    const BatchStats& bs = *s->h_stats;
+    out->batch_id = batch_id;
+    out->n_msgs = s->in.n_msgs;
+    out->n_spans = std::min<uint32_t>(bs.n_spans, 2 * e->geo.max_conns);
+    out->spans = reinterpret_cast<const pcdn_span*>(s->h_spans);
+    out->n_deliveries = bs.n_deliveries;
+    out->bytes_out = bs.bytes_out;
+    out->n_overflow = std::min<uint32_t>(bs.n_overflow, e->geo.max_conns);
+    out->overflow_conns = s->h_overflow;
+    out->n_direct_dropped = bs.n_direct_dropped;
+    out->status = bs.status ? (uint32_t)(-PCDN_E2BIG) : 0;
+  }
+  return 0;
+  GUARD_END
+}
+
+int pcdn_read(pcdn_engine* e, pcdn_conn conn, uint32_t ring_off, uint32_t len, void* dst) {
+  GUARD_BEGIN
+  LOCK;
+  if (!e->has_device) return fail(PCDN_ENODEV, "host-only engine");
+  if (conn >= e->geo.max_conns || (uint64_t)ring_off + len > e->cfg.ring_bytes_per_conn)
+    return fail(PCDN_EINVAL, "read outside the connection's ring");
+  CUDA_TRY(cudaMemcpyAsync(dst, e->dev.rings + (size_t)conn * e->cfg.ring_bytes_per_conn + ring_off, len,
+                           cudaMemcpyDeviceToHost, e->copy_stream));
+  CUDA_TRY(cudaStreamSynchronize(e->copy_stream));
+  return 0;
+  GUARD_END
+}
+
+int pcdn_release_batch(pcdn_engine* e, uint64_t batch_id) {
+  GUARD_BEGIN
+  LOCK;
+  Slot* s = find_slot(e, batch_id);
+  if (!s) return fail(PCDN_ENOENT, "unknown batch id");
+  if (e->inflight.empty() || e->inflight.front() != batch_id)
+    return fail(PCDN_EINVAL, "batches must be released oldest first");
+  launch_release(e->dev, s->w.batch_units, e->stream);
+  CUDA_TRY(cudaGetLastError());
+  e->inflight.erase(e->inflight.begin());
+  s->state = SLOT_FREE;
+  return 0;
+  GUARD_END
+}
+
+// ---- introspection ----------------------------------------------------------------------------
+int pcdn_get_stats(pcdn_engine* e, pcdn_stats* out) {
+  LOCK;
+  *out = e->stats;
+  return 0;
+}
+int pcdn_set_timing(pcdn_engine* e, int on) {
+  LOCK;
+  e->timing = on != 0;
+  return 0;
+}
+int pcdn_ring_info(pcdn_engine* e, void** dev_base, uint64_t* ring_bytes, uint32_t* max_conns) {
+  LOCK;
+  if (dev_base) *dev_base = e->has_device ? (void*)e->dev.rings : nullptr;
+  if (ring_bytes) *ring_bytes = e->cfg.ring_bytes_per_conn;
+  if (max_conns) *max_conns = e->geo.max_conns;
+  return 0;
+}
+int pcdn_num_users(pcdn_engine* e, uint32_t* users, uint32_t* brokers) {
+  LOCK;
+  if (users) *users = e->conns->num_users();
+  if (brokers) *brokers = e->conns->num_brokers();
+  return 0;
+}
+int pcdn_debug_interested(pcdn_engine* e, const uint16_t* topics, uint32_t n_topics, int to_users_only, pcdn_conn* out,
+                          uint32_t cap, uint32_t* n) {
+  GUARD_BEGIN
+  LOCK;
+  std::vector<uint32_t> v;
+  e->conns->interested(topics, n_topics, to_users_only != 0, v);
+  *n = (uint32_t)v.size();
+  for (uint32_t i = 0; i < v.size() && i < cap; i++) out[i] = v[i];
+  return 0;
+  GUARD_END
+}
+int pcdn_debug_route(pcdn_engine* e, const uint8_t* key, uint32_t key_len, int* kind, pcdn_conn* conn) {
+  GUARD_BEGIN
+  LOCK;
+  *kind = e->conns->route(std::string((const char*)key, key_len), conn);
+  return 0;
+  GUARD_END
+}
+int pcdn_parse_frame(const uint8_t* raw, uint32_t raw_len, uint16_t* topics_out, uint32_t* n_topics, uint32_t* field_off,
+                     uint32_t* field_len) {
+  ParsedFrame pf;
+  if (!parse_frame(raw, raw_len, &pf)) return fail(PCDN_EPARSE, "failed to deserialize message");
+  if (field_off) *field_off = pf.f0_off;
+  if (field_len) *field_len = pf.f0_len;
+  if (n_topics) *n_topics = 0;
+  if ((pf.kind == PCDN_KIND_BROADCAST || pf.kind == PCDN_KIND_SUBSCRIBE || pf.kind == PCDN_KIND_UNSUBSCRIBE) && topics_out &&
+      n_topics) {
+    uint32_t n = std::min<uint32_t>(pf.f0_len, 256);
+    for (uint32_t i = 0; i < n; i++) topics_out[i] = raw[pf.f0_off + i];
+    *n_topics = n;
+  }
+  return pf.kind;
+}
+
+}  // extern "C"

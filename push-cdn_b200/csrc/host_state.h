@@ -1,0 +1,137 @@
+// host_state.h — host-side mirror of the broker's routing state.
+//
+// `Connections` restates cdn-broker/src/connections/mod.rs:40-388 (with RelationalMap
+// broadcast/relational_map.rs:13-116 and VersionedMap versioned_map.rs:39-270 folded in) but keeps
+// its results in the layout the GPU kernels read: a topic→connection subscription bitmap, a broker
+// mask, an owner→connection table and a cuckoo hash from user public key to route.  `HostTables`
+// owns those arrays and remembers which words/slots changed since the last upload, so that a state
+// call costs O(1) host work and a few scattered device words (R12 ordering: the journal is applied
+// on the engine stream before the next batch's kernels).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "hash.h"
+
+namespace pcdn {
+
+struct Geometry {
+  uint32_t max_conns = 0;   // usable connection ids
+  uint32_t N = 0;           // max_conns rounded up to a multiple of 8192 (256 bitmap words)
+  uint32_t W = 0;           // N / 32 bitmap words per topic row
+  uint32_t T = 0;           // topic rows
+  uint32_t max_keys = 0;
+  uint32_t max_key_len = 0;
+  uint32_t key_stride = 0;  // bytes per key-arena slot (multiple of 16)
+  uint32_t nbuckets = 0;    // power of two, 4 slots each
+  uint32_t bucket_mask = 0;
+  uint32_t max_owners = 0;
+  uint64_t seed = 0;
+};
+
+enum { CONN_FREE = 0, CONN_USER = 1, CONN_BROKER = 2 };
+
+class HostTables {
+ public:
+  explicit HostTables(const Geometry& g);
+  Geometry g;
+  std::vector<uint32_t> sub;         // [T][W]
+  std::vector<uint32_t> brk;         // [W]
+  std::vector<uint32_t> owner_conn;  // [max_owners]
+  std::vector<CuckooEntry> cuckoo;   // [nbuckets*4]
+  std::vector<uint8_t> keys;         // [max_keys][key_stride]
+
+  // dirty sets since the last take_*()
+  std::vector<uint32_t> dirty_sub, dirty_brk, dirty_owner, dirty_slots, dirty_keys;
+
+  void set_bit(uint32_t topic, uint32_t conn, bool on);
+  bool get_bit(uint32_t topic, uint32_t conn) const;
+  void set_broker(uint32_t conn, bool on);
+  void set_owner_conn(uint32_t owner, uint32_t conn);
+  // cuckoo: returns 0, PCDN_ENOSPC or PCDN_EKEYLEN
+  int route_upsert(const uint8_t* key, uint32_t len, uint32_t route);
+  void route_erase(const uint8_t* key, uint32_t len);
+  bool route_find(const uint8_t* key, uint32_t len, uint32_t* route) const;
+  uint32_t n_keys() const { return n_keys_; }
+  void clear_dirty();
+
+ private:
+  std::vector<uint8_t> f_sub_, f_brk_, f_owner_, f_slot_, f_key_;
+  std::vector<uint32_t> free_key_slots_;
+  uint32_t next_key_slot_ = 0, n_keys_ = 0;
+  uint32_t kick_rng_ = 0x9E3779B9u;
+  void mark(std::vector<uint32_t>& list, std::vector<uint8_t>& flag, uint32_t idx);
+  int find_slot(const uint8_t* key, uint32_t len, uint64_t h) const;  // slot index or -1
+  int place(CuckooEntry e, uint32_t bucket);                          // with eviction
+  void write_slot(uint32_t slot, const CuckooEntry& e);
+};
+
+// BrokerIdentifier (cdn-proto/src/discovery/mod.rs:80-129): "public/private", ordered as the tuple
+struct BrokerIdent {
+  std::string pub, priv;
+  static BrokerIdent parse(const char* s);
+  std::string str() const { return pub + "/" + priv; }
+  bool operator>(const BrokerIdent& o) const { return pub != o.pub ? pub > o.pub : priv > o.priv; }
+};
+
+struct UserSyncEntry {
+  std::string key;
+  uint64_t version;
+  bool has_owner;
+  std::string owner;
+};
+
+class Connections {
+ public:
+  Connections(HostTables& t, const char* identity);
+
+  // -- the reference's mutation API (connections/mod.rs) ---------------------------------------
+  int add_user(const std::string& key, const uint16_t* topics, uint32_t n, uint32_t* conn);  // :278
+  int remove_user(const std::string& key);                                                   // :330
+  int subscribe_user_to(const std::string& key, const uint16_t* topics, uint32_t n);         // :365
+  int unsubscribe_user_from(const std::string& key, const uint16_t* topics, uint32_t n);     // :383
+  int add_broker(const char* ident, uint32_t* conn);                                         // :252
+  int remove_broker(const char* ident);                                                      // :308
+  int subscribe_broker_to(const char* ident, const uint16_t* topics, uint32_t n);            // :354
+  int unsubscribe_broker_from(const char* ident, const uint16_t* topics, uint32_t n);        // :372
+  int apply_user_sync(const char* remote_identity, const std::vector<UserSyncEntry>& e);     // :154
+
+  // -- lookups on the mirror (tests / debug; the data path does these on the GPU) --------------
+  void interested(const uint16_t* topics, uint32_t n, bool to_users_only,
+                  std::vector<uint32_t>& conns) const;                                       // :94
+  // 0 none, 1 local user, 2 remote broker (conn may be NONE)
+  int route(const std::string& key, uint32_t* conn) const;                                   // :69,:84,:74
+  uint32_t num_users() const { return (uint32_t)users_.size(); }
+  uint32_t num_brokers() const { return (uint32_t)brokers_.size(); }
+  bool has_user(const std::string& key) const { return users_.count(key) != 0; }
+  bool has_broker(const char* ident) const;
+
+ private:
+  struct VV { uint64_t version; bool has; uint32_t owner; };  // VersionedValue<BrokerIdentifier>
+  struct BrokerRec { uint32_t conn; uint32_t owner; };
+  HostTables& t_;
+  BrokerIdent identity_;
+  std::unordered_map<std::string, uint32_t> users_;                         // users :45
+  std::unordered_map<std::string, BrokerRec> brokers_;                      // brokers :47
+  std::unordered_map<std::string, VV> direct_map_;                          // direct_map :50
+  std::unordered_set<std::string> locally_modified_;                        // versioned_map.rs:47
+  std::unordered_map<std::string, std::vector<uint16_t>> user_topics_;      // broadcast_map.users key_to_values
+  std::unordered_map<std::string, std::vector<uint16_t>> broker_topics_;    // broadcast_map.brokers key_to_values
+  std::unordered_map<std::string, uint32_t> owner_ids_;                     // identifier → owner index (0 = self)
+  std::vector<BrokerIdent> owners_;
+  std::vector<uint8_t> conn_kind_;
+  std::vector<uint32_t> free_conns_;
+  uint32_t next_conn_ = 0;
+
+  int alloc_conn(int kind, uint32_t* conn);
+  void free_conn(uint32_t conn);
+  int owner_id(const BrokerIdent& b, uint32_t* id);
+  int update_route(const std::string& key);
+  void dm_modify_local(const std::string& key, bool has, uint32_t owner);   // versioned_map.rs:84-113
+  int check_topics(const uint16_t* topics, uint32_t n) const;
+};
+
+}  // namespace pcdn

@@ -1,0 +1,697 @@
+// kernels.cu — hand-written sm_100a kernels of the fan-out engine.  See kernels.cuh for the
+// pipeline and DESIGN.md for the roofline of each kernel.  Everything here is integer/byte work
+// bound by HBM bandwidth; there is deliberately no tensor-core code.
+#include "kernels.cuh"
+
+namespace pcdn {
+
+// =============================================================================== small helpers
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+  const uint32_t lane = lane_id();
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t n = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= (uint32_t)o) v += n;
+  }
+  return v;
+}
+
+// exclusive scan over a 256-thread block; *total = block sum.  `sm` needs 9 words.
+__device__ __forceinline__ uint32_t block256_excl_scan(uint32_t v, uint32_t* total, uint32_t* sm) {
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  uint32_t incl = warp_incl_scan(v);
+  if (lane == 31) sm[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t x = lane < 8 ? sm[lane] : 0;
+    uint32_t xi = warp_incl_scan(x);
+    if (lane < 8) sm[lane] = xi - x;
+    if (lane == 7) sm[8] = xi;
+  }
+  __syncthreads();
+  uint32_t r = incl - v + sm[warp];
+  *total = sm[8];
+  __syncthreads();
+  return r;
+}
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+// 16-byte streaming store: written once, never read back by the GPU
+__device__ __forceinline__ void st_stream16(void* p, const uint4& v) {
+  asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ld_nc16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+// ---- mbarrier / TMA bulk copy (cp.async.bulk → SASS UBLKCP) -----------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// global → shared, completion counted on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared → global, bulk-group completion
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// =============================================================================== K4 table updates
+__global__ void k_apply_u32(DevState s, const Upd32* __restrict__ u, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Upd32 x = u[i];
+  uint32_t* a = x.arr == 0 ? s.sub : (x.arr == 1 ? s.brk : s.owner_conn);
+  a[x.idx] = x.val;
+}
+__global__ void k_apply_slots(DevState s, const UpdSlot* __restrict__ u, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  s.cuckoo[u[i].slot] = u[i].e;
+}
+__global__ void k_apply_keys(DevState s, const uint32_t* __restrict__ slots, const uint8_t* __restrict__ bytes,
+                             uint32_t n) {
+  // one thread per 16 bytes of key
+  uint32_t per = s.key_stride >> 4;
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (uint64_t)n * per) return;
+  uint32_t k = (uint32_t)(i / per), v = (uint32_t)(i % per);
+  const uint4* src = reinterpret_cast<const uint4*>(bytes + (size_t)k * s.key_stride) + v;
+  uint4* dst = reinterpret_cast<uint4*>(s.keys + (size_t)slots[k] * s.key_stride) + v;
+  *dst = *src;
+}
+
+void launch_apply_updates(const DevState& s, const Upd32* u32, uint32_t n32, const UpdSlot* us, uint32_t nslot,
+                          const uint32_t* key_slots, const uint8_t* key_bytes, uint32_t nkeys, cudaStream_t st) {
+  if (nkeys) {
+    uint64_t th = (uint64_t)nkeys * (s.key_stride >> 4);
+    k_apply_keys<<<(unsigned)((th + 255) / 256), 256, 0, st>>>(s, key_slots, key_bytes, nkeys);
+  }
+  if (nslot) k_apply_slots<<<(nslot + 255) / 256, 256, 0, st>>>(s, us, nslot);
+  if (n32) k_apply_u32<<<(n32 + 255) / 256, 256, 0, st>>>(s, u32, n32);
+}
+
+// =============================================================================== generic u32 scan
+__global__ void k_scan_a(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n,
+                         uint32_t* __restrict__ tile_tot) {
+  __shared__ uint32_t sm[9];
+  uint32_t base = blockIdx.x * 1024 + threadIdx.x * 4;
+  uint32_t v[4], s = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { v[k] = (base + k < n) ? in[base + k] : 0; s += v[k]; }
+  uint32_t tot, ex = block256_excl_scan(s, &tot, sm);
+#pragma unroll
+  for (int k = 0; k < 4; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+  if (threadIdx.x == 0) tile_tot[blockIdx.x] = tot;
+}
+// single block: in-place exclusive scan of `n` tile totals
+__global__ void k_scan_b(uint32_t* __restrict__ t, uint32_t n) {
+  __shared__ uint32_t sm[9];
+  uint32_t carry = 0;
+  for (uint32_t b = 0; b < n; b += 256) {
+    uint32_t i = b + threadIdx.x;
+    uint32_t v = i < n ? t[i] : 0;
+    uint32_t tot, ex = block256_excl_scan(v, &tot, sm);
+    if (i < n) t[i] = ex + carry;
+    carry += tot;
+  }
+}
+__global__ void k_scan_c(uint32_t* __restrict__ out, uint32_t n, const uint32_t* __restrict__ tile_tot) {
+  uint32_t i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n) out[i] += tile_tot[i >> 10];
+}
+static void scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp, cudaStream_t st) {
+  uint32_t tiles = (n + 1023) / 1024;
+  k_scan_a<<<tiles, 256, 0, st>>>(in, out, n, tmp);
+  if (tiles > 1) {
+    k_scan_b<<<1, 256, 0, st>>>(tmp, tiles);
+    k_scan_c<<<(n + 255) / 256, 256, 0, st>>>(out, n, tmp);
+  }
+}
+
+// =============================================================================== K3 direct lookup
+__device__ __forceinline__ uint32_t key_word32(const uint8_t* kp, uint32_t j, uint32_t klen) {
+  uint32_t o = j * 4;
+  if (o >= klen) return 0;
+  uint32_t w = *reinterpret_cast<const uint32_t*>(kp + o);  // kp is 4-byte aligned (engine contract)
+  uint32_t rem = klen - o;
+  if (rem < 4) w &= (1u << (8 * rem)) - 1u;
+  return w;
+}
+
+// One warp per message.  Direct messages: hash the recipient key (one 64-bit word per lane,
+// shuffle-reduced), probe both 4-slot buckets with 8 lanes, verify the full key against the key
+// arena, resolve the route (handler.rs:204-236).  Also seeds the (conn, msg) sort arrays.
+__global__ void __launch_bounds__(256) k_direct_lookup(DevState s, BatchIn b, Work w) {
+  const uint32_t m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = lane_id();
+  if (m >= b.n_msgs) return;
+  const bool is_direct = b.kind[m] == 3;
+  uint32_t target = kConnNone;
+  if (is_direct) {
+    const uint32_t klen = b.aux_len[m];
+    const uint8_t* kp = b.arena + b.aux_off[m];
+    const uint32_t nw = (klen + 7) >> 3;
+    uint64_t acc = 0;
+    for (uint32_t i = lane; i < nw; i += 32) {
+      uint64_t wd = (uint64_t)key_word32(kp, 2 * i, klen) | ((uint64_t)key_word32(kp, 2 * i + 1, klen) << 32);
+      acc += key_word_mix(wd, i, s.seed);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const uint64_t h = key_hash_finish(acc, klen);
+    const uint32_t tag = key_tag(h), b1 = key_bucket(h, s.bucket_mask), b2 = alt_bucket(b1, tag, s.bucket_mask);
+    CuckooEntry e{0, 0, ROUTE_NONE, 0};
+    if (lane < 8) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(&s.cuckoo[(size_t)(lane < 4 ? b1 : b2) * 4 + (lane & 3)]);
+      e.tag = raw.x; e.key_slot = raw.y; e.route = raw.z; e.key_len = raw.w;
+    }
+    bool cand = lane < 8 && e.tag == tag && e.key_len == klen;
+    if (b1 == b2 && lane >= 4) cand = false;
+    uint32_t mask = __ballot_sync(0xffffffffu, cand);
+    uint32_t route = ROUTE_NONE;
+    const uint32_t nw32 = (klen + 3) >> 2;
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const uint32_t kslot = __shfl_sync(0xffffffffu, e.key_slot, src);
+      const uint32_t rt = __shfl_sync(0xffffffffu, e.route, src);
+      const uint32_t* ak = reinterpret_cast<const uint32_t*>(s.keys + (size_t)kslot * s.key_stride);
+      bool eq = true;
+      for (uint32_t i = lane; i < nw32; i += 32) eq = eq && (ak[i] == key_word32(kp, i, klen));
+      if (__all_sync(0xffffffffu, eq)) { route = rt; break; }
+    }
+    if (route != ROUTE_NONE) {
+      if (route & ROUTE_REMOTE) {
+        // owner is another broker: forward unless the message came from a broker (to_user_only)
+        if (!(b.flags[m] & 1)) target = s.owner_conn[route & ~ROUTE_REMOTE];
+      } else {
+        target = route;
+      }
+    }
+    if (target != kConnNone && target >= s.N) target = kConnNone;
+  }
+  if (lane == 0) {
+    w.dconn[m] = target;
+    if (is_direct) {
+      w.D[m] = target != kConnNone ? 1u : 0u;
+      if (target == kConnNone) atomicAdd(&w.stats->n_direct_dropped, 1u);
+    }
+    w.skey[0][m] = (is_direct && target != kConnNone) ? target : s.N;
+    w.sval[0][m] = m;
+  }
+}
+
+// ---- stable LSD radix sort of (target conn, msg index), 8-bit digits ---------------------------
+constexpr uint32_t kSortTile = 2048;
+size_t sort_tiles(uint32_t n) { return (n + kSortTile - 1) / kSortTile; }
+
+__global__ void __launch_bounds__(256) k_sort_hist(const uint32_t* __restrict__ key, uint32_t n, uint32_t shift,
+                                                   uint32_t* __restrict__ hist, uint32_t ntiles) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t base = blockIdx.x * kSortTile;
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    uint32_t i = base + r * 256 + threadIdx.x;
+    if (i < n) atomicAdd(&h[(key[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];  // digit-major for the global scan
+}
+
+__global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin,
+                                                      uint32_t* __restrict__ kout, uint32_t* __restrict__ vout,
+                                                      uint32_t n, uint32_t shift, const uint32_t* __restrict__ hist,
+                                                      uint32_t ntiles) {
+  __shared__ uint32_t run[256];      // next output position per digit for this tile
+  __shared__ uint32_t wcnt[8][256];  // per-warp digit counts of the current round
+  __shared__ uint32_t woff[8][256];  // per-warp output start per digit
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  run[threadIdx.x] = hist[threadIdx.x * ntiles + blockIdx.x];
+  const uint32_t base = blockIdx.x * kSortTile;
+  for (int r = 0; r < 8; r++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) wcnt[k][threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t i = base + r * 256 + threadIdx.x;  // index order inside the tile is preserved
+    const bool valid = i < n;
+    const uint32_t key = valid ? kin[i] : 0, val = valid ? vin[i] : 0;
+    const uint32_t d = (key >> shift) & 255u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xFFFFFFFFu);
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rank == 0) wcnt[warp][d] = __popc(peers);
+    __syncthreads();
+    {  // thread = digit: prefix over the 8 warps (warp order = index order)
+      uint32_t off = run[threadIdx.x];
+#pragma unroll
+      for (int k = 0; k < 8; k++) { woff[k][threadIdx.x] = off; off += wcnt[k][threadIdx.x]; }
+      run[threadIdx.x] = off;
+    }
+    __syncthreads();
+    if (valid) {
+      const uint32_t pos = woff[warp][d] + rank;
+      kout[pos] = key;
+      vout[pos] = val;
+    }
+    __syncthreads();
+  }
+}
+
+// sorted keys → [dstart, dend) per connection (arrays pre-zeroed)
+__global__ void k_bucket_bounds(const uint32_t* __restrict__ skey, uint32_t n, uint32_t* __restrict__ dstart,
+                                uint32_t* __restrict__ dend) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k = skey[i];
+  if (i == 0 || skey[i - 1] != k) dstart[k] = i;
+  if (i + 1 == n || skey[i + 1] != k) dend[k] = i + 1;
+}
+
+void launch_batch_begin(const DevState& s, const Work& w, const BatchIn&, bool has_direct, cudaStream_t st) {
+  cudaMemsetAsync(w.stats, 0, sizeof(BatchStats), st);
+  if (has_direct) {
+    cudaMemsetAsync(w.dstart, 0, (size_t)(s.N + 1) * 4, st);
+    cudaMemsetAsync(w.dend, 0, (size_t)(s.N + 1) * 4, st);
+  }
+}
+
+void launch_direct(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st) {
+  const uint32_t n = b.n_msgs;
+  k_direct_lookup<<<(n * 32 + 255) / 256, 256, 0, st>>>(s, b, w);
+  uint32_t bits = 1;
+  while ((1ull << bits) <= (uint64_t)s.N) bits++;  // keys are in [0, N]
+  const uint32_t passes = (bits + 7) / 8;
+  const uint32_t ntiles = (uint32_t)sort_tiles(n);
+  int cur = 0;
+  for (uint32_t p = 0; p < passes; p++) {
+    k_sort_hist<<<ntiles, 256, 0, st>>>(w.skey[cur], n, p * 8, w.hist, ntiles);
+    scan_u32(w.hist, w.hist, 256 * ntiles, w.hist_tmp, st);
+    k_sort_scatter<<<ntiles, 256, 0, st>>>(w.skey[cur], w.sval[cur], w.skey[cur ^ 1], w.sval[cur ^ 1], n, p * 8,
+                                           w.hist, ntiles);
+    cur ^= 1;
+  }
+  if (cur != 0) {  // leave the result in buffer 0
+    cudaMemcpyAsync(w.skey[0], w.skey[1], (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(w.sval[0], w.sval[1], (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
+  }
+  k_bucket_bounds<<<(n + 255) / 256, 256, 0, st>>>(w.skey[0], n, w.dstart, w.dend);
+}
+
+// =============================================================================== K1a topic match
+// grid (W/256, n_bcast): thread = one 32-connection word of one broadcast message.
+__global__ void __launch_bounds__(256) k_match(DevState s, BatchIn b, Work w) {
+  __shared__ uint32_t sm[9];
+  const uint32_t j = blockIdx.y;
+  const uint32_t wd = blockIdx.x * kBlockWords + threadIdx.x;  // W is a multiple of 256
+  const uint32_t m = b.bcast_index[j];
+  const uint32_t toff = b.aux_off[m], tn = b.aux_len[m];
+  uint32_t word = 0;
+  for (uint32_t i = 0; i < tn; i++) {
+    const uint32_t t = b.topics[toff + i];
+    if (t < s.T) word |= s.sub[(size_t)t * s.W + wd];
+  }
+  if (b.flags[m] & 1) word &= ~s.brk[wd];  // to_users_only (connections/mod.rs:111)
+  w.B[(size_t)j * s.W + wd] = word;
+  uint32_t tot, ex = block256_excl_scan(__popc(word), &tot, sm);
+  w.wpre[(size_t)j * s.W + wd] = (uint16_t)ex;
+  if (threadIdx.x == 0) w.cnt[(size_t)j * s.nblk + blockIdx.x] = tot;
+}
+// one block per broadcast: exclusive prefix of the block counts, D_m
+__global__ void __launch_bounds__(256) k_match_base(DevState s, BatchIn b, Work w) {
+  __shared__ uint32_t sm[9];
+  const uint32_t j = blockIdx.x;
+  uint32_t carry = 0;
+  for (uint32_t bb = 0; bb < s.nblk; bb += 256) {
+    const uint32_t i = bb + threadIdx.x;
+    const uint32_t v = i < s.nblk ? w.cnt[(size_t)j * s.nblk + i] : 0;
+    uint32_t tot, ex = block256_excl_scan(v, &tot, sm);
+    if (i < s.nblk) w.base[(size_t)j * s.nblk + i] = ex + carry;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) w.D[b.bcast_index[j]] = carry;
+}
+void launch_match(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st) {
+  if (!b.n_bcast) return;
+  dim3 grid(s.W / kBlockWords, b.n_bcast);
+  k_match<<<grid, 256, 0, st>>>(s, b, w);
+  k_match_base<<<b.n_bcast, 256, 0, st>>>(s, b, w);
+}
+
+// =============================================================================== K1p plan
+__device__ __forceinline__ uint32_t frame_vec_bytes(uint32_t raw_len) { return (4u + raw_len + 15u) & ~15u; }
+__device__ __forceinline__ uint32_t frame_units(uint32_t raw_len) { return (4u + raw_len + kUnit - 1u) / kUnit; }
+
+__global__ void __launch_bounds__(256) k_plan_a(BatchIn b, Work w, uint32_t nblk) {
+  __shared__ uint32_t sm[9];
+  const uint32_t m = blockIdx.x * 256 + threadIdx.x;
+  const bool valid = m < b.n_msgs;
+  const uint32_t d = valid ? w.D[m] : 0;
+  const bool fat = d >= kFatMin;
+  uint32_t tiles = 0;
+  if (fat) {
+    const uint32_t nch = (frame_vec_bytes(b.raw_len[m]) + kChunkBytes - 1) / kChunkBytes;
+    tiles = nch * ((d + kTileRecipients - 1) / kTileRecipients);
+  }
+  uint32_t tot;
+  uint32_t e0 = block256_excl_scan(fat ? d : 0, &tot, sm);
+  if (threadIdx.x == 0) w.scan_tmp[blockIdx.x] = tot;
+  uint32_t e1 = block256_excl_scan(fat ? 0 : d, &tot, sm);
+  if (threadIdx.x == 0) w.scan_tmp[nblk + blockIdx.x] = tot;
+  uint32_t e2 = block256_excl_scan(tiles, &tot, sm);
+  if (threadIdx.x == 0) w.scan_tmp[2 * nblk + blockIdx.x] = tot;
+  if (valid) { w.eb_fat[m] = e0; w.eb_thin[m] = e1; w.tbase[m] = e2; }
+}
+__global__ void __launch_bounds__(256) k_plan_b(Work w, uint32_t nblk) {
+  __shared__ uint32_t sm[9];
+  uint32_t totals[3];
+  for (int q = 0; q < 3; q++) {
+    uint32_t* t = w.scan_tmp + (size_t)q * nblk;
+    uint32_t carry = 0;
+    for (uint32_t bb = 0; bb < nblk; bb += 256) {
+      const uint32_t i = bb + threadIdx.x;
+      const uint32_t v = i < nblk ? t[i] : 0;
+      uint32_t tot, ex = block256_excl_scan(v, &tot, sm);
+      if (i < nblk) t[i] = ex + carry;
+      carry += tot;
+    }
+    totals[q] = carry;
+  }
+  if (threadIdx.x == 0) {
+    w.stats->n_fat_entries = totals[0];
+    w.stats->n_thin_entries = totals[1];
+    w.stats->n_fat_tiles = totals[2];
+    w.stats->tile_cursor = 0;
+    if (totals[0] > w.cap_fat || totals[1] > w.cap_thin) w.stats->status = 1;  // PCDN_E2BIG
+  }
+}
+__global__ void __launch_bounds__(256) k_plan_c(BatchIn b, Work w, uint32_t nblk) {
+  const uint32_t m = blockIdx.x * 256 + threadIdx.x;
+  if (m < b.n_msgs) {
+    w.eb_fat[m] += w.scan_tmp[blockIdx.x];
+    w.eb_thin[m] += w.scan_tmp[nblk + blockIdx.x];
+    w.tbase[m] += w.scan_tmp[2 * nblk + blockIdx.x];
+  } else if (m == b.n_msgs) {
+    w.eb_fat[m] = w.stats->n_fat_entries;
+    w.eb_thin[m] = w.stats->n_thin_entries;
+    w.tbase[m] = w.stats->n_fat_tiles;
+  }
+}
+void launch_plan(const DevState&, const Work& w, const BatchIn& b, cudaStream_t st) {
+  const uint32_t nblk = (b.n_msgs + 255) / 256;
+  k_plan_a<<<nblk, 256, 0, st>>>(b, w, nblk);
+  k_plan_b<<<1, 256, 0, st>>>(w, nblk);
+  k_plan_c<<<(b.n_msgs + 1 + 255) / 256, 256, 0, st>>>(b, w, nblk);
+}
+
+// =============================================================================== K1b offsets
+struct ConnCursor {
+  uint32_t pt, us, bu;          // ring tail, units in use, units consumed by this batch
+  uint32_t s1_off, s1_units, s1_rec, s2_units, s2_rec;
+  uint32_t ovf, in2;
+  unsigned long long bytes;
+};
+// reserve `u` units for one record; records never straddle the ring end
+__device__ __forceinline__ uint32_t alloc_record(ConnCursor& k, uint32_t u, uint32_t R, uint32_t raw_len) {
+  if (k.ovf) return kOffInvalid;
+  const bool wrap = k.pt + u > R;
+  const uint32_t pad = wrap ? R - k.pt : 0, at = wrap ? 0 : k.pt;
+  if (u > R || k.us + pad + u > R) { k.ovf = 1; return kOffInvalid; }
+  k.us += pad + u;
+  k.bu += pad + u;
+  if (wrap && k.s1_rec) k.in2 = 1;
+  if (!k.in2) { if (!k.s1_rec) k.s1_off = at; k.s1_units += u; k.s1_rec++; }
+  else { k.s2_units += u; k.s2_rec++; }
+  k.pt = at + u;
+  k.bytes += 4ull + raw_len;
+  return at;
+}
+
+// Thread per connection.  Walks the batch in order (broadcast matches from the match words, direct
+// hits from the connection's sorted bucket), so a connection's records are laid out in batch order
+// (R9) with no atomics, and writes each (conn, offset) into the per-message scatter list at its
+// deterministic rank (block base + word prefix + lane rank).
+__global__ void __launch_bounds__(256) k_offsets(DevState s, BatchIn b, Work w, int has_direct, uint32_t max_conns) {
+  __shared__ uint32_t sm[9];
+  __shared__ unsigned long long red[2][8];
+  __shared__ uint32_t span_base;
+  if (w.stats->status) return;  // batch rejected (E2BIG): leave all cursors untouched
+  const uint32_t c = blockIdx.x * 256 + threadIdx.x;  // N is a multiple of 8192
+  const uint32_t wd = c >> 5, lane = c & 31, lt = (1u << lane) - 1u;
+  const uint32_t R = s.ring_units;
+  ConnCursor k;
+  k.pt = s.ptail[c]; k.us = s.used[c]; k.bu = 0;
+  k.s1_off = 0; k.s1_units = 0; k.s1_rec = 0; k.s2_units = 0; k.s2_rec = 0; k.ovf = 0; k.in2 = 0; k.bytes = 0;
+  uint32_t dp = 0, de = 0;
+  if (has_direct) { dp = w.dstart[c]; de = w.dend[c]; }
+  const uint32_t* dmsg = w.sval[0];
+
+  auto emit = [&](uint32_t m, uint32_t rank) {
+    const uint32_t len = b.raw_len[m];
+    const uint32_t off = alloc_record(k, frame_units(len), R, len);
+    if (w.D[m] >= kFatMin) w.efat[w.eb_fat[m] + rank] = make_uint2(c, off);
+    else w.ethin[w.eb_thin[m] + rank] = make_uint4(c, off, b.slot_off16[m], len);
+  };
+
+  for (uint32_t j = 0; j < b.n_bcast; j++) {
+    const uint32_t word = w.B[(size_t)j * s.W + wd];  // warp-uniform
+    if (word == 0) continue;                          // nobody in this warp: directs can wait
+    const uint32_t mb = b.bcast_index[j];
+    while (dp < de && dmsg[dp] < mb) { emit(dmsg[dp], 0); dp++; }
+    if ((word >> lane) & 1u) {
+      const uint32_t rank = w.base[(size_t)j * s.nblk + (wd / kBlockWords)] + w.wpre[(size_t)j * s.W + wd] +
+                            __popc(word & lt);
+      emit(mb, rank);
+    }
+  }
+  while (dp < de) { emit(dmsg[dp], 0); dp++; }
+
+  s.ptail[c] = k.pt;
+  s.used[c] = k.us;
+  w.batch_units[c] = k.bu;
+
+  // spans: one per contiguous run (two when the ring wrapped inside the batch)
+  const uint32_t nsp = (k.s1_rec ? 1u : 0u) + (k.s2_rec ? 1u : 0u);
+  uint32_t tot, ex = block256_excl_scan(nsp, &tot, sm);
+  if (threadIdx.x == 0) span_base = tot ? atomicAdd(&w.stats->n_spans, tot) : 0;
+  // block reduction of deliveries / bytes
+  unsigned long long nrec = k.s1_rec + k.s2_rec, by = k.bytes;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nrec += __shfl_xor_sync(0xffffffffu, nrec, o);
+    by += __shfl_xor_sync(0xffffffffu, by, o);
+  }
+  if (lane == 0) { red[0][threadIdx.x >> 5] = nrec; red[1][threadIdx.x >> 5] = by; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long a = 0, bb = 0;
+    for (int i = 0; i < 8; i++) { a += red[0][i]; bb += red[1][i]; }
+    if (a) { atomicAdd(&w.stats->n_deliveries, a); atomicAdd(&w.stats->bytes_out, bb); }
+  }
+  if (nsp) {
+    uint32_t at = span_base + ex;
+    if (k.s1_rec) w.spans[at++] = Span{c, k.s1_off * kUnit, k.s1_units * kUnit, k.s1_rec};
+    if (k.s2_rec) w.spans[at] = Span{c, 0, k.s2_units * kUnit, k.s2_rec};
+  }
+  if (k.ovf) {
+    uint32_t i = atomicAdd(&w.stats->n_overflow, 1u);
+    if (i < max_conns) w.overflow[i] = c;
+  }
+}
+void launch_offsets(const DevState& s, const Work& w, const BatchIn& b, bool has_direct, cudaStream_t st) {
+  k_offsets<<<s.N / 256, 256, 0, st>>>(s, b, w, has_direct ? 1 : 0, s.N);
+}
+
+// =============================================================================== K2a pack (fat)
+// Persistent CTAs pull tiles (message, frame chunk, group of <=1024 recipients) from a counter.
+// The chunk is staged ONCE per CTA into shared memory with a TMA bulk copy (mbarrier-completed),
+// the 4-byte hole at the front of the slot is overwritten with the big-endian length (the
+// cdn-proto framing, protocols/mod.rs:366-385), then every recipient gets the chunk:
+//   VARIANT 0: lanes keep their 16-byte pieces in registers and issue st.global.cs.v4 per recipient
+//   VARIANT 1: one TMA bulk store (shared → global) per recipient, one lane each
+template <int VARIANT>
+__global__ void __launch_bounds__(256) k_pack_fat(DevState s, BatchIn b, Work w) {
+  __shared__ __align__(128) uint8_t buf[kChunkBytes];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t t_info[8];  // tile, m, chunk, r0, r1, nbytes, need_load
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (w.stats->status) return;
+  const uint32_t ntiles = w.stats->n_fat_tiles;
+  if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  uint32_t phase = 0;
+  uint32_t staged_m = 0xFFFFFFFFu, staged_k = 0xFFFFFFFFu;  // meaningful in thread 0 only
+
+  for (;;) {
+    if (tid == 0) {
+      const uint32_t t = atomicAdd(&w.stats->tile_cursor, 1u);
+      t_info[0] = t;
+      if (t < ntiles) {
+        uint32_t lo = 0, hi = b.n_msgs;  // largest m with tbase[m] <= t
+        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (w.tbase[mid] <= t) lo = mid; else hi = mid; }
+        const uint32_t m = lo, ltile = t - w.tbase[m], d = w.D[m];
+        const uint32_t ngrp = (d + kTileRecipients - 1) / kTileRecipients;
+        const uint32_t ch = ltile / ngrp, grp = ltile % ngrp;
+        const uint32_t fb = frame_vec_bytes(b.raw_len[m]);
+        const uint32_t nbytes = min(kChunkBytes, fb - ch * kChunkBytes);
+        t_info[1] = m; t_info[2] = ch; t_info[3] = grp * kTileRecipients;
+        t_info[4] = min(d, (grp + 1) * kTileRecipients); t_info[5] = nbytes;
+        const uint32_t need = (m != staged_m || ch != staged_k) ? 1u : 0u;
+        t_info[6] = need;
+        if (need) {
+          mbar_arrive_expect_tx(&bar, nbytes);
+          bulk_g2s(buf, b.arena + (size_t)b.slot_off16[m] * 16 + (size_t)ch * kChunkBytes, nbytes, &bar);
+          staged_m = m; staged_k = ch;
+        }
+      }
+    }
+    __syncthreads();
+    if (t_info[0] >= ntiles) break;
+    const uint32_t m = t_info[1], ch = t_info[2], r0 = t_info[3], r1 = t_info[4], nbytes = t_info[5];
+    if (t_info[6]) {
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+      if (ch == 0) {  // fused framing: BE length prefix
+        if (tid == 0) {
+          *reinterpret_cast<uint32_t*>(buf) = bswap32(b.raw_len[m]);
+          if (VARIANT == 1) fence_proxy_async_smem();
+        }
+        __syncthreads();
+      }
+    }
+    const uint2* E = w.efat + w.eb_fat[m];
+    const size_t chunk_off = (size_t)ch * kChunkBytes;
+    const uint32_t nvec = nbytes >> 4;
+
+    if (VARIANT == 1) {
+      for (uint32_t r = r0 + tid; r < r1; r += 256) {
+        const uint2 ent = E[r];
+        if (ent.y != kOffInvalid)
+          bulk_s2g(s.rings + (size_t)ent.x * s.ring_bytes + (size_t)ent.y * kUnit + chunk_off, buf, nbytes);
+      }
+      bulk_commit();
+      bulk_wait_read0();  // smem may be overwritten by the next tile
+    } else if (nvec <= 128) {
+      // frame chunk fits 4 registers per lane: load once, then pure store stream
+      uint4 v0, v1, v2, v3;
+      const uint4* sb = reinterpret_cast<const uint4*>(buf);
+      v0 = lane < nvec ? sb[lane] : make_uint4(0, 0, 0, 0);
+      v1 = lane + 32 < nvec ? sb[lane + 32] : make_uint4(0, 0, 0, 0);
+      v2 = lane + 64 < nvec ? sb[lane + 64] : make_uint4(0, 0, 0, 0);
+      v3 = lane + 96 < nvec ? sb[lane + 96] : make_uint4(0, 0, 0, 0);
+      for (uint32_t r = r0 + warp * 32; r < r1; r += 8 * 32) {
+        const uint2 ent = (r + lane < r1) ? E[r + lane] : make_uint2(0, kOffInvalid);
+        const uint32_t cnt = min(32u, r1 - r);
+        for (uint32_t i = 0; i < cnt; i++) {
+          const uint32_t conn = __shfl_sync(0xffffffffu, ent.x, i), off = __shfl_sync(0xffffffffu, ent.y, i);
+          if (off == kOffInvalid) continue;
+          uint4* dst = reinterpret_cast<uint4*>(s.rings + (size_t)conn * s.ring_bytes + (size_t)off * kUnit + chunk_off);
+          if (lane < nvec) st_stream16(dst + lane, v0);
+          if (lane + 32 < nvec) st_stream16(dst + lane + 32, v1);
+          if (lane + 64 < nvec) st_stream16(dst + lane + 64, v2);
+          if (lane + 96 < nvec) st_stream16(dst + lane + 96, v3);
+        }
+      }
+    } else {
+      const uint4* sb = reinterpret_cast<const uint4*>(buf);
+      for (uint32_t r = r0 + warp * 32; r < r1; r += 8 * 32) {
+        const uint2 ent = (r + lane < r1) ? E[r + lane] : make_uint2(0, kOffInvalid);
+        const uint32_t cnt = min(32u, r1 - r);
+        for (uint32_t i = 0; i < cnt; i++) {
+          const uint32_t conn = __shfl_sync(0xffffffffu, ent.x, i), off = __shfl_sync(0xffffffffu, ent.y, i);
+          if (off == kOffInvalid) continue;
+          uint4* dst = reinterpret_cast<uint4*>(s.rings + (size_t)conn * s.ring_bytes + (size_t)off * kUnit + chunk_off);
+          for (uint32_t v = lane; v < nvec; v += 32) st_stream16(dst + v, sb[v]);
+        }
+      }
+    }
+    __syncthreads();  // all reads of buf / t_info done before thread 0 starts the next tile
+  }
+}
+
+// =============================================================================== K2b pack (thin)
+// Warp per scatter-list entry (messages with < kFatMin recipients, all direct messages): 16-byte
+// read-only loads from the frame slot, length prefix patched into the first vector, 16-byte stores.
+__global__ void __launch_bounds__(256) k_pack_thin(DevState s, BatchIn b, Work w) {
+  if (w.stats->status) return;
+  const uint32_t n = w.stats->n_thin_entries;
+  const uint32_t lane = lane_id();
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t e = gw; e < n; e += nw) {
+    const uint4 ent = w.ethin[e];
+    if (ent.y == kOffInvalid) continue;
+    const uint4* src = reinterpret_cast<const uint4*>(b.arena + (size_t)ent.z * 16);
+    uint4* dst = reinterpret_cast<uint4*>(s.rings + (size_t)ent.x * s.ring_bytes + (size_t)ent.y * kUnit);
+    const uint32_t nvec = (4u + ent.w + 15u) >> 4;
+    const uint32_t hdr = bswap32(ent.w);
+    for (uint32_t v = lane; v < nvec; v += 128) {
+      uint4 x0, x1, x2, x3;
+      const bool p1 = v + 32 < nvec, p2 = v + 64 < nvec, p3 = v + 96 < nvec;
+      x0 = ld_nc16(src + v);
+      if (p1) x1 = ld_nc16(src + v + 32);
+      if (p2) x2 = ld_nc16(src + v + 64);
+      if (p3) x3 = ld_nc16(src + v + 96);
+      if (v == 0) x0.x = hdr;
+      st_stream16(dst + v, x0);
+      if (p1) st_stream16(dst + v + 32, x1);
+      if (p2) st_stream16(dst + v + 64, x2);
+      if (p3) st_stream16(dst + v + 96, x3);
+    }
+  }
+}
+
+int pack_setup() { return 0; }
+
+void launch_pack(const DevState& s, const Work& w, const BatchIn& b, uint32_t variant, int n_sms, cudaStream_t st) {
+  const uint32_t ctas_per_sm = (variant >> 8) ? (variant >> 8) : 4;
+  const uint32_t grid = (uint32_t)n_sms * ctas_per_sm;
+  if ((variant & 0xFF) == 1) k_pack_fat<1><<<grid, 256, 0, st>>>(s, b, w);
+  else k_pack_fat<0><<<grid, 256, 0, st>>>(s, b, w);
+  k_pack_thin<<<(uint32_t)n_sms * 8, 256, 0, st>>>(s, b, w);
+}
+
+// =============================================================================== release
+__global__ void k_release(DevState s, const uint32_t* __restrict__ batch_units) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < s.N) {
+    const uint32_t u = batch_units[c];
+    if (u) s.used[c] -= u;
+  }
+}
+void launch_release(const DevState& s, const uint32_t* batch_units, cudaStream_t st) {
+  k_release<<<(s.N + 255) / 256, 256, 0, st>>>(s, batch_units);
+}
+
+}  // namespace pcdn

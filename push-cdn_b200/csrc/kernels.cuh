@@ -1,0 +1,124 @@
+// kernels.cuh — device-side data layout and kernel launchers of the fan-out engine (sm_100a).
+//
+// Per batch the engine runs (all on one stream, no host round trip in between):
+//   K3  direct_lookup   warp per direct message: cuckoo probe pubkey → route → target connection
+//       sort            stable LSD radix sort of (target conn, msg index) → per-connection buckets
+//   K1a topic_match     OR of subscription-bitmap rows per broadcast → match words + popcount ranks
+//   K1p plan            D_m per message, fat/thin class, scatter-list bases, pack tiles (prefix sums)
+//   K1b offsets         thread per connection walks the batch IN ORDER (R9), assigns ring offsets
+//                       and emits the compacted (connection, offset) scatter list per message
+//   K2a pack_fat        CTA stages a frame chunk in shared memory with one TMA bulk copy, patches
+//                       the big-endian length prefix, replicates it to every recipient (16 B stores
+//                       or TMA bulk stores)
+//   K2b pack_thin       warp per (message, recipient) for messages with few recipients
+//   K4  apply_updates   scatter of changed table words/slots (subscribe, add/remove, direct map)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hash.h"
+
+namespace pcdn {
+
+constexpr uint32_t kUnit = 32;               // record alignment in ring (bytes) = PCDN_RECORD_ALIGN
+constexpr uint32_t kOffInvalid = 0xFFFFFFFFu;
+constexpr uint32_t kConnNone = 0xFFFFFFFFu;
+constexpr uint32_t kFatMin = 32;             // >= this many recipients → staged (fat) path
+constexpr uint32_t kChunkBytes = 16384;      // shared-memory staging chunk of the fat path
+constexpr uint32_t kTileRecipients = 1024;   // recipients per fat tile
+constexpr uint32_t kBlockWords = 256;        // bitmap words per match block (8192 connections)
+
+// device-resident routing state + rings
+struct DevState {
+  uint32_t* sub;         // [T][W] subscription bitmap, row = topic
+  uint32_t* brk;         // [W]    1 = connection is a peer broker
+  uint32_t* owner_conn;  // [max_owners] broker owner index → its connection (or NONE)
+  CuckooEntry* cuckoo;   // [nbuckets*4]
+  uint8_t* keys;         // [max_keys][key_stride]
+  uint32_t* ptail;       // [N] next free unit in the connection's ring
+  uint32_t* used;        // [N] units not yet released
+  uint8_t* rings;        // [max_conns][ring_bytes]
+  uint32_t N, W, T, nblk;
+  uint32_t bucket_mask, key_stride;
+  uint32_t ring_units;   // ring_bytes / 32
+  uint64_t ring_bytes;
+  uint64_t seed;
+};
+
+// inputs of one batch (device pointers) — same meaning as pcdn_device_batch
+struct BatchIn {
+  uint32_t n_msgs, n_bcast;
+  const uint8_t* arena;
+  const uint8_t* kind;
+  const uint8_t* flags;
+  const uint32_t* slot_off16;
+  const uint32_t* raw_len;
+  const uint32_t* aux_off;
+  const uint32_t* aux_len;
+  const uint16_t* topics;
+  const uint32_t* bcast_index;
+};
+
+struct BatchStats {
+  unsigned long long n_deliveries;
+  unsigned long long bytes_out;
+  uint32_t n_spans;
+  uint32_t n_overflow;
+  uint32_t n_direct_dropped;
+  uint32_t status;          // 0 ok, 1 = scatter list capacity exceeded (E2BIG)
+  uint32_t n_fat_entries;
+  uint32_t n_thin_entries;
+  uint32_t n_fat_tiles;
+  uint32_t tile_cursor;
+};
+
+struct Span { uint32_t conn, ring_off, len, n_records; };
+
+// per-slot scratch
+struct Work {
+  uint32_t* B;           // [max_bcast][W] match words
+  uint16_t* wpre;        // [max_bcast][W] exclusive popcount prefix inside the 256-word block
+  uint32_t* cnt;         // [max_bcast][nblk]
+  uint32_t* base;        // [max_bcast][nblk] exclusive prefix of cnt over blocks
+  uint32_t* D;           // [max_msgs] recipients per message
+  uint32_t* dconn;       // [max_msgs] direct: target connection or NONE
+  uint32_t* eb_fat;      // [max_msgs+1] scatter-list base per message (fat list)
+  uint32_t* eb_thin;     // [max_msgs+1]
+  uint32_t* tbase;       // [max_msgs+1] fat tile base per message
+  uint32_t* scan_tmp;    // [3 * nscanblk] block totals of the plan scan
+  uint2* efat;           // [cap_fat]  {conn, ring offset in units}
+  uint4* ethin;          // [cap_thin] {conn, ring offset in units, slot_off16, raw_len}
+  uint32_t cap_fat, cap_thin;
+  // direct buckets
+  uint32_t* skey[2];     // [max_msgs] sort keys (target conn, N = none)
+  uint32_t* sval[2];     // [max_msgs] msg index
+  uint32_t* hist;        // [256 * ntiles]
+  uint32_t* hist_tmp;    // scan scratch
+  uint32_t* dstart;      // [N+1]
+  uint32_t* dend;        // [N+1]
+  // outputs
+  uint32_t* batch_units; // [N] units consumed by this batch per connection (for release)
+  Span* spans;           // [2*max_conns]
+  uint32_t* overflow;    // [max_conns]
+  BatchStats* stats;
+};
+
+// table-update journal records (K4)
+struct Upd32 { uint32_t arr, idx, val; };   // arr: 0 sub, 1 brk, 2 owner_conn
+struct UpdSlot { uint32_t slot; CuckooEntry e; };
+
+// ---- launchers (host functions defined in kernels.cu) -------------------------------------------
+void launch_apply_updates(const DevState& s, const Upd32* u32, uint32_t n32, const UpdSlot* us,
+                          uint32_t nslot, const uint32_t* key_slots, const uint8_t* key_bytes,
+                          uint32_t nkeys, cudaStream_t st);
+void launch_batch_begin(const DevState& s, const Work& w, const BatchIn& b, bool has_direct, cudaStream_t st);
+void launch_direct(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st);
+void launch_match(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st);
+void launch_plan(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st);
+void launch_offsets(const DevState& s, const Work& w, const BatchIn& b, bool has_direct, cudaStream_t st);
+void launch_pack(const DevState& s, const Work& w, const BatchIn& b, uint32_t variant, int n_sms, cudaStream_t st);
+void launch_release(const DevState& s, const uint32_t* batch_units, cudaStream_t st);
+size_t sort_tiles(uint32_t n);
+int pack_setup();  // sets kernel attributes (dynamic smem); returns cudaError
+
+}  // namespace pcdn

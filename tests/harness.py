@@ -174,14 +174,8 @@ class EngineBackend:
         self.e.handle_direct_message(recipient, raw, to_user_only)
 
     def flush(self):
-        bid = self.e.flush()
-        if not bid:
-            return None
-        res = self.e.poll(bid)
-        for conn, frames in self.e.collect_frames(res).items():
+        for conn, frames in self.e.drain().items():
             self._frames.setdefault(conn, []).extend(frames)
-        self.e.release_batch(bid)
-        return res
 
     def take_frames(self, conn):
         self.flush()

@@ -1,0 +1,224 @@
+"""CPU tests of the product's host side through the C ABI with a host-only engine (device=-1):
+the `Connections` mirror (bitmap / route table the GPU kernels read) against the oracle, the ingress
+frame parser against the oracle's capnp restatement, and the ABI surface itself.  No compute calls.
+"""
+import ctypes as C
+import os
+import random
+import re
+
+import pytest
+
+from oracle import oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(pcdn):
+    hdr = open(os.path.join(ROOT, "include", "pcdn_fanout.h")).read()
+    declared = set(re.findall(r"\b(pcdn_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"pcdn_engine"}
+    assert len(declared) >= 30
+    L = C.CDLL(pcdn.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in pcdn_fanout.h but not exported"
+    assert set(pcdn.ABI) == declared, (set(pcdn.ABI) ^ declared)
+
+
+def test_no_cpu_data_path(pcdn):
+    """the product must fail loudly without a device instead of falling back"""
+    e = pcdn.Engine(device=-1, max_conns=64)
+    e.add_user(b"k", [0])
+    with pytest.raises(pcdn.PcdnError) as ei:
+        e.handle_broadcast_message([0], b"12345678")
+    assert ei.value.code == -3
+    with pytest.raises(pcdn.PcdnError):
+        e.handle_direct_message(b"k", b"12345678")
+    assert e.user_receive(b"k", orc.broadcast_frame([0], b"x")) == -3
+
+
+def test_product_does_not_import_oracle(pcdn):
+    src = open(os.path.join(ROOT, "push-cdn_b200", "__init__.py")).read()
+    assert "oracle" not in src.replace("oracle's", "")
+    for f in os.listdir(os.path.join(ROOT, "push-cdn_b200", "csrc")):
+        assert "oracle" not in open(os.path.join(ROOT, "push-cdn_b200", "csrc", f)).read().lower(), f
+
+
+def _mk(pcdn, **kw):
+    cfg = dict(device=-1, max_conns=512, max_topics=256, max_keys=2048, max_key_len=128, identity="me/me")
+    cfg.update(kw)
+    return pcdn.Engine(**cfg), orc.Oracle("me/me")
+
+
+class Pair:
+    """drives the product's host mirror and the oracle with the same calls; maps connection ids"""
+
+    def __init__(self, pcdn, **kw):
+        self.e, self.o = _mk(pcdn, **kw)
+        self.map = {}  # engine conn -> oracle conn
+
+    def add_user(self, k, t):
+        self.map[self.e.add_user(k, t)] = self.o.add_user(k, t)
+
+    def add_broker(self, b):
+        self.map[self.e.add_broker(b)] = self.o.add_broker(b)
+
+    def both(self, name, *a):
+        getattr(self.e, name)(*a)
+        getattr(self.o, name)(*a)
+
+    def check(self, keys, rng):
+        for _ in range(6):
+            topics = [rng.randrange(8) for _ in range(rng.randrange(0, 4))]
+            for flag in (False, True):
+                got = sorted(self.map[c] for c in self.e.debug_interested(topics, flag))
+                assert got == self.o.interested(topics, flag), (topics, flag)
+        for k in keys:
+            kind, conn = self.e.debug_route(k)
+            okind, oconn = self.o.route(k)
+            assert kind == okind, k
+            assert (self.map[conn] if conn >= 0 else -1) == oconn, k
+        assert self.e.num_users()[0] == self.o.num_users()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_connections_mirror_matches_oracle(pcdn, seed):
+    """random Connections::* call sequences (mod.rs:252-388 + apply_user_sync :154): the product's
+    bitmap and route table resolve exactly like the reference's maps"""
+    rng = random.Random(seed)
+    p = Pair(pcdn)
+    keys = [bytes([i]) * rng.choice([1, 8, 33, 128]) for i in range(24)]
+    brokers = [f"b{i}/p{i}" for i in range(4)]
+    for step in range(400):
+        op = rng.randrange(10)
+        k = rng.choice(keys)
+        b = rng.choice(brokers)
+        t = [rng.randrange(8) for _ in range(rng.randrange(0, 4))]
+        if op == 0:
+            p.add_user(k, t)
+        elif op == 1:
+            p.both("remove_user", k)
+        elif op == 2:
+            p.both("subscribe_user_to", k, t)
+        elif op == 3:
+            p.both("unsubscribe_user_from", k, t)
+        elif op == 4:
+            p.add_broker(b)
+        elif op == 5:
+            p.both("remove_broker", b)
+        elif op == 6:
+            p.both("subscribe_broker_to", b, t)
+        elif op == 7:
+            p.both("unsubscribe_broker_from", b, t)
+        else:
+            ents = [(rng.choice(keys), rng.randrange(1, 5), rng.choice(brokers + ["me/me", None]))
+                    for _ in range(rng.randrange(1, 4))]
+            # one entry per key (a remote map is a map)
+            ents = list({e[0]: e for e in ents}.values())
+            p.both("apply_user_sync", rng.choice(brokers), ents)
+        if step % 20 == 0:
+            p.check(keys, rng)
+    p.check(keys, rng)
+
+
+def test_add_user_kicks_same_key_and_reuses_ids(pcdn):
+    e, _ = _mk(pcdn, max_conns=4)
+    a = e.add_user(b"A", [1])
+    b = e.add_user(b"A", [2])       # same key: old connection kicked (mod.rs:289-290)
+    assert e.num_users() == (1, 0)
+    assert e.debug_interested([1]) == [] and e.debug_interested([2]) == [b]
+    for i in range(3):
+        e.add_user(b"u%d" % i, [])
+    with pytest.raises(pcdn.PcdnError) as ei:
+        e.add_user(b"overflow", [])
+    assert ei.value.code == -5       # PCDN_ENOSPC, state unchanged
+    assert e.num_users() == (4, 0) and e.debug_route(b"overflow") == (0, -1)
+    e.remove_user(b"u0")
+    assert e.add_user(b"again", [7]) in (a, b, 0, 1, 2, 3)
+
+
+def test_key_length_limit(pcdn):
+    e, _ = _mk(pcdn, max_key_len=32)
+    e.add_user(b"x" * 32, [])
+    with pytest.raises(pcdn.PcdnError) as ei:
+        e.add_user(b"x" * 33, [])
+    assert ei.value.code == -6
+
+
+def test_cuckoo_table_many_keys(pcdn):
+    """fill the direct map to its configured capacity; every key resolves, erased keys do not"""
+    n = 20000
+    e = pcdn.Engine(device=-1, max_conns=n, max_keys=n, max_key_len=16)
+    rng = random.Random(1)
+    keys = [rng.getrandbits(128).to_bytes(16, "little") for _ in range(n)]
+    conns = [e.add_user(k, []) for k in keys]
+    for k, c in zip(keys[::97], conns[::97]):
+        assert e.debug_route(k) == (1, c)
+    for k in keys[:5000]:
+        e.remove_user(k)
+    for k in keys[:5000:53]:
+        assert e.debug_route(k) == (0, -1)
+    for k, c in zip(keys[5000::101], conns[5000::101]):
+        assert e.debug_route(k) == (1, c)
+
+
+def test_parse_frame_matches_oracle(pcdn):
+    rng = random.Random(3)
+    for _ in range(300):
+        kind = rng.choice([3, 4, 5, 6, 7, 8])
+        f0 = bytes(rng.randrange(256) for _ in range(rng.choice([0, 1, 2, 8, 9, 128])))
+        pl = bytes(rng.randrange(256) for _ in range(rng.choice([0, 1, 7, 8, 100, 9000])))
+        if kind in (5, 6):
+            raw = orc.serialize(kind, f0)
+        elif kind in (7, 8):
+            raw = orc.serialize(kind, b"", pl)
+        else:
+            raw = orc.serialize(kind, f0, pl)
+        k, topics, (off, ln) = pcdn.parse_frame(raw)
+        ok, of0, opl = orc.deserialize(raw)
+        assert k == ok == kind
+        want = opl if kind in (7, 8) else of0
+        assert raw[off:off + ln] == want
+        if kind in (4, 5, 6):
+            assert bytes(topics) == of0[:256]
+
+
+def test_parse_frame_rejects_what_the_oracle_rejects(pcdn):
+    rng = random.Random(4)
+    good = [orc.broadcast_frame([0, 1], b"payload" * 3), orc.direct_frame(b"k" * 8, b"m" * 40),
+            orc.broadcast_frame([1], bytes(9000))]
+    n_bad = 0
+    for _ in range(3000):
+        raw = bytearray(rng.choice(good))
+        for _ in range(rng.randrange(1, 4)):
+            raw[rng.randrange(min(len(raw), 64))] = rng.randrange(256)
+        if rng.random() < 0.2:
+            raw = raw[: rng.randrange(len(raw))]
+        raw = bytes(raw)
+        want = orc.deserialize(raw)
+        try:
+            k, topics, (off, ln) = pcdn.parse_frame(raw)
+        except pcdn.PcdnError as ex:
+            assert ex.code == -7
+            assert want is None, raw.hex()
+            n_bad += 1
+            continue
+        assert want is not None, raw.hex()
+        assert k == want[0]
+        if k in (3, 4, 5, 6):
+            assert raw[off:off + ln] == want[1]
+    assert n_bad > 100
+
+
+def test_prune_and_dispatch_errors(pcdn):
+    """user_receive_loop error paths (user/handler.rs:133,142,153,160) need no device"""
+    e = pcdn.Engine(device=-1, max_conns=16, n_valid_topics=2)
+    e.add_user(b"u", [0])
+    assert e.user_receive(b"u", b"\x01\x02") == -7                        # Error::Deserialize
+    assert e.user_receive(b"u", orc.serialize(orc.KIND_SUBSCRIBE, bytes([9]))) == -8   # prune → Err
+    assert e.user_receive(b"u", orc.serialize(orc.KIND_USER_SYNC, b"", b"x")) == -9    # invalid kind
+    assert e.user_receive(b"u", orc.serialize(orc.KIND_SUBSCRIBE, bytes([1, 1, 9]))) == 0
+    assert e.debug_interested([1]) == [0]
+    assert e.user_receive(b"u", orc.serialize(orc.KIND_UNSUBSCRIBE, bytes([1]))) == 0
+    assert e.debug_interested([1]) == []
+    assert e.user_receive(b"u", orc.broadcast_frame([7], b"x")) == -8      # only invalid topics
