@@ -1,0 +1,180 @@
+// ORACLE — test/bench infrastructure only (CPU baseline; never linked into the product).
+//
+// cpu_broker_timed.cpp — timed C++ restatement of the reference cdn-broker's CPU broadcast path,
+// used as bench.py's `cpu_baseline` and `--impl reference` arm because the reference itself (Rust)
+// cannot be built here.  It reproduces the *shape* of the reference's work per message:
+//
+//  stage 1  Connections::get_interested_by_topic (cdn-broker/src/connections/mod.rs:94-124):
+//           RelationalMap::get_keys_by_value clones every subscribed key (Arc bump) into a Vec
+//           (relational_map.rs:39-47), each is inserted into a HashSet<UserPublicKey> (std SipHash-1-3
+//           over the key bytes), the set is collected into a Vec.
+//  stage 2  handle_broadcast_message's sequential loop (tasks/broker/handler.rs:268-271): per
+//           recipient try_send_to_user = HashMap<UserPublicKey,Connection> probe (SipHash) +
+//           Connection clone + Bytes clone (2 Arc bumps) + unbounded channel push
+//           (tasks/user/sender.rs:16-32, cdn-proto/src/connection/protocols/mod.rs:239-251).
+//           One receive loop handles one sender's messages sequentially; different senders run on
+//           different worker threads — here: one thread per in-flight message, all host threads.
+//  stage 3  per-connection writer tasks (protocols/mod.rs:156-186,354-394): pop, write u32 BE length,
+//           write the bytes (= one memcpy of the frame per recipient into that connection's buffer),
+//           parallel over all host threads.
+//
+// It is deliberately generous to the CPU: no tokio scheduling, no syscalls/TLS, no allocator
+// contention between stages, perfect static load balance.
+//
+// usage: cpu_broker_timed <n_conns> <payload_bytes> <msgs_per_step> <steps> <warmup> <threads>
+// prints one JSON object.
+#include <atomic>
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+// SipHash-1-3 (Rust's DefaultHasher) over a byte string
+static inline uint64_t rotl(uint64_t x, int b) { return (x << b) | (x >> (64 - b)); }
+struct Sip13 {
+  uint64_t k0 = 0x0706050403020100ULL, k1 = 0x0f0e0d0c0b0a0908ULL;
+  size_t operator()(const std::shared_ptr<const std::string>& sp) const {
+    const std::string& s = *sp;
+    uint64_t v0 = k0 ^ 0x736f6d6570736575ULL, v1 = k1 ^ 0x646f72616e646f6dULL, v2 = k0 ^ 0x6c7967656e657261ULL,
+             v3 = k1 ^ 0x7465646279746573ULL;
+    auto round = [&]() {
+      v0 += v1; v1 = rotl(v1, 13); v1 ^= v0; v0 = rotl(v0, 32);
+      v2 += v3; v3 = rotl(v3, 16); v3 ^= v2;
+      v0 += v3; v3 = rotl(v3, 21); v3 ^= v0;
+      v2 += v1; v1 = rotl(v1, 17); v1 ^= v2; v2 = rotl(v2, 32);
+    };
+    const uint8_t* p = (const uint8_t*)s.data();
+    size_t n = s.size(), i = 0;
+    for (; i + 8 <= n; i += 8) { uint64_t m; memcpy(&m, p + i, 8); v3 ^= m; round(); v0 ^= m; }
+    uint64_t b = (uint64_t)n << 56;
+    for (size_t j = 0; i + j < n; j++) b |= (uint64_t)p[i + j] << (8 * j);
+    v3 ^= b; round(); v0 ^= b;
+    v2 ^= 0xff; round(); round(); round();
+    return (size_t)(v0 ^ v1 ^ v2 ^ v3);
+  }
+};
+struct KeyEq {
+  bool operator()(const std::shared_ptr<const std::string>& a, const std::shared_ptr<const std::string>& b) const {
+    return *a == *b;
+  }
+};
+using Key = std::shared_ptr<const std::string>;       // UserPublicKey = Arc<Vec<u8>>
+using Bytes = std::shared_ptr<const std::vector<uint8_t>>;  // Bytes = Arc<Vec<u8>> (+permit)
+
+struct Connection {  // the sending half: an unbounded MPSC queue
+  std::mutex mu;
+  std::vector<Bytes> q;
+};
+
+int main(int argc, char** argv) {
+  if (argc < 7) { fprintf(stderr, "usage: %s n_conns payload msgs_per_step steps warmup threads\n", argv[0]); return 2; }
+  const size_t N = strtoull(argv[1], 0, 10), K = strtoull(argv[2], 0, 10), M = strtoull(argv[3], 0, 10);
+  const int steps = atoi(argv[4]), warmup = atoi(argv[5]);
+  int T = atoi(argv[6]);
+  if (T <= 0) T = (int)std::thread::hardware_concurrency();
+  if (T <= 0) T = 1;
+  const size_t L = 8 * (6 + 1 + (K + 7) / 8), F = 4 + L;  // single-segment Broadcast, one topic
+  const size_t slot = (F + 63) / 64 * 64, depth = 2;
+
+  // state: users map, topic 0 → set of keys (all subscribed), 32-byte keys
+  std::unordered_map<Key, std::shared_ptr<Connection>, Sip13, KeyEq> users;
+  std::unordered_set<Key, Sip13, KeyEq> topic0;
+  std::vector<std::shared_ptr<Connection>> conns(N);
+  users.reserve(N * 2); topic0.reserve(N * 2);
+  for (size_t i = 0; i < N; i++) {
+    std::string k(32, 0);
+    uint64_t x = i * 0x9E3779B97F4A7C15ULL + 1;
+    for (int j = 0; j < 4; j++) { x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ULL; memcpy(&k[j * 8], &x, 8); }
+    Key key = std::make_shared<const std::string>(std::move(k));
+    conns[i] = std::make_shared<Connection>();
+    users.emplace(key, conns[i]);
+    topic0.insert(key);
+  }
+  std::vector<uint8_t> out(N * slot * depth);  // per-connection output buffers (stand-in for sockets)
+  std::vector<uint32_t> wr(N, 0);
+
+  std::vector<Bytes> msgs(M);
+  for (size_t m = 0; m < M; m++) {
+    auto v = std::make_shared<std::vector<uint8_t>>(L);
+    for (size_t i = 0; i < L; i++) (*v)[i] = (uint8_t)(i * 131 + m);
+    msgs[m] = v;
+  }
+
+  double t12 = 0, t3 = 0;
+  uint64_t deliveries = 0, bytes = 0, checksum = 0;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  for (int it = 0; it < warmup + steps; it++) {
+    auto a = now();
+    {  // stages 1+2: one thread per in-flight message
+      std::atomic<size_t> next{0};
+      std::vector<std::thread> th;
+      for (int t = 0; t < T; t++)
+        th.emplace_back([&] {
+          for (;;) {
+            size_t m = next.fetch_add(1);
+            if (m >= M) break;
+            // stage 1
+            std::vector<Key> cloned;
+            cloned.reserve(topic0.size());
+            for (const Key& k : topic0) cloned.push_back(k);            // get_keys_by_value: clone
+            std::unordered_set<Key, Sip13, KeyEq> recipients;
+            for (Key& k : cloned) recipients.insert(std::move(k));     // HashSet insert
+            std::vector<Key> list(recipients.begin(), recipients.end());  // into_iter().collect()
+            // stage 2
+            for (const Key& k : list) {
+              auto it2 = users.find(k);                                  // get_user_connection
+              if (it2 == users.end()) continue;
+              std::shared_ptr<Connection> c = it2->second;               // Connection clone
+              Bytes b = msgs[m];                                         // message.clone()
+              std::lock_guard<std::mutex> g(c->mu);
+              c->q.push_back(std::move(b));                              // send_message_raw
+            }
+          }
+        });
+      for (auto& x : th) x.join();
+    }
+    auto b = now();
+    {  // stage 3: writer tasks, connections partitioned over threads
+      std::vector<std::thread> th;
+      std::vector<uint64_t> cs(T, 0), dl(T, 0), by(T, 0);
+      for (int t = 0; t < T; t++)
+        th.emplace_back([&, t] {
+          size_t lo = N * t / T, hi = N * (t + 1) / T;
+          for (size_t c = lo; c < hi; c++) {
+            Connection& cn = *conns[c];
+            for (Bytes& msg : cn.q) {
+              uint8_t* dst = &out[(c * depth + (wr[c]++ % depth)) * slot];
+              uint32_t len = (uint32_t)msg->size();
+              dst[0] = len >> 24; dst[1] = len >> 16; dst[2] = len >> 8; dst[3] = len;  // write_u32 (BE)
+              memcpy(dst + 4, msg->data(), len);                                          // write_all
+              cs[t] += dst[4 + (len >> 1)];
+              dl[t]++; by[t] += 4 + len;
+            }
+            cn.q.clear();
+          }
+        });
+      for (auto& x : th) x.join();
+      if (it >= warmup) for (int t = 0; t < T; t++) { deliveries += dl[t]; bytes += by[t]; checksum += cs[t]; }
+    }
+    auto c = now();
+    if (it >= warmup) {
+      t12 += std::chrono::duration<double>(b - a).count();
+      t3 += std::chrono::duration<double>(c - b).count();
+    }
+  }
+  double sec = t12 + t3;
+  printf("{\"n_conns\": %zu, \"payload\": %zu, \"frame_bytes\": %zu, \"msgs_per_step\": %zu, \"steps\": %d, \"threads\": %d, "
+         "\"deliveries\": %llu, \"bytes\": %llu, \"seconds\": %.6f, \"stage12_s\": %.6f, \"stage3_s\": %.6f, "
+         "\"gbps\": %.4f, \"deliveries_per_s\": %.1f, \"checksum\": %llu}\n",
+         N, K, F, M, steps, T, (unsigned long long)deliveries, (unsigned long long)bytes, sec, t12, t3,
+         bytes / sec / 1e9, deliveries / sec, (unsigned long long)checksum);
+  return 0;
+}

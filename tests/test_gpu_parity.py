@@ -1,0 +1,255 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle on the same seeded
+inputs.  Bit-exact: every connection must receive exactly the oracle's frames, in the oracle's
+order (integer/byte work — no tolerance).  Run with `pytest -m gpu` on a B200.
+"""
+import random
+
+import pytest
+
+import scenarios
+from harness import EngineBackend
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------ the reference's own scenarios
+@pytest.mark.parametrize("scenario", scenarios.ALL, ids=lambda f: f.__name__)
+def test_reference_scenario_on_gpu(pcdn, scenario):
+    scenario(EngineBackend(pcdn))
+
+
+@pytest.mark.parametrize("scenario", [scenarios.test_broadcast_user, scenarios.test_fifo_order],
+                         ids=lambda f: f.__name__)
+def test_reference_scenario_bulk_store_variant(pcdn, scenario):
+    scenario(EngineBackend(pcdn, pack_variant=1))
+
+
+# ------------------------------------------------------------------ differential harness
+class World:
+    """drives engine and oracle with identical calls and compares delivered frames"""
+
+    def __init__(self, pcdn, n_valid_topics=0, **cfg):
+        kw = dict(max_conns=8192, max_topics=256, max_keys=16384, ring_bytes_per_conn=1 << 18,
+                  max_batch_msgs=4096, max_batch_bcast=512, max_batch_bytes=32 << 20,
+                  max_batch_deliveries=1 << 20, identity="/", n_valid_topics=n_valid_topics)
+        kw.update(cfg)
+        self.pcdn = pcdn
+        self.e = pcdn.Engine(**kw)
+        self.o = orc.Oracle("/", n_valid_topics)
+        self.map = {}
+        self.taken = {}
+
+    def add_user(self, key, topics):
+        c = self.e.add_user(key, topics)
+        self.map[c] = self.o.add_user(key, topics)
+        return c
+
+    def add_broker(self, ident, topics=()):
+        c = self.e.add_broker(ident)
+        self.map[c] = self.o.add_broker(ident)
+        if topics:
+            self.both("subscribe_broker_to", ident, list(topics))
+        return c
+
+    def both(self, name, *a):
+        getattr(self.e, name)(*a)
+        getattr(self.o, name)(*a)
+
+    def bcast(self, topics, raw, to_users_only=False):
+        self.both("handle_broadcast_message", topics, raw, to_users_only)
+
+    def direct(self, rcpt, raw, to_user_only=False):
+        self.both("handle_direct_message", rcpt, raw, to_user_only)
+
+    def expect(self):
+        """oracle frames per ENGINE conn id since the last call"""
+        out = {}
+        for ec, oc in self.map.items():
+            fr = self.o.frames(oc)
+            k = self.taken.get(oc, 0)
+            if len(fr) > k:
+                out[ec] = fr[k:]
+            self.taken[oc] = len(fr)
+        return out
+
+    def check(self):
+        got = self.e.drain()
+        want = self.expect()
+        assert set(got) == set(want), (sorted(set(got) ^ set(want))[:10])
+        for c in want:
+            assert len(got[c]) == len(want[c]), (c, len(got[c]), len(want[c]))
+            for i, (g, w) in enumerate(zip(got[c], want[c])):
+                assert g == w, f"conn {c} frame {i}: {len(g)} vs {len(w)} bytes"
+        return sum(len(v) for v in want.values())
+
+
+def payload(rng, n):
+    return bytes(rng.getrandbits(8) for _ in range(min(n, 64))) * (n // 64 + 1)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_mixed_batches(pcdn, seed, variant):
+    """users + peer brokers, multi-topic broadcasts (fat and thin recipient sets), directs to local,
+    remote and unknown keys, frame sizes from 0 B to 3 staging chunks, several batches"""
+    rng = random.Random(seed)
+    w = World(pcdn, pack_variant=variant)
+    keys = []
+    for i in range(1500):
+        k = rng.getrandbits(64).to_bytes(8, "little") * rng.choice([1, 4, 16])
+        keys.append(k)
+        # topic 0 is popular (fat path), topics 10+ are rare (thin path)
+        t = [x for x in range(16) if rng.random() < (0.6 if x == 0 else 0.1 if x < 10 else 0.004)]
+        w.add_user(k, t)
+    for b in range(3):
+        w.add_broker(f"b{b}/p{b}", [rng.randrange(16) for _ in range(3)])
+    remote = [b"remote%d" % i for i in range(8)]
+    w.both("apply_user_sync", "b1/p1", [(k, 1, "b1/p1") for k in remote])
+    total = 0
+    for batch in range(4):
+        for j in range(rng.randrange(20, 120)):
+            r = rng.random()
+            size = rng.choice([0, 1, 11, 12, 13, 100, 1024, 4096, 16000, 16384, 20000, 40000]) if rng.random() < 0.5 \
+                else rng.randrange(0, 3000)
+            if r < 0.55:
+                topics = [rng.randrange(16) for _ in range(rng.randrange(1, 4))]
+                if rng.random() < 0.4:
+                    topics.append(0)
+                w.bcast(topics, orc.broadcast_frame([t for t in topics], payload(rng, size)), rng.random() < 0.3)
+            else:
+                rc = rng.choice(keys) if rng.random() < 0.7 else rng.choice(remote + [b"nobody", b""])
+                w.direct(rc, orc.direct_frame(rc, payload(rng, size)), rng.random() < 0.3)
+        if batch == 2:  # state change between batches
+            for k in rng.sample(keys, 50):
+                w.both("remove_user", k)
+            for k in rng.sample(keys, 50):
+                w.both("subscribe_user_to", k, [rng.randrange(16)])
+        total += w.check()
+    assert total > 1000
+
+
+def test_state_change_is_ordered_with_messages(pcdn):
+    """R12: a subscribe/unsubscribe/remove between two messages affects only the later one, even
+    when both travel through the engine back to back"""
+    w = World(pcdn)
+    a = w.add_user(b"a" * 8, [])
+    w.add_user(b"b" * 8, [1])
+    m1, m2, m3 = (orc.broadcast_frame([1], b"m%d" % i) for i in (1, 2, 3))
+    w.bcast([1], m1)
+    w.both("subscribe_user_to", b"a" * 8, [1])
+    w.bcast([1], m2)
+    w.both("remove_user", b"b" * 8)
+    w.bcast([1], m3)
+    got = w.e.drain()
+    assert got[a] == [m2, m3]
+    want = w.expect()
+    assert got == want
+
+
+def test_direct_hot_recipient_keeps_order(pcdn):
+    """many directs to ONE key in one batch (votes to a leader): per-connection order = batch order
+    (R9) — exercises the stable (connection, message) sort"""
+    rng = random.Random(7)
+    w = World(pcdn, max_conns=20480, max_keys=65536, max_batch_msgs=8192, ring_bytes_per_conn=1 << 20,
+              max_batch_bytes=8 << 20)
+    keys = [rng.getrandbits(128).to_bytes(16, "little") * 8 for _ in range(20000)]  # 128-byte keys
+    for k in keys:
+        w.add_user(k, [0] if rng.random() < 0.001 else [])
+    leader = keys[123]
+    for j in range(6000):
+        r = rng.random()
+        if r < 0.5:
+            rc = leader
+        elif r < 0.9:
+            rc = rng.choice(keys)
+        else:
+            rc = rng.getrandbits(128).to_bytes(16, "little") * 8  # unknown: dropped
+        w.direct(rc, orc.direct_frame(rc, j.to_bytes(4, "little") * rng.randrange(1, 30)))
+        if j % 500 == 0:
+            w.bcast([0], orc.broadcast_frame([0], b"tick%d" % j))
+    n = w.check()
+    assert n > 5000
+    assert w.e.last_result.n_direct_dropped > 300
+
+
+def test_ring_wrap_and_release(pcdn):
+    """rings much smaller than the traffic: records never straddle the ring end, spans split at the
+    wrap, released space is reused; delivered streams stay identical to the oracle's"""
+    rng = random.Random(11)
+    w = World(pcdn, ring_bytes_per_conn=8192, max_conns=256)
+    for i in range(100):
+        w.add_user(bytes([i]) * 8, [0] if i % 2 == 0 else [1])
+    for rnd in range(60):
+        for j in range(rng.randrange(1, 5)):
+            t = rng.randrange(2)
+            w.bcast([t], orc.broadcast_frame([t], payload(rng, rng.randrange(0, 1500))))
+        w.direct(bytes([rnd % 100]) * 8, orc.direct_frame(bytes([rnd % 100]) * 8, payload(rng, rng.randrange(0, 900))))
+        w.check()
+
+
+def test_ring_overflow_reports_connection(pcdn):
+    """a slow consumer (nothing released) overflows its ring: deliveries stop at the overflow point,
+    the connection is reported so the host can remove it (the R13 analogue); others are unaffected"""
+    w = World(pcdn, ring_bytes_per_conn=4096, max_conns=64)
+    a = w.add_user(b"slow" * 2, [0])
+    b = w.add_user(b"fast" * 2, [1])
+    frames = [orc.broadcast_frame([0], bytes([i]) * 900) for i in range(8)]
+    other = [orc.broadcast_frame([1], bytes([i]) * 10) for i in range(8)]
+    for f, g in zip(frames, other):
+        w.e.handle_broadcast_message([0], f)
+        w.e.handle_broadcast_message([1], g)
+    w.e.flush()
+    bid = w.e.next_batch()
+    res = w.e.poll(bid)
+    got = w.e.collect_frames(res)
+    assert res.n_overflow == 1 and res.overflow_conns[0] == a
+    assert got[b] == other
+    k = len(got[a])
+    assert 0 < k < 8 and got[a] == frames[:k]      # a prefix, in order
+    assert res.n_deliveries == k + 8
+    w.e.release_batch(bid)
+
+
+def test_explicit_submit_and_counters(pcdn):
+    w = World(pcdn)
+    for i in range(64):
+        w.add_user(bytes([i]) * 8, [i % 4])
+    msgs, raws = [], []
+    for j in range(20):
+        if j % 3:
+            raw = orc.broadcast_frame([j % 4], b"x" * (j * 31))
+            msgs.append(("b", [j % 4], raw, False))
+            w.o.handle_broadcast_message([j % 4], raw)
+        else:
+            raw = orc.direct_frame(bytes([j]) * 8, b"y" * (j * 17))
+            msgs.append(("d", bytes([j]) * 8, raw, False))
+            w.o.handle_direct_message(bytes([j]) * 8, raw)
+    bid = w.e.submit(msgs)
+    res = w.e.poll(bid)
+    assert res.n_msgs == 20 and res.status == 0
+    assert res.n_deliveries == w.o.deliveries() and res.bytes_out == w.o.bytes_sent()
+    got = w.e.collect_frames(res)
+    w.e.release_batch(bid)
+    assert got == w.expect()
+
+
+def test_batch_capacity_rejected_not_truncated(pcdn):
+    """more deliveries than max_batch_deliveries: the device rejects the whole batch (E2BIG),
+    nothing is written and ring cursors are untouched"""
+    w = World(pcdn, max_batch_deliveries=1000, max_conns=4096)
+    for i in range(2000):
+        w.add_user(i.to_bytes(8, "little"), [0])
+    raw = orc.broadcast_frame([0], b"big fan-out")
+    w.e.handle_broadcast_message([0], raw)
+    w.e.flush()
+    bid = w.e.next_batch()
+    res = w.e.poll(bid)
+    assert res.status == 12 and res.n_deliveries == 0 and res.n_spans == 0
+    w.e.release_batch(bid)
+    # the engine keeps working afterwards
+    w.both("unsubscribe_user_from", (5).to_bytes(8, "little"), [0])
+    for i in range(1500):
+        w.both("unsubscribe_user_from", (i + 100).to_bytes(8, "little"), [0])
+    w.bcast([0], raw)
+    assert w.check() == 499
