@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--conns", type=int, default=N_CONNS)
     ap.add_argument("--payload", type=int, default=PAYLOAD)
     ap.add_argument("--msgs", type=int, default=MSGS_PER_STEP)
+    ap.add_argument("--ring-records", type=int, default=RING_RECORDS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-verify", action="store_true")
     args = ap.parse_args()
@@ -190,7 +191,7 @@ def main():
     frames = [broadcast_frame(0, bytes(((i * 131 + m * 7 + 1) & 0xFF) for i in range(args.payload))) for m in range(M)]
     L = len(frames[0]); F = 4 + L
     rec = (F + 31) // 32 * 32
-    ring_bytes = RING_RECORDS * rec
+    ring_bytes = args.ring_records * rec
     eng = pkg.Engine(device=local, stream=stream.cuda_stream, max_conns=n_conns, max_topics=256, max_keys=n_conns,
                      max_key_len=KEY_LEN, ring_bytes_per_conn=ring_bytes, max_batch_msgs=max(64, M), max_batch_bcast=max(16, M),
                      max_batch_bytes=max(1 << 20, 4 * M * (rec + 64)), max_batch_deliveries=M * n_conns + 1024, batch_slots=4,

@@ -120,7 +120,7 @@ typedef struct pcdn_batch_result {
   uint32_t n_spans;
   const pcdn_span* spans;          /* engine-owned pinned host memory, valid until release      */
   uint64_t n_deliveries;           /* records written                                           */
-  uint64_t bytes_out;              /* sum of 4+L over deliveries (what BYTES_SENT would add, protocols/mod.rs:388) */
+  uint64_t bytes_out;              /* sum of 4+L over deliveries = bytes put on the wire (BYTES_SENT of protocols/mod.rs:388 counts L only: bytes_out - 4*n_deliveries) */
   uint32_t n_overflow;             /* connections whose ring was full: their deliveries from the overflow point on were dropped; the host must remove them (R13 analogue) */
   const pcdn_conn* overflow_conns; /* engine-owned                                              */
   uint32_t n_direct_dropped;       /* direct messages with no route (handler.rs:210,224)        */

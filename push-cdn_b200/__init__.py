@@ -363,7 +363,8 @@ class Engine:
             per.setdefault(conn, []).append((off, ln, nrec))
         out: Dict[int, List[bytes]] = {}
         for conn, pieces in per.items():
-            pieces.sort(key=lambda p: (p[0] == 0 and len(pieces) > 1, p[0]))
+            two = len(pieces) > 1  # (a list is empty while it is being sorted: take the length first)
+            pieces.sort(key=lambda p: (p[0] == 0 and two, p[0]))
             frames = []
             for off, ln, nrec in pieces:
                 data = self.read(conn, off, ln)

@@ -149,8 +149,10 @@ def test_double_connect_same_broker(backend):
     run = TestDefinition(connected_users=[TestUser(0, [GLOBAL])]).into_run(backend)
     old = run.connected_users[0]
     new = backend.add_user(at_index(0), [GLOBAL])
-    assert new != old
-    run.connected_users.append(new)
+    # (the engine may hand the kicked connection's dense id to the new connection: ids are only
+    # meaningful between add and remove, like a slab index)
+    if new != old:
+        run.connected_users.append(new)
     m = Direct(at_index(0), b"hello direct")
     assert run.send_as_user(0, m) == 0
     run.assert_received(new, m)

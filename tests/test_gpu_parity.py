@@ -76,12 +76,36 @@ class World:
     def check(self):
         got = self.e.drain()
         want = self.expect()
+        bad = [c for c in sorted(set(got) | set(want)) if got.get(c, []) != want.get(c, [])]
+        if bad:
+            self.dump(bad, got, want)
         assert set(got) == set(want), (sorted(set(got) ^ set(want))[:10])
         for c in want:
             assert len(got[c]) == len(want[c]), (c, len(got[c]), len(want[c]))
             for i, (g, w) in enumerate(zip(got[c], want[c])):
                 assert g == w, f"conn {c} frame {i}: {len(g)} vs {len(w)} bytes"
         return sum(len(v) for v in want.values())
+
+    def dump(self, bad, got, want):
+        """diagnostics for a failing comparison (kept under gpurun_out/ on the GPU box)"""
+        import os
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open("gpurun_out/parity_dump.txt", "a") as f:
+            f.write(f"==== {len(bad)} bad connections of {len(want)}; first: {bad[:20]}\n")
+            r = self.e.last_result
+            f.write(f"last batch: msgs={r.n_msgs} deliveries={r.n_deliveries} spans={r.n_spans} overflow={r.n_overflow} "
+                    f"dropped={r.n_direct_dropped} status={r.status}\n")
+            for c in bad[:6]:
+                g, w = got.get(c, []), want.get(c, [])
+                f.write(f"conn {c}: got {len(g)} frames, want {len(w)}\n")
+                sig = lambda fr: (len(fr), fr[:4].hex(), fr[-12:].hex())
+                f.write("  got : " + " ".join(str(sig(x)) for x in g[:40]) + "\n")
+                f.write("  want: " + " ".join(str(sig(x)) for x in w[:40]) + "\n")
+                for i, (a, b) in enumerate(zip(g, w)):
+                    if a != b and len(a) == len(b):
+                        d = next(k for k in range(len(a)) if a[k] != b[k])
+                        f.write(f"  frame {i}: same length {len(a)}, first diff at byte {d}: {a[d:d+16].hex()} vs {b[d:d+16].hex()}\n")
+                        break
 
 
 def payload(rng, n):
@@ -94,7 +118,7 @@ def test_random_mixed_batches(pcdn, seed, variant):
     """users + peer brokers, multi-topic broadcasts (fat and thin recipient sets), directs to local,
     remote and unknown keys, frame sizes from 0 B to 3 staging chunks, several batches"""
     rng = random.Random(seed)
-    w = World(pcdn, pack_variant=variant)
+    w = World(pcdn, pack_variant=variant, ring_bytes_per_conn=1 << 20)
     keys = []
     for i in range(1500):
         k = rng.getrandbits(64).to_bytes(8, "little") * rng.choice([1, 4, 16])
@@ -228,7 +252,7 @@ def test_explicit_submit_and_counters(pcdn):
     bid = w.e.submit(msgs)
     res = w.e.poll(bid)
     assert res.n_msgs == 20 and res.status == 0
-    assert res.n_deliveries == w.o.deliveries() and res.bytes_out == w.o.bytes_sent()
+    assert res.n_deliveries == w.o.deliveries() and res.bytes_out == w.o.bytes_sent() + 4 * w.o.deliveries()
     got = w.e.collect_frames(res)
     w.e.release_batch(bid)
     assert got == w.expect()
