@@ -227,12 +227,34 @@ def main():
     db = pkg.DeviceBatch(M, M, d_arena.data_ptr(), d_arena.numel(), d_kind.data_ptr(), d_flags.data_ptr(), d_slot.data_ptr(),
                          d_len.data_ptr(), d_aoff.data_ptr(), d_alen.data_ptr(), d_topics.data_ptr(), M, d_bidx.data_ptr())
 
+    # Batches are pipelined the way a broker streams them: batch n is released (its ring space
+    # handed back by the consumer) right after batch n+1 has been submitted, so the engine can run
+    # the match/plan/offsets kernels of n+1 while the pack of n is still streaming to HBM.  With
+    # N>1 the ingest buffer is double-buffered so the NCCL broadcast of step n+1 never touches the
+    # frames the pack of step n is reading.
+    torch.cuda.synchronize(dev)
+    with torch.cuda.stream(stream):
+        d_arenas = [d_arena, d_arena.clone()]
+    dbs = [db, pkg.DeviceBatch(M, M, d_arenas[1].data_ptr(), d_arenas[1].numel(), d_kind.data_ptr(), d_flags.data_ptr(),
+                               d_slot.data_ptr(), d_len.data_ptr(), d_aoff.data_ptr(), d_alen.data_ptr(),
+                               d_topics.data_ptr(), M, d_bidx.data_ptr())]
+    state = {"prev": 0, "i": 0}
+
     def step_device():
+        k = state["i"] & 1
+        state["i"] += 1
         if world > 1:
-            dist.broadcast(d_arena, src=0)  # NCCL ingest over NVLink, on `stream`
-        b = eng.submit_device(db)
-        eng.release_batch(b)                 # the consumer (NIC hand-off) frees the ring space
+            dist.broadcast(d_arenas[k], src=0)  # NCCL ingest over NVLink, on `stream`
+        b = eng.submit_device(dbs[k])
+        if state["prev"]:
+            eng.release_batch(state["prev"])     # the consumer (NIC hand-off) frees the ring space
+        state["prev"] = b
         return b
+
+    def drain_device():
+        if state["prev"]:
+            eng.release_batch(state["prev"])
+            state["prev"] = 0
 
     def sync_all():
         if world > 1:
@@ -242,6 +264,7 @@ def main():
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
             step_device()
+        drain_device()
         sync_all()
         sampler = ClockSampler(local)
         sampler.start()
@@ -249,6 +272,7 @@ def main():
         ev0.record(stream)
         for _ in range(args.steps):
             step_device()
+        drain_device()                        # waits (on the stream) for the last pack
         ev1.record(stream)
         sync_all()
         clocks = sampler.stop()
@@ -364,7 +388,7 @@ def main():
             cpu = {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
 
     if rank == 0:
-        launches_per_step = 9 + (0 if world == 1 else 0)
+        launches_per_step = 6  # k_match, k_match_base, k_plan_a, k_offsets, k_pack, k_release
         line = {
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -377,7 +401,7 @@ def main():
                        "ring_bytes_per_conn": ring_bytes, "parallelism": "connection shards x%d, NCCL ingest broadcast" % world
                        if world > 1 else "single GPU", "l2": "outputs 9.1 GB/step >> L2; inputs 8.7 KB (algorithmically resident)",
                        "pack_variant": args.variant, "verify": verify, "setup_s": round(setup_s, 2)},
-            "roofline": {"bound": "hbm", "kernel": "k_pack_fat", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_pack (connection-major phase)" if not (args.variant & 2) else "k_pack (message-major phase)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": pack_bytes, "ms_per_launch": ms_pack,
                          "stage_ms": {"match": ms_match, "plan_offsets": ms_plan, "pack": ms_pack}},

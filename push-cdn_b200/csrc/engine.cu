@@ -74,11 +74,14 @@ struct Slot {
   Work w{};
   BatchIn in{};
   // results
-  BatchStats* h_stats = nullptr;  // pinned
+  BatchStats* h_stats = nullptr;  // pinned: final counters (after the pack)
+  BatchStats* h_early = nullptr;  // pinned: counters as of k_offsets (n_spans, n_overflow are final there)
   Span* h_spans = nullptr;        // pinned
   uint32_t* h_overflow = nullptr; // pinned
-  cudaEvent_t ev_done = nullptr;
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_done = nullptr;   // pack + final counters complete (pack stream)
+  cudaEvent_t ev_ctrl = nullptr;   // match/plan/offsets complete (main stream)
+  cudaEvent_t ev_early = nullptr;  // early counters are in h_early (copy stream)
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool timed = false;
 };
 
@@ -93,7 +96,9 @@ struct pcdn_engine {
   std::unique_ptr<Connections> conns;
   bool has_device = false;
   int n_sms = 148;
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  // main stream: uploads, table updates, direct/match/plan/offsets, release.  pack stream: k_pack, so
+  // that the control kernels of batch n+1 overlap the HBM-bound pack of batch n.  copy stream: D2H.
+  cudaStream_t stream = nullptr, pack_stream = nullptr, copy_stream = nullptr;
   bool own_stream = false;
   DevState dev{};
   std::vector<Slot> slots;
@@ -201,7 +206,10 @@ int acquire_open_slot(pcdn_engine* e) {
 
 // run the kernel pipeline for slot `s` whose BatchIn is ready on the device
 int launch_pipeline(pcdn_engine* e, Slot& s, uint32_t n_direct) {
-  cudaStream_t st = e->stream;
+  // Default: the pack runs on the main stream.  A/B switch (pack_variant bit 3): run it on the
+  // high-priority pack stream so the next batch's control kernels overlap it — measured SLOWER for
+  // the bulk-store pack (profiles/r1_sweep_overlap.txt), so it stays opt-in.
+  cudaStream_t st = e->stream, ps = (e->cfg.pack_variant & 8) ? e->pack_stream : e->stream, cs = e->copy_stream;
   const bool has_direct = n_direct > 0;
   s.timed = e->timing;
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[0], st));
@@ -213,11 +221,19 @@ int launch_pipeline(pcdn_engine* e, Slot& s, uint32_t n_direct) {
   launch_plan(e->dev, s.w, s.in, st);
   launch_offsets(e->dev, s.w, s.in, has_direct, st);
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[3], st));
-  launch_pack(e->dev, s.w, s.in, e->cfg.pack_variant, e->n_sms, st);
-  if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[4], st));
+  CUDA_TRY(cudaEventRecord(s.ev_ctrl, st));
+  // the span table is final once k_offsets is done: its counters go home while the pack runs
+  CUDA_TRY(cudaStreamWaitEvent(cs, s.ev_ctrl, 0));
+  CUDA_TRY(cudaMemcpyAsync(s.h_early, s.w.stats, sizeof(BatchStats), cudaMemcpyDeviceToHost, cs));
+  CUDA_TRY(cudaEventRecord(s.ev_early, cs));
+  // pack on its own stream (packs of successive batches stay ordered among themselves)
+  CUDA_TRY(cudaStreamWaitEvent(ps, s.ev_ctrl, 0));
+  if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[4], ps));
+  launch_pack(e->dev, s.w, s.in, e->cfg.pack_variant, e->n_sms, ps);
+  if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[5], ps));
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(s.h_stats, s.w.stats, sizeof(BatchStats), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaEventRecord(s.ev_done, st));
+  CUDA_TRY(cudaMemcpyAsync(s.h_stats, s.w.stats, sizeof(BatchStats), cudaMemcpyDeviceToHost, ps));
+  CUDA_TRY(cudaEventRecord(s.ev_done, ps));
   s.state = SLOT_INFLIGHT;
   s.batch_id = e->next_batch_id++;
   s.polled = false;
@@ -352,8 +368,12 @@ void destroy_engine(pcdn_engine* e) {
   if (e->has_device) {
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
+    if (e->pack_stream) cudaStreamSynchronize(e->pack_stream);
+    if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     for (auto& s : e->slots) {
       if (s.ev_done) cudaEventDestroy(s.ev_done);
+      if (s.ev_ctrl) cudaEventDestroy(s.ev_ctrl);
+      if (s.ev_early) cudaEventDestroy(s.ev_early);
       for (auto& ev : s.ev) if (ev) cudaEventDestroy(ev);
     }
     for (void* p : e->dev_allocs) cudaFree(p);
@@ -363,6 +383,7 @@ void destroy_engine(pcdn_engine* e) {
     if (e->j_kslot) cudaFree(e->j_kslot);
     if (e->j_kbytes) cudaFree(e->j_kbytes);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->pack_stream) cudaStreamDestroy(e->pack_stream);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   }
   delete e;
@@ -396,12 +417,20 @@ int init_device(pcdn_engine* e) {
   if (c.stream) { e->stream = (cudaStream_t)c.stream; e->own_stream = false; }
   else { CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true; }
   CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  {
+    // highest priority: when a pack and the (small) control kernels of the next batch become
+    // runnable together, the pack's persistent CTAs must be placed first and evenly over the SMs
+    int lo = 0, hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_TRY(cudaStreamCreateWithPriority(&e->pack_stream, cudaStreamNonBlocking, hi));
+  }
   e->has_device = true;
 
   DevState& d = e->dev;
   d.N = g.N; d.W = g.W; d.T = g.T; d.nblk = g.W / kBlockWords;
   d.bucket_mask = g.bucket_mask; d.key_stride = g.key_stride; d.seed = g.seed;
   d.ring_bytes = c.ring_bytes_per_conn; d.ring_units = (uint32_t)(c.ring_bytes_per_conn / kUnit);
+  d.cm_enable = (c.pack_variant & 2) ? 0 : 1;
   DEV_ALLOC(d.sub, (size_t)g.T * g.W);
   DEV_ALLOC(d.brk, g.W);
   DEV_ALLOC(d.owner_conn, g.max_owners);
@@ -440,8 +469,13 @@ int init_device(pcdn_engine* e) {
     DEV_ALLOC(w.eb_fat, (size_t)M + 1);
     DEV_ALLOC(w.eb_thin, (size_t)M + 1);
     DEV_ALLOC(w.tbase, (size_t)M + 1);
-    DEV_ALLOC(w.scan_tmp, 3 * ((size_t)M / 256 + 2));
+    DEV_ALLOC(w.scan_tmp, 4 * ((size_t)M / 256 + 2));
+    DEV_ALLOC(w.cls, M);
+    DEV_ALLOC(w.cm_rank, (size_t)M + 1);
+    DEV_ALLOC(w.cm_list, MB);
+    DEV_ALLOC(w.jidx, M);
     DEV_ALLOC(w.efat, cap_fat);
+    DEV_ALLOC(w.ecm, cap_fat);
     DEV_ALLOC(w.ethin, cap_thin);
     w.cap_fat = (uint32_t)std::min<size_t>(cap_fat, 0xFFFFFFFFu);
     w.cap_thin = (uint32_t)std::min<size_t>(cap_thin, 0xFFFFFFFFu);
@@ -455,9 +489,12 @@ int init_device(pcdn_engine* e) {
     DEV_ALLOC(w.overflow, g.N);
     DEV_ALLOC(w.stats, 1);
     PIN_ALLOC(s.h_stats, 1);
+    PIN_ALLOC(s.h_early, 1);
     PIN_ALLOC(s.h_spans, (size_t)2 * g.max_conns);
     PIN_ALLOC(s.h_overflow, g.max_conns);
     CUDA_TRY(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&s.ev_ctrl, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&s.ev_early, cudaEventDisableTiming));
     for (auto& ev : s.ev) CUDA_TRY(cudaEventCreate(&ev));
   }
   CUDA_TRY(cudaStreamSynchronize(e->stream));
@@ -780,24 +817,28 @@ int pcdn_poll(pcdn_engine* e, uint64_t batch_id, pcdn_batch_result* out, int blo
   Slot* s = find_slot(e, batch_id);
   if (!s) return fail(PCDN_ENOENT, "unknown batch id");
   if (!s->polled) {
-    if (block) CUDA_TRY(cudaEventSynchronize(s->ev_done));
-    else {
+    if (!block) {
       cudaError_t q = cudaEventQuery(s->ev_done);
       if (q == cudaErrorNotReady) return 1;
       CUDA_TRY(q);
     }
-    const BatchStats& bs = *s->h_stats;
-    uint32_t nsp = std::min<uint32_t>(bs.n_spans, 2 * e->geo.max_conns);
-    uint32_t nov = std::min<uint32_t>(bs.n_overflow, e->geo.max_conns);
+    // 1. counters as of k_offsets → exact size of the span table; its D2H overlaps the pack
+    CUDA_TRY(cudaEventSynchronize(s->ev_early));
+    const uint32_t nsp = std::min<uint32_t>(s->h_early->n_spans, 2 * e->geo.max_conns);
+    const uint32_t nov = std::min<uint32_t>(s->h_early->n_overflow, e->geo.max_conns);
     if (nsp) CUDA_TRY(cudaMemcpyAsync(s->h_spans, s->w.spans, (size_t)nsp * sizeof(Span), cudaMemcpyDeviceToHost, e->copy_stream));
     if (nov) CUDA_TRY(cudaMemcpyAsync(s->h_overflow, s->w.overflow, (size_t)nov * 4, cudaMemcpyDeviceToHost, e->copy_stream));
+    // 2. the pack itself (ring bytes are valid after this)
+    CUDA_TRY(cudaEventSynchronize(s->ev_done));
     if (nsp || nov) CUDA_TRY(cudaStreamSynchronize(e->copy_stream));
+    const BatchStats& bs = *s->h_stats;
     s->polled = true;
     e->stats.deliveries += bs.n_deliveries;
     e->stats.bytes_out += bs.bytes_out;
     if (s->timed) {
       float t[4] = {0, 0, 0, 0};
-      for (int i = 0; i < 4; i++) cudaEventElapsedTime(&t[i], s->ev[i], s->ev[i + 1]);
+      for (int i = 0; i < 3; i++) cudaEventElapsedTime(&t[i], s->ev[i], s->ev[i + 1]);
+      cudaEventElapsedTime(&t[3], s->ev[4], s->ev[5]);
       e->stats.ms_direct += t[0];
       e->stats.ms_match += t[1];
       e->stats.ms_plan += t[2];
@@ -843,6 +884,8 @@ int pcdn_release_batch(pcdn_engine* e, uint64_t batch_id) {
   if (!s) return fail(PCDN_ENOENT, "unknown batch id");
   if (e->inflight.empty() || e->inflight.front() != batch_id)
     return fail(PCDN_EINVAL, "batches must be released oldest first");
+  // ring space may be reused only after the pack that filled it has finished
+  CUDA_TRY(cudaStreamWaitEvent(e->stream, s->ev_done, 0));
   launch_release(e->dev, s->w.batch_units, e->stream);
   CUDA_TRY(cudaGetLastError());
   e->inflight.erase(e->inflight.begin());

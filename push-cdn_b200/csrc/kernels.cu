@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(256) k_match_base(DevState s, BatchIn b, Work 
     if (i < s.nblk) w.base[(size_t)j * s.nblk + i] = ex + carry;
     carry += tot;
   }
-  if (threadIdx.x == 0) w.D[b.bcast_index[j]] = carry;
+  if (threadIdx.x == 0) { w.D[b.bcast_index[j]] = carry; w.jidx[b.bcast_index[j]] = j; }
 }
 void launch_match(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st) {
   if (!b.n_bcast) return;
@@ -374,30 +374,51 @@ void launch_match(const DevState& s, const Work& w, const BatchIn& b, cudaStream
 __device__ __forceinline__ uint32_t frame_vec_bytes(uint32_t raw_len) { return (4u + raw_len + 15u) & ~15u; }
 __device__ __forceinline__ uint32_t frame_units(uint32_t raw_len) { return (4u + raw_len + kUnit - 1u) / kUnit; }
 
-__global__ void __launch_bounds__(256) k_plan_a(BatchIn b, Work w, uint32_t nblk) {
+__global__ void __launch_bounds__(256) k_plan_a(DevState s, BatchIn b, Work w, uint32_t nblk) {
   __shared__ uint32_t sm[9];
   const uint32_t m = blockIdx.x * 256 + threadIdx.x;
   const bool valid = m < b.n_msgs;
   const uint32_t d = valid ? w.D[m] : 0;
-  const bool fat = d >= kFatMin;
-  uint32_t tiles = 0;
-  if (fat) {
-    const uint32_t nch = (frame_vec_bytes(b.raw_len[m]) + kChunkBytes - 1) / kChunkBytes;
-    tiles = nch * ((d + kTileRecipients - 1) / kTileRecipients);
+  uint32_t cls = CLS_THIN, tiles = 0;
+  if (d >= kFatMin) {
+    const uint32_t len = b.raw_len[m];
+    const bool dense = s.cm_enable && ((uint64_t)d << kCmDenseShift) >= s.N && b.kind[m] == 4;
+    if (dense && frame_units(len) * kUnit <= kCmMaxBytes) {
+      cls = CLS_CM;
+    } else {
+      cls = CLS_FAT;
+      const uint32_t nch = (frame_vec_bytes(len) + kChunkBytes - 1) / kChunkBytes;
+      tiles = nch * ((d + kTileRecipients - 1) / kTileRecipients);
+    }
   }
   uint32_t tot;
-  uint32_t e0 = block256_excl_scan(fat ? d : 0, &tot, sm);
+  uint32_t e0 = block256_excl_scan(cls != CLS_THIN ? d : 0, &tot, sm);
   if (threadIdx.x == 0) w.scan_tmp[blockIdx.x] = tot;
-  uint32_t e1 = block256_excl_scan(fat ? 0 : d, &tot, sm);
+  uint32_t e1 = block256_excl_scan(cls == CLS_THIN ? d : 0, &tot, sm);
   if (threadIdx.x == 0) w.scan_tmp[nblk + blockIdx.x] = tot;
   uint32_t e2 = block256_excl_scan(tiles, &tot, sm);
   if (threadIdx.x == 0) w.scan_tmp[2 * nblk + blockIdx.x] = tot;
-  if (valid) { w.eb_fat[m] = e0; w.eb_thin[m] = e1; w.tbase[m] = e2; }
+  uint32_t e3 = block256_excl_scan(cls == CLS_CM ? 1u : 0u, &tot, sm);
+  if (threadIdx.x == 0) w.scan_tmp[3 * nblk + blockIdx.x] = tot;
+  if (valid) { w.eb_fat[m] = e0; w.eb_thin[m] = e1; w.tbase[m] = e2; w.cm_rank[m] = e3; w.cls[m] = (uint8_t)cls; }
+  if (gridDim.x == 1) {
+    // whole batch in one block (<= 256 messages): the local scans are already global, finish here
+    // (saves the k_plan_b / k_plan_c launches on the latency-critical small-batch path)
+    if (valid && cls == CLS_CM) w.cm_list[e3] = m;
+    if (threadIdx.x == 0) {
+      const uint32_t t0 = w.scan_tmp[0], t1 = w.scan_tmp[1], t2 = w.scan_tmp[2], t3 = w.scan_tmp[3];
+      w.stats->n_fat_entries = t0; w.stats->n_thin_entries = t1; w.stats->n_fat_tiles = t2; w.stats->tile_cursor = 0;
+      w.stats->n_cm = t3; w.stats->cm_cursor = 0;
+      if (t0 > w.cap_fat || t1 > w.cap_thin) w.stats->status = 1;  // PCDN_E2BIG
+      const uint32_t n = b.n_msgs;
+      w.eb_fat[n] = t0; w.eb_thin[n] = t1; w.tbase[n] = t2; w.cm_rank[n] = t3;
+    }
+  }
 }
 __global__ void __launch_bounds__(256) k_plan_b(Work w, uint32_t nblk) {
   __shared__ uint32_t sm[9];
-  uint32_t totals[3];
-  for (int q = 0; q < 3; q++) {
+  uint32_t totals[4];
+  for (int q = 0; q < 4; q++) {
     uint32_t* t = w.scan_tmp + (size_t)q * nblk;
     uint32_t carry = 0;
     for (uint32_t bb = 0; bb < nblk; bb += 256) {
@@ -414,6 +435,8 @@ __global__ void __launch_bounds__(256) k_plan_b(Work w, uint32_t nblk) {
     w.stats->n_thin_entries = totals[1];
     w.stats->n_fat_tiles = totals[2];
     w.stats->tile_cursor = 0;
+    w.stats->n_cm = totals[3];
+    w.stats->cm_cursor = 0;
     if (totals[0] > w.cap_fat || totals[1] > w.cap_thin) w.stats->status = 1;  // PCDN_E2BIG
   }
 }
@@ -423,15 +446,20 @@ __global__ void __launch_bounds__(256) k_plan_c(BatchIn b, Work w, uint32_t nblk
     w.eb_fat[m] += w.scan_tmp[blockIdx.x];
     w.eb_thin[m] += w.scan_tmp[nblk + blockIdx.x];
     w.tbase[m] += w.scan_tmp[2 * nblk + blockIdx.x];
+    const uint32_t r = w.cm_rank[m] + w.scan_tmp[3 * nblk + blockIdx.x];
+    w.cm_rank[m] = r;
+    if (w.cls[m] == CLS_CM) w.cm_list[r] = m;
   } else if (m == b.n_msgs) {
     w.eb_fat[m] = w.stats->n_fat_entries;
     w.eb_thin[m] = w.stats->n_thin_entries;
     w.tbase[m] = w.stats->n_fat_tiles;
+    w.cm_rank[m] = w.stats->n_cm;
   }
 }
-void launch_plan(const DevState&, const Work& w, const BatchIn& b, cudaStream_t st) {
+void launch_plan(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st) {
   const uint32_t nblk = (b.n_msgs + 255) / 256;
-  k_plan_a<<<nblk, 256, 0, st>>>(b, w, nblk);
+  k_plan_a<<<nblk, 256, 0, st>>>(s, b, w, nblk);
+  if (nblk == 1) return;  // finished inside k_plan_a
   k_plan_b<<<1, 256, 0, st>>>(w, nblk);
   k_plan_c<<<(b.n_msgs + 1 + 255) / 256, 256, 0, st>>>(b, w, nblk);
 }
@@ -478,25 +506,54 @@ __global__ void __launch_bounds__(256) k_offsets(DevState s, BatchIn b, Work w, 
   if (has_direct) { dp = w.dstart[c]; de = w.dend[c]; }
   const uint32_t* dmsg = w.sval[0];
 
-  auto emit = [&](uint32_t m, uint32_t rank) {
+  // direct hit (always the thin list, rank 0)
+  auto emit_direct = [&](uint32_t m) {
     const uint32_t len = b.raw_len[m];
     const uint32_t off = alloc_record(k, frame_units(len), R, len);
-    if (w.D[m] >= kFatMin) w.efat[w.eb_fat[m] + rank] = make_uint2(c, off);
-    else w.ethin[w.eb_thin[m] + rank] = make_uint4(c, off, b.slot_off16[m], len);
+    w.ethin[w.eb_thin[m]] = make_uint4(c, off, b.slot_off16[m], len);
   };
 
-  for (uint32_t j = 0; j < b.n_bcast; j++) {
-    const uint32_t word = w.B[(size_t)j * s.W + wd];  // warp-uniform
-    if (word == 0) continue;                          // nobody in this warp: directs can wait
-    const uint32_t mb = b.bcast_index[j];
-    while (dp < de && dmsg[dp] < mb) { emit(dmsg[dp], 0); dp++; }
-    if ((word >> lane) & 1u) {
-      const uint32_t rank = w.base[(size_t)j * s.nblk + (wd / kBlockWords)] + w.wpre[(size_t)j * s.W + wd] +
-                            __popc(word & lt);
-      emit(mb, rank);
+  // Broadcasts are taken 32 at a time: the block stages their per-message metadata in shared
+  // memory once, and every warp fetches its 32 match words / rank prefixes with ONE load per lane
+  // (lane i ↔ message j0+i) instead of a dependent chain of warp-uniform loads per message.
+  __shared__ uint32_t m_mb[32], m_len[32], m_eb[32], m_slot[32], m_cls[32];
+  for (uint32_t j0 = 0; j0 < b.n_bcast; j0 += 32) {
+    const uint32_t nj = min(32u, b.n_bcast - j0);
+    __syncthreads();
+    if (threadIdx.x < nj) {
+      const uint32_t m = b.bcast_index[j0 + threadIdx.x];
+      const uint32_t cl = w.cls[m];
+      m_mb[threadIdx.x] = m;
+      m_len[threadIdx.x] = b.raw_len[m];
+      m_cls[threadIdx.x] = cl;
+      m_eb[threadIdx.x] = cl != CLS_THIN ? w.eb_fat[m] : w.eb_thin[m];
+      m_slot[threadIdx.x] = b.slot_off16[m];
+    }
+    uint32_t Bw = 0, pre = 0;
+    if (lane < nj) {
+      const size_t at = (size_t)(j0 + lane) * s.W + wd;
+      Bw = w.B[at];
+      pre = w.base[(size_t)(j0 + lane) * s.nblk + (wd / kBlockWords)] + w.wpre[at];
+    }
+    __syncthreads();
+    uint32_t hits = __ballot_sync(0xffffffffu, Bw != 0);  // messages of this chunk that reach the warp
+    while (hits) {
+      const int i = __ffs(hits) - 1;
+      hits &= hits - 1;
+      const uint32_t word = __shfl_sync(0xffffffffu, Bw, i), p = __shfl_sync(0xffffffffu, pre, i);
+      const uint32_t mb = m_mb[i];
+      while (dp < de && dmsg[dp] < mb) { emit_direct(dmsg[dp]); dp++; }  // keep batch order (R9)
+      if ((word >> lane) & 1u) {
+        const uint32_t rank = p + __popc(word & lt), len = m_len[i];
+        const uint32_t off = alloc_record(k, frame_units(len), R, len);
+        const uint32_t cl = m_cls[i];
+        if (cl == CLS_CM) w.ecm[m_eb[i] + rank] = off;
+        else if (cl == CLS_FAT) w.efat[m_eb[i] + rank] = make_uint2(c, off);
+        else w.ethin[m_eb[i] + rank] = make_uint4(c, off, m_slot[i], len);
+      }
     }
   }
-  while (dp < de) { emit(dmsg[dp], 0); dp++; }
+  while (dp < de) { emit_direct(dmsg[dp]); dp++; }
 
   s.ptail[c] = k.pt;
   s.used[c] = k.us;
@@ -542,15 +599,13 @@ void launch_offsets(const DevState& s, const Work& w, const BatchIn& b, bool has
 //   VARIANT 0: lanes keep their 16-byte pieces in registers and issue st.global.cs.v4 per recipient
 //   VARIANT 1: one TMA bulk store (shared → global) per recipient, one lane each
 template <int VARIANT>
-__global__ void __launch_bounds__(256) k_pack_fat(DevState s, BatchIn b, Work w) {
-  __shared__ __align__(128) uint8_t buf[kChunkBytes];
-  __shared__ __align__(8) uint64_t bar;
+__device__ __forceinline__ void pack_fat_phase(const DevState& s, const BatchIn& b, const Work& w, uint8_t* buf,
+                                               uint64_t* barp) {
+  uint64_t& bar = *barp;
   __shared__ uint32_t t_info[8];  // tile, m, chunk, r0, r1, nbytes, need_load
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (w.stats->status) return;
   const uint32_t ntiles = w.stats->n_fat_tiles;
-  if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-  __syncthreads();
+  if (ntiles == 0) return;
   uint32_t phase = 0;
   uint32_t staged_m = 0xFFFFFFFFu, staged_k = 0xFFFFFFFFu;  // meaningful in thread 0 only
 
@@ -568,19 +623,21 @@ __global__ void __launch_bounds__(256) k_pack_fat(DevState s, BatchIn b, Work w)
         const uint32_t nbytes = min(kChunkBytes, fb - ch * kChunkBytes);
         t_info[1] = m; t_info[2] = ch; t_info[3] = grp * kTileRecipients;
         t_info[4] = min(d, (grp + 1) * kTileRecipients); t_info[5] = nbytes;
-        const uint32_t need = (m != staged_m || ch != staged_k) ? 1u : 0u;
-        t_info[6] = need;
-        if (need) {
-          mbar_arrive_expect_tx(&bar, nbytes);
-          bulk_g2s(buf, b.arena + (size_t)b.slot_off16[m] * 16 + (size_t)ch * kChunkBytes, nbytes, &bar);
-          staged_m = m; staged_k = ch;
-        }
+        t_info[6] = (m != staged_m || ch != staged_k) ? 1u : 0u;
+        staged_m = m; staged_k = ch;
       }
     }
     __syncthreads();
     if (t_info[0] >= ntiles) break;
     const uint32_t m = t_info[1], ch = t_info[2], r0 = t_info[3], r1 = t_info[4], nbytes = t_info[5];
     if (t_info[6]) {
+      // re-stage: drain the bulk stores that still read the old chunk (only here, not per tile)
+      if (VARIANT == 1) bulk_wait_read0();
+      __syncthreads();
+      if (tid == 0) {
+        mbar_arrive_expect_tx(&bar, nbytes);
+        bulk_g2s(buf, b.arena + (size_t)b.slot_off16[m] * 16 + (size_t)ch * kChunkBytes, nbytes, &bar);
+      }
       mbar_wait(&bar, phase);
       phase ^= 1;
       if (ch == 0) {  // fused framing: BE length prefix
@@ -602,7 +659,6 @@ __global__ void __launch_bounds__(256) k_pack_fat(DevState s, BatchIn b, Work w)
           bulk_s2g(s.rings + (size_t)ent.x * s.ring_bytes + (size_t)ent.y * kUnit + chunk_off, buf, nbytes);
       }
       bulk_commit();
-      bulk_wait_read0();  // smem may be overwritten by the next tile
     } else if (nvec <= 128) {
       // frame chunk fits 4 registers per lane: load once, then pure store stream
       uint4 v0, v1, v2, v3;
@@ -637,15 +693,163 @@ __global__ void __launch_bounds__(256) k_pack_fat(DevState s, BatchIn b, Work w)
         }
       }
     }
-    __syncthreads();  // all reads of buf / t_info done before thread 0 starts the next tile
+    __syncthreads();  // all reads of t_info done before thread 0 starts the next tile
   }
+  if (VARIANT == 1) bulk_wait_read0();
+}
+
+// =============================================================================== K2c pack (connection-major)
+// Dense messages with small records (class CLS_CM) are taken in groups of up to kCmGroup in batch
+// order.  A CTA stages the whole group in shared memory (one TMA bulk copy per frame, all counted
+// on one mbarrier) in exactly the layout the records have in a ring (32-byte padded, back to back),
+// patches the big-endian length prefixes, and then walks a tile of 512 connections.  For every
+// connection the offsets of its matched records come from the scatter list (rank = block base +
+// word prefix + lane rank, the same formula k_offsets used); records that are adjacent in the ring
+// are written as ONE contiguous run — for the all-subscribed case that is the whole batch
+// (8 x 1088 B = 8.7 KB) per connection instead of eight separate 1 KB writes, which is what the
+// HBM row buffers want (profiles/: 1 KB granules reach 83 % of the copy peak, >=4 KB runs 96 %).
+//   VARIANT 0: the warp copies a connection's run with 16-byte shared loads + st.global.cs.v4
+//   VARIANT 1: every lane issues one TMA bulk store (shared → global) per run of ITS connection
+template <int VARIANT>
+__device__ __forceinline__ void pack_cm_phase(const DevState& s, const BatchIn& b, const Work& w, uint8_t* buf,
+                                              uint64_t* barp) {
+  uint64_t& bar = *barp;
+  __shared__ uint32_t g_m[kCmGroup], g_j[kCmGroup], g_soff[kCmGroup], g_units[kCmGroup], g_eb[kCmGroup];
+  __shared__ uint32_t t_info[4];  // tile, group, gcount, need_load
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (w.stats->status) return;
+  const uint32_t ncm = w.stats->n_cm;
+  if (ncm == 0) return;
+  const uint32_t ngroups = (ncm + kCmGroup - 1) / kCmGroup;
+  const uint32_t tpg = s.W / kCmTileWords;  // tiles per group (W is a multiple of 256)
+  const uint32_t ntiles = ngroups * tpg;
+  uint32_t phase = 0;
+  uint32_t staged_g = 0xFFFFFFFFu;  // meaningful in thread 0 only
+
+  for (;;) {
+    if (tid == 0) {
+      const uint32_t t = atomicAdd(&w.stats->cm_cursor, 1u);
+      t_info[0] = t;
+      if (t < ntiles) {
+        const uint32_t g = t / tpg;
+        const uint32_t gcount = min(kCmGroup, ncm - g * kCmGroup);
+        t_info[1] = g; t_info[2] = gcount;
+        t_info[3] = g != staged_g ? 1u : 0u;
+        staged_g = g;
+      }
+    }
+    __syncthreads();
+    if (t_info[0] >= ntiles) break;
+    const uint32_t gcount = t_info[2];
+    if (t_info[3]) {
+      // New group: shared memory is re-staged.  Bulk stores issued for earlier tiles only have to
+      // be drained HERE (they read the old frames) — not after every tile, so the TMA store
+      // queue never runs dry while the next tile's offsets are being fetched.
+      if (VARIANT == 1) bulk_wait_read0();
+      __syncthreads();
+      if (tid == 0) {
+        const uint32_t g = t_info[1];
+        uint32_t soff = 0, total = 0;
+        for (uint32_t i = 0; i < gcount; i++) {
+          const uint32_t m = w.cm_list[g * kCmGroup + i];
+          const uint32_t len = b.raw_len[m];
+          g_m[i] = m; g_j[i] = w.jidx[m]; g_soff[i] = soff; g_units[i] = frame_units(len); g_eb[i] = w.eb_fat[m];
+          soff += frame_units(len) * kUnit;
+          total += frame_vec_bytes(len);
+        }
+        mbar_arrive_expect_tx(&bar, total);
+        for (uint32_t i = 0; i < gcount; i++)
+          bulk_g2s(buf + g_soff[i], b.arena + (size_t)b.slot_off16[g_m[i]] * 16, frame_vec_bytes(b.raw_len[g_m[i]]), &bar);
+      }
+      __syncthreads();
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+      if (tid < gcount) {  // fused framing: one BE length prefix per staged frame
+        *reinterpret_cast<uint32_t*>(buf + g_soff[tid]) = bswap32(b.raw_len[g_m[tid]]);
+        if (VARIANT == 1) fence_proxy_async_smem();
+      }
+      __syncthreads();
+    }
+    const uint32_t wt = t_info[0] % tpg;
+    for (uint32_t wi = warp; wi < kCmTileWords; wi += 8) {
+      const uint32_t wd = wt * kCmTileWords + wi;
+      const uint32_t myword = lane < gcount ? w.B[(size_t)g_j[lane] * s.W + wd] : 0u;
+      const uint32_t any = __reduce_or_sync(0xffffffffu, myword);
+      if (!any) continue;
+      // ring offset of (connection = wd*32+lane, message i of the group), or invalid
+      uint32_t offs[kCmGroup];
+#pragma unroll
+      for (int i = 0; i < (int)kCmGroup; i++) {
+        const uint32_t wordi = __shfl_sync(0xffffffffu, myword, i);
+        offs[i] = kOffInvalid;
+        if ((uint32_t)i < gcount && ((wordi >> lane) & 1u)) {
+          const uint32_t j = g_j[i];
+          const uint32_t idx = g_eb[i] + w.base[(size_t)j * s.nblk + wd / kBlockWords] + w.wpre[(size_t)j * s.W + wd] +
+                               __popc(wordi & ((1u << lane) - 1u));
+          offs[i] = w.ecm[idx];
+        }
+      }
+      if (VARIANT == 1) {
+        // one lane = one connection: merge adjacent records into runs, one bulk store per run
+        uint8_t* ring = s.rings + (size_t)(wd * 32 + lane) * s.ring_bytes;
+        uint32_t run_o = kOffInvalid, run_units = 0, run_s = 0;
+#pragma unroll
+        for (int i = 0; i < (int)kCmGroup; i++) {
+          const uint32_t o = offs[i];
+          if (o != kOffInvalid && run_o != kOffInvalid && o == run_o + run_units) {
+            run_units += g_units[i];
+          } else {
+            if (run_o != kOffInvalid) bulk_s2g(ring + (size_t)run_o * kUnit, buf + run_s, run_units * kUnit);
+            run_o = o; run_s = g_soff[i]; run_units = (o != kOffInvalid) ? g_units[i] : 0;
+          }
+        }
+        if (run_o != kOffInvalid) bulk_s2g(ring + (size_t)run_o * kUnit, buf + run_s, run_units * kUnit);
+      } else {
+        uint32_t rem = any;
+        while (rem) {
+          const int l = __ffs(rem) - 1;
+          rem &= rem - 1;
+          uint8_t* ring = s.rings + (size_t)(wd * 32 + l) * s.ring_bytes;
+          uint32_t run_o = kOffInvalid, run_units = 0, run_s = 0;
+#pragma unroll
+          for (int i = 0; i <= (int)kCmGroup; i++) {
+            const uint32_t o = i < (int)kCmGroup ? __shfl_sync(0xffffffffu, offs[i < (int)kCmGroup ? i : 0], l) : kOffInvalid;
+            if (o != kOffInvalid && run_o != kOffInvalid && o == run_o + run_units) {
+              run_units += g_units[i];
+            } else {
+              if (run_o != kOffInvalid) {  // warp-cooperative copy of one contiguous run
+                const uint4* src = reinterpret_cast<const uint4*>(buf + run_s);
+                uint4* dst = reinterpret_cast<uint4*>(ring + (size_t)run_o * kUnit);
+                const uint32_t nvec = run_units * 2;
+                for (uint32_t v = lane; v < nvec; v += 128) {
+                  const bool p1 = v + 32 < nvec, p2 = v + 64 < nvec, p3 = v + 96 < nvec;
+                  uint4 x0 = src[v], x1, x2, x3;
+                  if (p1) x1 = src[v + 32];
+                  if (p2) x2 = src[v + 64];
+                  if (p3) x3 = src[v + 96];
+                  st_stream16(dst + v, x0);
+                  if (p1) st_stream16(dst + v + 32, x1);
+                  if (p2) st_stream16(dst + v + 64, x2);
+                  if (p3) st_stream16(dst + v + 96, x3);
+                }
+              }
+              run_o = o;
+              if (i < (int)kCmGroup) { run_s = g_soff[i]; run_units = (o != kOffInvalid) ? g_units[i] : 0; }
+            }
+          }
+        }
+      }
+    }
+    if (VARIANT == 1) bulk_commit();
+    __syncthreads();  // all reads of g_* / t_info done before thread 0 starts the next tile
+  }
+  if (VARIANT == 1) bulk_wait_read0();  // the next phase reuses buf
 }
 
 // =============================================================================== K2b pack (thin)
 // Warp per scatter-list entry (messages with < kFatMin recipients, all direct messages): 16-byte
 // read-only loads from the frame slot, length prefix patched into the first vector, 16-byte stores.
-__global__ void __launch_bounds__(256) k_pack_thin(DevState s, BatchIn b, Work w) {
-  if (w.stats->status) return;
+__device__ __forceinline__ void pack_thin_phase(const DevState& s, const BatchIn& b, const Work& w) {
   const uint32_t n = w.stats->n_thin_entries;
   const uint32_t lane = lane_id();
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -672,14 +876,36 @@ __global__ void __launch_bounds__(256) k_pack_thin(DevState s, BatchIn b, Work w
   }
 }
 
+// One launch runs the three pack phases back to back in persistent CTAs (each phase pulls its own
+// work from its own cursor, so CTAs drift from phase to phase without a grid barrier; the phases
+// write disjoint records).
+template <int VARIANT>
+__global__ void __launch_bounds__(256) k_pack(DevState s, BatchIn b, Work w) {
+  __shared__ __align__(128) uint8_t buf[kCmGroup * kCmMaxBytes];  // 32 KB; the fat phase uses the first 16 KB
+  __shared__ __align__(8) uint64_t bars[2];
+  if (w.stats->status) return;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  pack_cm_phase<VARIANT>(s, b, w, buf, &bars[0]);
+  __syncthreads();
+  pack_fat_phase<VARIANT>(s, b, w, buf, &bars[1]);
+  pack_thin_phase(s, b, w);
+}
+
 int pack_setup() { return 0; }
 
 void launch_pack(const DevState& s, const Work& w, const BatchIn& b, uint32_t variant, int n_sms, cudaStream_t st) {
-  const uint32_t ctas_per_sm = (variant >> 8) ? (variant >> 8) : 4;
+  // Default (variant 0): TMA bulk stores, 3 CTAs per SM — the best of the sweep in profiles/.
+  // A/B switches for profiling: bit 2 = st.global.cs.v4 stores instead of bulk stores; bit 1 = no
+  // connection-major class (DevState::cm_enable, read by k_plan_a); bits 8+ = CTAs per SM.
+  const uint32_t ctas_per_sm = (variant >> 8) ? (variant >> 8) : 3;
   const uint32_t grid = (uint32_t)n_sms * ctas_per_sm;
-  if ((variant & 0xFF) == 1) k_pack_fat<1><<<grid, 256, 0, st>>>(s, b, w);
-  else k_pack_fat<0><<<grid, 256, 0, st>>>(s, b, w);
-  k_pack_thin<<<(uint32_t)n_sms * 8, 256, 0, st>>>(s, b, w);
+  if (variant & 4) k_pack<0><<<grid, 256, 0, st>>>(s, b, w);
+  else k_pack<1><<<grid, 256, 0, st>>>(s, b, w);
 }
 
 // =============================================================================== release

@@ -27,6 +27,13 @@ constexpr uint32_t kFatMin = 32;             // >= this many recipients → stag
 constexpr uint32_t kChunkBytes = 16384;      // shared-memory staging chunk of the fat path
 constexpr uint32_t kTileRecipients = 1024;   // recipients per fat tile
 constexpr uint32_t kBlockWords = 256;        // bitmap words per match block (8192 connections)
+// connection-major (cm) pack path: dense messages with small records are grouped and written
+// connection by connection, so that one connection's records form ONE contiguous run in its ring
+constexpr uint32_t kCmGroup = 8;             // messages staged together in shared memory
+constexpr uint32_t kCmMaxBytes = 4096;       // largest padded record that takes the cm path
+constexpr uint32_t kCmTileWords = 16;        // bitmap words (512 connections) per cm tile
+constexpr uint32_t kCmDenseShift = 4;        // cm needs D >= N/16 recipients
+enum : uint8_t { CLS_THIN = 0, CLS_FAT = 1, CLS_CM = 2 };
 
 // device-resident routing state + rings
 struct DevState {
@@ -41,6 +48,7 @@ struct DevState {
   uint32_t N, W, T, nblk;
   uint32_t bucket_mask, key_stride;
   uint32_t ring_units;   // ring_bytes / 32
+  uint32_t cm_enable;    // connection-major pack class on (default) / off (A/B profiling)
   uint64_t ring_bytes;
   uint64_t seed;
 };
@@ -70,6 +78,8 @@ struct BatchStats {
   uint32_t n_thin_entries;
   uint32_t n_fat_tiles;
   uint32_t tile_cursor;
+  uint32_t n_cm;            // messages on the connection-major path
+  uint32_t cm_cursor;
 };
 
 struct Span { uint32_t conn, ring_off, len, n_records; };
@@ -85,8 +95,14 @@ struct Work {
   uint32_t* eb_fat;      // [max_msgs+1] scatter-list base per message (fat list)
   uint32_t* eb_thin;     // [max_msgs+1]
   uint32_t* tbase;       // [max_msgs+1] fat tile base per message
-  uint32_t* scan_tmp;    // [3 * nscanblk] block totals of the plan scan
-  uint2* efat;           // [cap_fat]  {conn, ring offset in units}
+  uint32_t* scan_tmp;    // [4 * nscanblk] block totals of the plan scan
+  uint8_t* cls;          // [max_msgs] CLS_THIN / CLS_FAT / CLS_CM
+  uint32_t* cm_rank;     // [max_msgs+1] rank among cm messages
+  uint32_t* cm_list;     // [max_bcast] cm rank → message index
+  uint32_t* jidx;        // [max_msgs] message index → broadcast slot j
+  uint2* efat;           // [cap_fat]  {conn, ring offset in units} — message-major (fat) class
+  uint32_t* ecm;         // [cap_fat]  ring offset in units — connection-major class (the connection is
+                         //            implied by the rank, so 4 bytes per delivery instead of 8)
   uint4* ethin;          // [cap_thin] {conn, ring offset in units, slot_off16, raw_len}
   uint32_t cap_fat, cap_thin;
   // direct buckets

@@ -21,8 +21,9 @@ def test_reference_scenario_on_gpu(pcdn, scenario):
 
 @pytest.mark.parametrize("scenario", [scenarios.test_broadcast_user, scenarios.test_fifo_order],
                          ids=lambda f: f.__name__)
-def test_reference_scenario_bulk_store_variant(pcdn, scenario):
-    scenario(EngineBackend(pcdn, pack_variant=1))
+def test_reference_scenario_st_variant(pcdn, scenario):
+    """A/B variant: st.global.cs.v4 stores instead of TMA bulk stores"""
+    scenario(EngineBackend(pcdn, pack_variant=4))
 
 
 # ------------------------------------------------------------------ differential harness
@@ -112,7 +113,7 @@ def payload(rng, n):
     return bytes(rng.getrandbits(8) for _ in range(min(n, 64))) * (n // 64 + 1)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 4, 2])
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_random_mixed_batches(pcdn, seed, variant):
     """users + peer brokers, multi-topic broadcasts (fat and thin recipient sets), directs to local,
