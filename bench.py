@@ -275,7 +275,6 @@ def main():
         drain_device()                        # waits (on the stream) for the last pack
         ev1.record(stream)
         sync_all()
-        clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -340,7 +339,7 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("k_pack_fat_dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("k_pack_dram_bytes_per_launch")
         except Exception:
             traffic = None
 
@@ -373,6 +372,7 @@ def main():
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = world * egress_step * e2e_steps / float(t_e2e.item()) / 1e9
+    clocks = sampler.stop()  # sampled from the start of the timed region to the end of the e2e loop (all under load)
     h2d = M * slot + 64 + 22 * M + 64 if (world == 1 or rank == 0) else 0
     d2h = 64 + 16 * n_conns
 
