@@ -1,0 +1,261 @@
+#!/usr/bin/env python
+"""bench_configs.py — the other BASELINE.json configs (C3, C4, C5) as secondary measurements.
+
+`bench.py` is the driver-facing benchmark (config C2).  This script measures the remaining configs
+of BASELINE.json on ONE GPU with the same rules (inputs resident in HBM, CUDA events on the engine's
+stream, >= 3 warm-up steps, outputs far larger than L2) and prints one JSON line per workload:
+
+    python bench_configs.py --workload C4        # direct path: 2^20 128-byte keys, 2^20 msgs/batch, 512 B
+    python bench_configs.py --workload C3        # 64 K subs, 4 K topics Zipf-0.99, 256 B-64 KiB payloads
+    python bench_configs.py --workload C5dense   # one shard of config 5: 2^20 subs, 4 KiB broadcast
+    python bench_configs.py --workload C5sparse  # 1 K topics, 4 subscriptions per connection
+
+Correctness of these paths is covered bit-exactly (against the oracle) by tests/test_gpu_parity.py and
+tests/test_gpu_configs.py at sizes the oracle finishes in seconds; here only the engine's own counters
+are cross-checked against the analytically expected delivery counts.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import bench as B  # noqa: E402  (helpers only)
+
+
+def direct_frame_template(key_len: int, payload_len: int):
+    """single-segment Direct{recipient[key_len], message[payload_len]}; returns
+    (frame bytes with zero recipient/payload, recipient offset, payload offset)"""
+    rw, pw = (key_len + 7) // 8, (payload_len + 7) // 8
+    words = 5 + rw + pw
+    out = bytearray()
+    out += (0).to_bytes(4, "little") + words.to_bytes(4, "little")
+    out += bytes.fromhex("0000000001000100")
+    out += (3).to_bytes(8, "little")
+    out += bytes.fromhex("0000000000000200")
+    out += (5).to_bytes(4, "little") + (2 | (key_len << 3)).to_bytes(4, "little")
+    out += ((rw << 2) | 1).to_bytes(4, "little") + (2 | (payload_len << 3)).to_bytes(4, "little")
+    roff = len(out)
+    out += bytes(rw * 8)
+    poff = len(out)
+    out += bytes(pw * 8)
+    return bytes(out), roff, poff
+
+
+def bcast_frame_n(topics_bytes: bytes, payload: bytes) -> bytes:
+    n, k = len(topics_bytes), len(payload)
+    tw = (n + 7) // 8
+    words = 5 + tw + (k + 7) // 8
+    out = bytearray()
+    out += (0).to_bytes(4, "little") + words.to_bytes(4, "little")
+    out += bytes.fromhex("0000000001000100") + (4).to_bytes(8, "little") + bytes.fromhex("0000000000000200")
+    out += (5).to_bytes(4, "little") + (2 | (n << 3)).to_bytes(4, "little")
+    out += ((tw << 2) | 1).to_bytes(4, "little") + (2 | (k << 3)).to_bytes(4, "little")
+    out += topics_bytes + bytes((-n) % 8) + payload + bytes((-k) % 8)
+    return bytes(out)
+
+
+class DeviceBatch:
+    """device-resident batch in the layout of pcdn_device_batch (slots 16-byte aligned, raw at +4)"""
+
+    def __init__(self, pkg, torch, dev, arena_np, kind, flags, slot16, raw_len, aux_off, aux_len, topics, bidx):
+        t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev) if len(a) else torch.zeros(1, dtype=dt, device=dev)
+        self.arena = t(arena_np, torch.uint8)
+        self.kind = t(kind.astype(np.uint8), torch.uint8)
+        self.flags = t(flags.astype(np.uint8), torch.uint8)
+        self.slot = t(slot16.astype(np.int32), torch.int32)
+        self.len = t(raw_len.astype(np.int32), torch.int32)
+        self.aoff = t(aux_off.astype(np.int32), torch.int32)
+        self.alen = t(aux_len.astype(np.int32), torch.int32)
+        self.topics = t(topics.astype(np.int16), torch.int16)
+        self.bidx = t(bidx.astype(np.int32), torch.int32)
+        n, nb = len(kind), len(bidx)
+        self.db = pkg.DeviceBatch(n, nb, self.arena.data_ptr(), self.arena.numel(), self.kind.data_ptr(), self.flags.data_ptr(),
+                                  self.slot.data_ptr(), self.len.data_ptr(), self.aoff.data_ptr(), self.alen.data_ptr(),
+                                  self.topics.data_ptr(), len(topics), self.bidx.data_ptr())
+
+
+def zipf_p(n, s=0.99):
+    p = 1.0 / np.arange(1, n + 1) ** s
+    return p / p.sum()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", required=True, choices=["C3", "C4", "C5dense", "C5sparse"])
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--hit", type=float, default=1.0, help="C4: fraction of recipients that exist")
+    args = ap.parse_args()
+    import torch
+
+    import __graft_entry__ as ge
+
+    pkg = ge.load_package()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream(device=dev)
+    wl = args.workload
+    t_setup = time.time()
+
+    if wl == "C4":
+        n, klen, K = 1 << 20, 128, 512
+        rng = np.random.default_rng(6)
+        keys = rng.integers(0, 256, size=(n, klen), dtype=np.uint8)
+        keys[:, :8] = np.arange(n, dtype=np.uint64).view(np.uint8).reshape(n, 8)  # distinct
+        tmpl, roff, poff = direct_frame_template(klen, K)
+        L = len(tmpl); slot = (4 + L + 15) // 16 * 16
+        M = n
+        eng = pkg.Engine(device=0, stream=stream.cuda_stream, max_conns=n, max_topics=16, max_keys=n, max_key_len=klen,
+                         ring_bytes_per_conn=16384, max_batch_msgs=M, max_batch_bcast=1, max_batch_bytes=M * slot + (1 << 16),
+                         max_batch_deliveries=M + 1024, batch_slots=2, pack_variant=args.variant)
+        conns = eng.add_users_bulk(keys, klen)
+        rcpt = rng.integers(0, n, size=M)
+        arena = np.zeros((M, slot), dtype=np.uint8)
+        arena[:, 4:4 + L] = np.frombuffer(tmpl, dtype=np.uint8)
+        arena[:, 4 + roff:4 + roff + klen] = keys[rcpt]
+        if args.hit < 1.0:
+            miss = rng.random(M) >= args.hit
+            arena[miss, 4 + roff + 8] ^= 0xFF  # unknown keys: must be dropped
+        arena[:, 4 + poff:4 + poff + K] = rng.integers(0, 256, size=(1, K), dtype=np.uint8)
+        idx = np.arange(M, dtype=np.int64)
+        db = DeviceBatch(pkg, torch, dev, np.concatenate([arena.reshape(-1), np.zeros(64, np.uint8)]), np.full(M, 3), np.zeros(M),
+                         idx * (slot // 16), np.full(M, L), idx * slot + 4 + roff, np.full(M, klen), np.zeros(1), np.zeros(0))
+        expect_deliveries = None if args.hit < 1.0 else M
+        alg_bytes = lambda d, bo: d * 0 + bo + M * L + M * (klen + 32)  # F per hit + L read + key compare + bucket sector
+        desc = {"workload": "C4: direct path, 2^20 128-byte keys, uniform recipients, 512 B payloads, %d msgs per step" % M,
+                "hit_rate": args.hit}
+        F = 4 + L
+    elif wl == "C3":
+        n, T, M = 65536, 4096, 128
+        rng = np.random.default_rng(3)
+        p = zipf_p(T)
+        keys = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        keys[:, :8] = np.arange(n, dtype=np.uint64).view(np.uint8).reshape(n, 8)
+        subs = np.stack([rng.choice(T, size=8, replace=False, p=p) for _ in range(n)]).astype(np.uint16)
+        eng = pkg.Engine(device=0, stream=stream.cuda_stream, max_conns=n, max_topics=T, max_keys=n, max_key_len=32,
+                         ring_bytes_per_conn=1 << 20, max_batch_msgs=M, max_batch_bcast=M, max_batch_bytes=16 << 20,
+                         max_batch_deliveries=M * n, batch_slots=2, pack_variant=args.variant)
+        eng.add_users_bulk(keys, 32, subs.reshape(-1).copy(), (np.arange(n + 1) * 8).astype(np.uint32))
+        rng4, rng5 = np.random.default_rng(4), np.random.default_rng(5)
+        topics = rng4.choice(T, size=M, p=p)
+        sizes = rng5.choice([256 << i for i in range(9)], size=M)
+        frames = [bcast_frame_n(bytes([int(t) & 0xFF]), bytes(rng5.integers(0, 256, size=int(k), dtype=np.uint8))) for t, k in zip(topics, sizes)]
+        offs, cur = [], 0
+        for fr in frames:
+            offs.append(cur); cur += (4 + len(fr) + 15) // 16 * 16
+        arena = np.zeros(cur + 64, dtype=np.uint8)
+        for o, fr in zip(offs, frames):
+            arena[o + 4:o + 4 + len(fr)] = np.frombuffer(fr, dtype=np.uint8)
+        lens = np.array([len(f) for f in frames])
+        db = DeviceBatch(pkg, torch, dev, arena, np.full(M, 4), np.zeros(M), np.array(offs) // 16, lens, np.arange(M), np.ones(M),
+                         topics.astype(np.int64), np.arange(M))
+        per_topic = np.bincount(subs.reshape(-1), minlength=T)
+        expect_deliveries = int(per_topic[topics].sum())
+        alg_bytes = lambda d, bo: bo + int(lens.sum()) + M * (n // 8)
+        desc = {"workload": "C3: 64 K subscribers, 4 K topics (extended ids) Zipf-0.99, 8 subscriptions each, payloads 256 B-64 KiB, %d msgs per step" % M}
+        F = None
+    else:
+        n, K = 1 << 20, 4096
+        dense = wl == "C5dense"
+        M = 8 if dense else 64
+        T = 1 if dense else 1024
+        rng = np.random.default_rng(7)
+        keys = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        keys[:, :8] = np.arange(n, dtype=np.uint64).view(np.uint8).reshape(n, 8)
+        if dense:
+            subs = np.zeros((n, 1), dtype=np.uint16)
+        else:
+            subs = np.stack([rng.permutation(T)[:4] for _ in range(1024)])[rng.integers(0, 1024, size=n)].astype(np.uint16)
+        frames = [bcast_frame_n(bytes([m & 0xFF]), bytes(((i * 31 + m) & 0xFF) for i in range(K))) for m in range(M)]
+        L = len(frames[0]); slot = (4 + L + 15) // 16 * 16; rec = (4 + L + 31) // 32 * 32
+        eng = pkg.Engine(device=0, stream=stream.cuda_stream, max_conns=n, max_topics=max(T, 16), max_keys=n, max_key_len=32,
+                         ring_bytes_per_conn=16 * rec, max_batch_msgs=M, max_batch_bcast=M, max_batch_bytes=4 << 20,
+                         max_batch_deliveries=M * n if dense else 1 << 22, batch_slots=2, pack_variant=args.variant)
+        nsub = subs.shape[1]
+        eng.add_users_bulk(keys, 32, subs.reshape(-1).copy(), (np.arange(n + 1) * nsub).astype(np.uint32))
+        topics = np.zeros(M, dtype=np.int64) if dense else rng.integers(0, T, size=M)
+        arena = np.zeros(M * slot + 64, dtype=np.uint8)
+        for m, fr in enumerate(frames):
+            arena[m * slot + 4:m * slot + 4 + L] = np.frombuffer(fr, dtype=np.uint8)
+        db = DeviceBatch(pkg, torch, dev, arena, np.full(M, 4), np.zeros(M), np.arange(M) * (slot // 16), np.full(M, L), np.arange(M),
+                         np.ones(M), topics, np.arange(M))
+        per_topic = np.bincount(subs.reshape(-1), minlength=max(T, 1))
+        expect_deliveries = int(per_topic[topics].sum())
+        alg_bytes = lambda d, bo: bo + M * L + M * (n // 8)
+        desc = {"workload": ("C5 shard, dense: 2^20 subscribers on 1 topic, 4 KiB broadcast, %d msgs per step" if dense else
+                             "C5 shard, sparse: 2^20 subscribers, 1 K topics (extended ids), 4 uniform subscriptions each, 4 KiB broadcast, %d msgs per step") % M}
+        F = 4 + L
+    setup_s = time.time() - t_setup
+
+    prev = 0
+    with torch.cuda.stream(stream):
+        def step():
+            nonlocal prev
+            b = eng.submit_device(db.db)
+            if prev:
+                eng.release_batch(prev)
+            prev = b
+
+        def drain():
+            nonlocal prev
+            if prev:
+                eng.release_batch(prev)
+                prev = 0
+
+        for _ in range(max(3, args.warmup)):
+            step()
+        drain()
+        torch.cuda.synchronize(dev)
+        sampler = B.ClockSampler(0)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        drain()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        # counters of one batch + per-stage device times
+        eng.set_timing(True)
+        s0 = eng.stats()
+        res = None
+        for _ in range(max(3, args.steps // 2)):
+            b = eng.submit_device(db.db)
+            res = eng.poll(b)
+            d, bo, dropped, ovf, status = res.n_deliveries, res.bytes_out, res.n_direct_dropped, res.n_overflow, res.status
+            eng.release_batch(b)
+        s1 = eng.stats()
+        clocks = sampler.stop()
+    assert status == 0 and ovf == 0, (status, ovf)
+    if expect_deliveries is not None:
+        assert d == expect_deliveries, (d, expect_deliveries)
+    nb = max(1, s1.timed_batches - s0.timed_batches)
+    st = {k: (getattr(s1, k) - getattr(s0, k)) / nb for k in ("ms_direct", "ms_match", "ms_plan", "ms_pack")}
+    peak, peak_src = B.measured_peak()
+    step_s = ms * 1e-3 / args.steps
+    ab = alg_bytes(d, bo)
+    pack_bytes = bo + int(db.len.sum().item())
+    line = {
+        "metric": "fan-out egress GB/s; msgs/s and deliveries/s alongside (secondary config)", "value": bo / step_s / 1e9, "unit": "GB/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "dtype": "u8", "data": "synthetic", "msgs_per_s": res.n_msgs / step_s, "deliveries_per_s": d / step_s,
+        "deliveries_per_step": int(d), "direct_dropped_per_step": int(dropped),
+        "algorithmic_GBps": ab / step_s / 1e9, "frac_of_hbm_peak": ab / step_s / 1e9 / peak,
+        "config": dict(desc, setup_s=round(setup_s, 1), pack_variant=args.variant),
+        "roofline": {"bound": "hbm", "kernel": "k_pack", "achieved": pack_bytes / (st["ms_pack"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": pack_bytes / (st["ms_pack"] * 1e-3) / 1e9 / peak, "peak_source": peak_src, "stage_ms": st},
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
