@@ -89,8 +89,19 @@ typedef struct pcdn_config {
   void* stream;                 /* optional cudaStream_t to run on (e.g. torch's); NULL = own   */
   const char* identity;         /* this broker's BrokerIdentifier string "public/private"       */
   uint32_t pack_variant;        /* 0 = default; see DESIGN.md (kernel selection for profiling)  */
-  uint32_t reserved;
+  uint32_t flags;               /* PCDN_FLAG_*                                                  */
 } pcdn_config;
+
+/* pcdn_config.flags */
+enum {
+  /* Ingress parse on the device: pcdn_user_receive / pcdn_broker_receive /
+   * pcdn_receive_frames only peek the union tag of Broadcast/Direct frames and copy the raw bytes;
+   * the Cap'n Proto walk, Topic::prune and the recipient extraction run in a kernel (k_parse) and
+   * the per-message outcome comes back in pcdn_batch_result.msg_status.  Other kinds keep the host
+   * path.  Deviation: a malformed / all-topics-invalid frame is reported after the batch instead of
+   * synchronously, so later frames of that sender inside the same batch are still routed. */
+  PCDN_FLAG_DEVICE_PARSE = 1
+};
 
 /* One routed message.  `raw` is the inbound frame body and is forwarded verbatim (R1). */
 typedef struct pcdn_msg {
@@ -125,6 +136,9 @@ typedef struct pcdn_batch_result {
   const pcdn_conn* overflow_conns; /* engine-owned                                              */
   uint32_t n_direct_dropped;       /* direct messages with no route (handler.rs:210,224)        */
   uint32_t status;                 /* 0 or PCDN_E2BIG (as positive number)                      */
+  const int8_t* msg_status;        /* device-parse batches: per message 0 or PCDN_EPARSE / PCDN_EPRUNE (the reference would have ended that sender's receive loop); NULL otherwise */
+  uint32_t n_msg_errors;           /* number of non-zero entries in msg_status                  */
+  uint32_t reserved;
 } pcdn_batch_result;
 
 /* Device-resident batch (inputs already in HBM; used by bench `value` and the NCCL ingest path).
@@ -217,6 +231,18 @@ int pcdn_user_receive(pcdn_engine* e, const uint8_t* sender_key, uint32_t key_le
  * Broadcast only (to_user(s)_only = true, no prune); other kinds return 1 = "not routed here". */
 int pcdn_broker_receive(pcdn_engine* e, const char* identifier, const uint8_t* raw,
                         uint32_t raw_len);
+/* Many inbound frames in one call (one lock, no per-call FFI cost): frame i enters
+ * user_receive_loop (origin 0, `sender` = that user's key) or broker_receive_loop (origin 1).
+ * rc_out[i] (optional) gets what pcdn_user_receive / pcdn_broker_receive would have returned. */
+typedef struct pcdn_frame {
+  const uint8_t* sender;
+  uint32_t sender_len;
+  uint32_t origin;
+  const uint8_t* raw;
+  uint32_t raw_len;
+  uint32_t reserved;
+} pcdn_frame;
+int pcdn_receive_frames(pcdn_engine* e, const pcdn_frame* frames, uint32_t n, int32_t* rc_out);
 /* Close the open batch and launch it.  *batch_id = 0 when the batch was empty. */
 int pcdn_flush(pcdn_engine* e, uint64_t* batch_id);
 /* Submit an explicit ordered batch (R9: batch order = per-connection delivery order). */

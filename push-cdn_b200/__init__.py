@@ -25,7 +25,7 @@ LIB_PATH = os.path.join(_HERE, "libpcdn_fanout.so")
 INCLUDE = os.path.join(_ROOT, "include")
 
 SOURCES = ["engine.cu", "kernels.cu", "host_state.cpp", "frame_parse.cpp"]
-HEADERS = ["kernels.cuh", "host_state.h", "frame_parse.h", "hash.h"]
+HEADERS = ["kernels.cuh", "host_state.h", "frame_parse.h", "frame_parse_core.h", "hash.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
@@ -33,6 +33,7 @@ NVCC_FLAGS = [
 
 KIND_DIRECT, KIND_BROADCAST, KIND_SUBSCRIBE, KIND_UNSUBSCRIBE = 3, 4, 5, 6
 TO_USERS_ONLY = 1
+FLAG_DEVICE_PARSE = 1
 RECORD_ALIGN = 32
 CONN_NONE = 0xFFFFFFFF
 
@@ -79,7 +80,7 @@ class Config(C.Structure):
         ("max_batch_msgs", C.c_uint32), ("max_batch_bcast", C.c_uint32), ("max_batch_bytes", C.c_uint64),
         ("max_batch_deliveries", C.c_uint64), ("batch_slots", C.c_uint32), ("n_valid_topics", C.c_uint32),
         ("hash_seed", C.c_uint64), ("stream", C.c_void_p), ("identity", C.c_char_p), ("pack_variant", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("flags", C.c_uint32),
     ]
 
 
@@ -99,6 +100,7 @@ class BatchResult(C.Structure):
         ("batch_id", C.c_uint64), ("n_msgs", C.c_uint32), ("n_spans", C.c_uint32), ("spans", C.POINTER(Span)),
         ("n_deliveries", C.c_uint64), ("bytes_out", C.c_uint64), ("n_overflow", C.c_uint32),
         ("overflow_conns", C.POINTER(C.c_uint32)), ("n_direct_dropped", C.c_uint32), ("status", C.c_uint32),
+        ("msg_status", C.POINTER(C.c_int8)), ("n_msg_errors", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 
@@ -117,6 +119,11 @@ class Stats(C.Structure):
         ("ms_match", C.c_double), ("ms_plan", C.c_double), ("ms_direct", C.c_double), ("ms_pack", C.c_double),
         ("ms_total", C.c_double), ("timed_batches", C.c_uint64),
     ]
+
+
+class Frame(C.Structure):
+    _fields_ = [("sender", C.c_char_p), ("sender_len", C.c_uint32), ("origin", C.c_uint32), ("raw", C.c_char_p),
+                ("raw_len", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class UserSyncEntry(C.Structure):
@@ -145,6 +152,7 @@ ABI = {
     "pcdn_handle_direct_message": (_ci, [_vp, _u8p, _u32, _u8p, _u32, _ci]),
     "pcdn_user_receive": (_ci, [_vp, _u8p, _u32, _u8p, _u32]),
     "pcdn_broker_receive": (_ci, [_vp, _cp, _u8p, _u32]),
+    "pcdn_receive_frames": (_ci, [_vp, C.POINTER(Frame), _u32, C.POINTER(C.c_int32)]),
     "pcdn_flush": (_ci, [_vp, C.POINTER(_u64)]),
     "pcdn_submit": (_ci, [_vp, C.POINTER(Msg), _u32, C.POINTER(_u64)]),
     "pcdn_submit_device": (_ci, [_vp, C.POINTER(DeviceBatch), C.POINTER(_u64)]),
@@ -304,6 +312,16 @@ class Engine:
 
     def broker_receive(self, ident: str, raw: bytes) -> int:
         return self.L.pcdn_broker_receive(self.h, ident.encode(), raw, len(raw))
+
+    def receive_frames(self, frames: Sequence[Tuple[bytes, int, bytes]]) -> List[int]:
+        """frames: (sender key, origin 0=user/1=broker, raw) → per-frame return codes"""
+        n = len(frames)
+        arr = (Frame * max(1, n))()
+        for i, (sender, origin, raw) in enumerate(frames):
+            arr[i] = Frame(sender, len(sender), origin, raw, len(raw), 0)
+        rcs = (C.c_int32 * max(1, n))()
+        self._chk(self.L.pcdn_receive_frames(self.h, arr, n, rcs))
+        return [rcs[i] for i in range(n)]
 
     def flush(self) -> int:
         b = C.c_uint64(0)

@@ -67,6 +67,9 @@ struct Slot {
   std::vector<uint32_t> slot_off16, raw_len, aux_off, aux_len, bcast_index;
   std::vector<uint16_t> topics;
   uint32_t n_direct = 0;
+  bool devparse = false;        // some messages carry MSGF_DEVPARSE (k_parse runs first)
+  int8_t* h_msg_status = nullptr;  // pinned
+  uint32_t n_msg_errors = 0;
   uint8_t* h_desc = nullptr;    // pinned descriptor block
   // device
   uint8_t* d_arena = nullptr;
@@ -186,7 +189,7 @@ int flush_journal(pcdn_engine* e) {
 }
 
 void slot_reset_open(Slot& s) {
-  s.arena_used = 0; s.n_direct = 0;
+  s.arena_used = 0; s.n_direct = 0; s.devparse = false; s.n_msg_errors = 0;
   s.kind.clear(); s.flags.clear(); s.slot_off16.clear(); s.raw_len.clear(); s.aux_off.clear(); s.aux_len.clear();
   s.bcast_index.clear(); s.topics.clear();
   s.polled = false; s.device_input = false; s.timed = false;
@@ -214,6 +217,7 @@ int launch_pipeline(pcdn_engine* e, Slot& s, uint32_t n_direct) {
   s.timed = e->timing;
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[0], st));
   launch_batch_begin(e->dev, s.w, s.in, has_direct, st);
+  if (s.devparse) launch_parse(e->dev, s.w, s.in, st);
   if (has_direct) launch_direct(e->dev, s.w, s.in, st);
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[1], st));
   launch_match(e->dev, s.w, s.in, st);
@@ -431,6 +435,8 @@ int init_device(pcdn_engine* e) {
   d.bucket_mask = g.bucket_mask; d.key_stride = g.key_stride; d.seed = g.seed;
   d.ring_bytes = c.ring_bytes_per_conn; d.ring_units = (uint32_t)(c.ring_bytes_per_conn / kUnit);
   d.cm_enable = (c.pack_variant & 2) ? 0 : 1;
+  d.n_valid_topics = c.n_valid_topics;
+  d.max_key_len = c.max_key_len;
   DEV_ALLOC(d.sub, (size_t)g.T * g.W);
   DEV_ALLOC(d.brk, g.W);
   DEV_ALLOC(d.owner_conn, g.max_owners);
@@ -487,6 +493,8 @@ int init_device(pcdn_engine* e) {
     DEV_ALLOC(w.batch_units, g.N);
     DEV_ALLOC(w.spans, (size_t)2 * g.N);
     DEV_ALLOC(w.overflow, g.N);
+    DEV_ALLOC(w.msg_status, M);
+    PIN_ALLOC(s.h_msg_status, M);
     DEV_ALLOC(w.stats, 1);
     PIN_ALLOC(s.h_stats, 1);
     PIN_ALLOC(s.h_early, 1);
@@ -698,9 +706,20 @@ int pcdn_handle_direct_message(pcdn_engine* e, const uint8_t* recipient, uint32_
   GUARD_END
 }
 
-int pcdn_user_receive(pcdn_engine* e, const uint8_t* sender_key, uint32_t key_len, const uint8_t* raw, uint32_t raw_len) {
-  GUARD_BEGIN
-  LOCK;
+// device-parse mode: Broadcast / Direct frames are only tag-peeked and copied; k_parse does the rest
+static int append_frame_devparse(pcdn_engine* e, int kind, bool from_broker, const uint8_t* raw, uint32_t raw_len) {
+  uint8_t flags = MSGF_DEVPARSE | (from_broker ? MSGF_USERS_ONLY : 0);
+  if (kind == PCDN_KIND_BROADCAST && !from_broker) flags |= MSGF_PRUNE;  // user-origin only (handler.rs:157 vs user/handler.rs:133)
+  int rc = append_msg(e, (uint8_t)kind, flags, nullptr, 0, nullptr, 0, raw, raw_len);
+  if (rc == 0) e->slots[e->open_slot].devparse = true;
+  return rc;
+}
+
+static int user_receive_locked(pcdn_engine* e, const uint8_t* sender_key, uint32_t key_len, const uint8_t* raw, uint32_t raw_len) {
+  if (e->cfg.flags & PCDN_FLAG_DEVICE_PARSE) {
+    const int k = peek_kind_core(raw, raw_len);
+    if (k == PCDN_KIND_DIRECT || k == PCDN_KIND_BROADCAST) return append_frame_devparse(e, k, false, raw, raw_len);
+  }
   ParsedFrame pf;
   if (!parse_frame(raw, raw_len, &pf)) return fail(PCDN_EPARSE, "failed to deserialize message");
   uint16_t topics[65536 / 8];
@@ -724,12 +743,13 @@ int pcdn_user_receive(pcdn_engine* e, const uint8_t* sender_key, uint32_t key_le
     default:
       return fail(PCDN_EKIND, "invalid message received");
   }
-  GUARD_END
 }
 
-int pcdn_broker_receive(pcdn_engine* e, const char* /*identifier*/, const uint8_t* raw, uint32_t raw_len) {
-  GUARD_BEGIN
-  LOCK;
+static int broker_receive_locked(pcdn_engine* e, const uint8_t* raw, uint32_t raw_len) {
+  if (e->cfg.flags & PCDN_FLAG_DEVICE_PARSE) {
+    const int k = peek_kind_core(raw, raw_len);
+    if (k == PCDN_KIND_DIRECT || k == PCDN_KIND_BROADCAST) return append_frame_devparse(e, k, true, raw, raw_len);
+  }
   ParsedFrame pf;
   if (!parse_frame(raw, raw_len, &pf)) return fail(PCDN_EPARSE, "failed to deserialize message");
   if (pf.kind == PCDN_KIND_DIRECT)
@@ -741,6 +761,36 @@ int pcdn_broker_receive(pcdn_engine* e, const char* /*identifier*/, const uint8_
     return append_msg(e, PCDN_KIND_BROADCAST, PCDN_TO_USERS_ONLY, topics, pf.f0_len, nullptr, 0, raw, raw_len);
   }
   return 1;
+}
+
+int pcdn_user_receive(pcdn_engine* e, const uint8_t* sender_key, uint32_t key_len, const uint8_t* raw, uint32_t raw_len) {
+  GUARD_BEGIN
+  LOCK;
+  return user_receive_locked(e, sender_key, key_len, raw, raw_len);
+  GUARD_END
+}
+
+int pcdn_broker_receive(pcdn_engine* e, const char* /*identifier*/, const uint8_t* raw, uint32_t raw_len) {
+  GUARD_BEGIN
+  LOCK;
+  return broker_receive_locked(e, raw, raw_len);
+  GUARD_END
+}
+
+int pcdn_receive_frames(pcdn_engine* e, const pcdn_frame* frames, uint32_t n, int32_t* rc_out) {
+  GUARD_BEGIN
+  LOCK;
+  int first_err = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const pcdn_frame& f = frames[i];
+    int rc = f.origin ? broker_receive_locked(e, f.raw, f.raw_len) : user_receive_locked(e, f.sender, f.sender_len, f.raw, f.raw_len);
+    if (rc_out) rc_out[i] = rc;
+    // capacity problems stop the call (the caller polls/releases and resumes at i); protocol errors
+    // of a single frame (the reference would drop that peer) do not
+    if (rc == PCDN_EAGAIN || rc == PCDN_ENOSPC || rc == PCDN_ECUDA || rc == PCDN_ENODEV) return rc;
+    if (rc < 0 && !first_err) first_err = rc;
+  }
+  return 0;
   GUARD_END
 }
 
@@ -794,6 +844,7 @@ int pcdn_submit_device(pcdn_engine* e, const pcdn_device_batch* b, uint64_t* bat
   s.in.topics = b->topics;
   s.in.bcast_index = b->bcast_index;
   s.device_input = true;
+  s.devparse = false;
   rc = launch_pipeline(e, s, b->n_msgs - b->n_bcast);
   if (rc) { s.state = SLOT_FREE; e->open_slot = -1; return rc; }
   if (batch_id) *batch_id = s.batch_id;
@@ -830,7 +881,9 @@ int pcdn_poll(pcdn_engine* e, uint64_t batch_id, pcdn_batch_result* out, int blo
     if (nov) CUDA_TRY(cudaMemcpyAsync(s->h_overflow, s->w.overflow, (size_t)nov * 4, cudaMemcpyDeviceToHost, e->copy_stream));
     // 2. the pack itself (ring bytes are valid after this)
     CUDA_TRY(cudaEventSynchronize(s->ev_done));
-    if (nsp || nov) CUDA_TRY(cudaStreamSynchronize(e->copy_stream));
+    if (s->devparse) CUDA_TRY(cudaMemcpyAsync(s->h_msg_status, s->w.msg_status, s->in.n_msgs, cudaMemcpyDeviceToHost, e->copy_stream));
+    if (nsp || nov || s->devparse) CUDA_TRY(cudaStreamSynchronize(e->copy_stream));
+    if (s->devparse) { s->n_msg_errors = 0; for (uint32_t i = 0; i < s->in.n_msgs; i++) s->n_msg_errors += s->h_msg_status[i] != 0; }
     const BatchStats& bs = *s->h_stats;
     s->polled = true;
     e->stats.deliveries += bs.n_deliveries;
@@ -859,6 +912,9 @@ int pcdn_poll(pcdn_engine* e, uint64_t batch_id, pcdn_batch_result* out, int blo
     out->overflow_conns = s->h_overflow;
     out->n_direct_dropped = bs.n_direct_dropped;
     out->status = bs.status ? (uint32_t)(-PCDN_E2BIG) : 0;
+    out->msg_status = s->devparse ? s->h_msg_status : nullptr;
+    out->n_msg_errors = s->n_msg_errors;
+    out->reserved = 0;
   }
   return 0;
   GUARD_END

@@ -1,25 +1,13 @@
-// frame_parse.h — ingress parse of a cdn-proto frame body, restating what the broker's receive
-// loops need from Message::deserialize (cdn-proto/src/message.rs:212-312): the union tag and, for
-// the routed kinds, WHERE inside the raw bytes the topics / recipient lie.  Nothing is copied — the
-// broker forwards the raw bytes verbatim (R1), and the direct-lookup kernel reads the recipient key
+// frame_parse.h — host ingress parse of a cdn-proto frame body (see frame_parse_core.h for the
+// walk itself, which is shared with the device parse kernel).  Nothing is copied: the broker
+// forwards the raw bytes verbatim (R1) and the direct-lookup kernel reads the recipient key
 // straight out of the frame in HBM.
-//
-// Wire layout: Cap'n Proto stream framing (u32 LE nseg-1, nseg × u32 LE words, pad to 8) followed by
-// the segments; Message = 1 data word (u16 union tag @0) + 1 pointer (messages_capnp.rs:175);
-// Direct/Broadcast = 0 data + 2 pointers (:1438,:1687); far pointers (single and double) are
-// followed because capnp-rust spills payloads that do not fit its 1024-word first segment.
 #pragma once
 #include <cstdint>
 
-namespace pcdn {
+#include "frame_parse_core.h"
 
-struct ParsedFrame {
-  int kind = -1;           // capnp union tag 0..8
-  uint32_t f0_off = 0;     // byte offset in raw of field 0 (topics list / recipient / sync blob)
-  uint32_t f0_len = 0;
-  uint32_t f1_off = 0;     // Direct.message / Broadcast.message
-  uint32_t f1_len = 0;
-};
+namespace pcdn {
 
 // returns true and fills `out`, or false = Error::Deserialize (the peer is disconnected)
 bool parse_frame(const uint8_t* raw, uint32_t len, ParsedFrame* out);

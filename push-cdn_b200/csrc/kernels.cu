@@ -3,6 +3,8 @@
 // bound by HBM bandwidth; there is deliberately no tensor-core code.
 #include "kernels.cuh"
 
+#include "frame_parse_core.h"
+
 namespace pcdn {
 
 // =============================================================================== small helpers
@@ -158,6 +160,49 @@ static void scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tm
     k_scan_b<<<1, 256, 0, st>>>(tmp, tiles);
     k_scan_c<<<(n + 255) / 256, 256, 0, st>>>(out, n, tmp);
   }
+}
+
+// =============================================================================== K0 ingress parse
+// Thread per message (device-parse mode): the same Cap'n Proto walk the host parser
+// runs (frame_parse_core.h, compiled for both), on the raw frame already resident in the arena.
+// Fills the routing fields the later kernels read — for a broadcast the wire topic list is used IN
+// PLACE (byte offset + count, Topic::prune applied while matching), for a direct message the
+// recipient key is read in place — and records a per-message outcome.  Host work per frame drops
+// to a tag peek and one memcpy.
+__global__ void __launch_bounds__(256) k_parse(DevState s, BatchIn b, Work w) {
+  const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= b.n_msgs) return;
+  uint8_t fl = b.flags[m];
+  if (!(fl & MSGF_DEVPARSE)) return;
+  const uint32_t slot_b = b.slot_off16[m] * 16u, len = b.raw_len[m];
+  const uint8_t* raw = b.arena + slot_b + 4;
+  uint8_t kind = b.kind[m];
+  uint32_t aoff = 0, alen = 0;
+  int8_t st = 0;
+  ParsedFrame pf;
+  if (!parse_frame_core(raw, len, &pf) || pf.kind != (int)kind) {
+    st = kErrParse; kind = 0;
+  } else if (kind == 4) {
+    aoff = slot_b + 4 + pf.f0_off; alen = pf.f0_len; fl |= MSGF_TOPICS_U8;
+    if (fl & MSGF_PRUNE) {
+      uint32_t kept = 0;
+      for (uint32_t i = 0; i < alen; i++) kept += topic_kept(raw + pf.f0_off, i, s.n_valid_topics) ? 1u : 0u;
+      if (kept == 0) { st = kErrPrune; alen = 0; kind = 0; }  // Err("supplied no valid topics")
+    }
+  } else {  // direct: recipient key in place (word aligned in a valid message)
+    aoff = slot_b + 4 + pf.f0_off; alen = pf.f0_len;
+    if (alen > s.max_key_len || (aoff & 3)) kind = 0;  // longer than any registered key: no route
+  }
+  const_cast<uint8_t*>(b.kind)[m] = kind;
+  const_cast<uint8_t*>(b.flags)[m] = fl;
+  const_cast<uint32_t*>(b.aux_off)[m] = aoff;
+  const_cast<uint32_t*>(b.aux_len)[m] = alen;
+  w.msg_status[m] = st;
+  if (kind == 0) w.D[m] = 0;
+}
+void launch_parse(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st) {
+  cudaMemsetAsync(w.msg_status, 0, b.n_msgs, st);
+  k_parse<<<(b.n_msgs + 255) / 256, 256, 0, st>>>(s, b, w);
 }
 
 // =============================================================================== K3 direct lookup
@@ -338,12 +383,22 @@ __global__ void __launch_bounds__(256) k_match(DevState s, BatchIn b, Work w) {
   const uint32_t wd = blockIdx.x * kBlockWords + threadIdx.x;  // W is a multiple of 256
   const uint32_t m = b.bcast_index[j];
   const uint32_t toff = b.aux_off[m], tn = b.aux_len[m];
+  const uint32_t fl = b.flags[m];
   uint32_t word = 0;
-  for (uint32_t i = 0; i < tn; i++) {
-    const uint32_t t = b.topics[toff + i];
-    if (t < s.T) word |= s.sub[(size_t)t * s.W + wd];
+  if (fl & MSGF_TOPICS_U8) {  // wire topic list read in place (device-parse mode)
+    const uint8_t* tb = b.arena + toff;
+    for (uint32_t i = 0; i < tn; i++) {
+      if ((fl & MSGF_PRUNE) && !topic_kept(tb, i, s.n_valid_topics)) continue;
+      const uint32_t t = tb[i];
+      if (t < s.T) word |= s.sub[(size_t)t * s.W + wd];
+    }
+  } else {
+    for (uint32_t i = 0; i < tn; i++) {
+      const uint32_t t = b.topics[toff + i];
+      if (t < s.T) word |= s.sub[(size_t)t * s.W + wd];
+    }
   }
-  if (b.flags[m] & 1) word &= ~s.brk[wd];  // to_users_only (connections/mod.rs:111)
+  if (fl & MSGF_USERS_ONLY) word &= ~s.brk[wd];  // to_users_only (connections/mod.rs:111)
   w.B[(size_t)j * s.W + wd] = word;
   uint32_t tot, ex = block256_excl_scan(__popc(word), &tot, sm);
   w.wpre[(size_t)j * s.W + wd] = (uint16_t)ex;

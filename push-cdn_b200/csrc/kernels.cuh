@@ -34,6 +34,14 @@ constexpr uint32_t kCmMaxBytes = 4096;       // largest padded record that takes
 constexpr uint32_t kCmTileWords = 16;        // bitmap words (512 connections) per cm tile
 constexpr uint32_t kCmDenseShift = 4;        // cm needs D >= N/16 recipients
 enum : uint8_t { CLS_THIN = 0, CLS_FAT = 1, CLS_CM = 2 };
+// per-message flag bits (BatchIn::flags); bit 0 = PCDN_TO_USERS_ONLY
+enum : uint8_t {
+  MSGF_USERS_ONLY = 1,
+  MSGF_DEVPARSE = 2,   // k_parse fills kind / aux_off / aux_len from the raw frame
+  MSGF_TOPICS_U8 = 4,  // aux_off = byte offset in the arena of the wire topic list (u8 each)
+  MSGF_PRUNE = 8       // user-origin: apply Topic::prune while reading the wire topic list
+};
+constexpr int8_t kErrParse = -7, kErrPrune = -8;  // PCDN_EPARSE / PCDN_EPRUNE
 
 // device-resident routing state + rings
 struct DevState {
@@ -49,6 +57,8 @@ struct DevState {
   uint32_t bucket_mask, key_stride;
   uint32_t ring_units;   // ring_bytes / 32
   uint32_t cm_enable;    // connection-major pack class on (default) / off (A/B profiling)
+  uint32_t n_valid_topics;  // Topic::prune validity bound (0 = all)
+  uint32_t max_key_len;
   uint64_t ring_bytes;
   uint64_t seed;
 };
@@ -116,6 +126,7 @@ struct Work {
   uint32_t* batch_units; // [N] units consumed by this batch per connection (for release)
   Span* spans;           // [2*max_conns]
   uint32_t* overflow;    // [max_conns]
+  int8_t* msg_status;    // [max_msgs] device-parse outcome per message
   BatchStats* stats;
 };
 
@@ -128,6 +139,7 @@ void launch_apply_updates(const DevState& s, const Upd32* u32, uint32_t n32, con
                           uint32_t nslot, const uint32_t* key_slots, const uint8_t* key_bytes,
                           uint32_t nkeys, cudaStream_t st);
 void launch_batch_begin(const DevState& s, const Work& w, const BatchIn& b, bool has_direct, cudaStream_t st);
+void launch_parse(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st);
 void launch_direct(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st);
 void launch_match(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st);
 void launch_plan(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st);

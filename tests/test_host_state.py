@@ -40,8 +40,12 @@ def test_no_cpu_data_path(pcdn):
 def test_product_does_not_import_oracle(pcdn):
     src = open(os.path.join(ROOT, "push-cdn_b200", "__init__.py")).read()
     assert "oracle" not in src.replace("oracle's", "")
-    for f in os.listdir(os.path.join(ROOT, "push-cdn_b200", "csrc")):
-        assert "oracle" not in open(os.path.join(ROOT, "push-cdn_b200", "csrc", f)).read().lower(), f
+    pk = os.path.join(ROOT, "push-cdn_b200")
+    for d, _, files in os.walk(pk):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".cpp", ".h", ".py")):
+                src = open(os.path.join(d, f)).read().lower().replace("oracle's", "")
+                assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src, f
 
 
 def _mk(pcdn, **kw):
