@@ -91,6 +91,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--hit", type=float, default=1.0, help="C4: fraction of recipients that exist")
+    ap.add_argument("--ingest", choices=["host", "device"], default=None,
+                    help="C4 only: measure end-to-end ingest of RAW FRAMES from host memory through pcdn_receive_frames with the host parser or the device parse kernel")
     args = ap.parse_args()
     import torch
 
@@ -113,7 +115,8 @@ def main():
         M = n
         eng = pkg.Engine(device=0, stream=stream.cuda_stream, max_conns=n, max_topics=16, max_keys=n, max_key_len=klen,
                          ring_bytes_per_conn=16384, max_batch_msgs=M, max_batch_bcast=1, max_batch_bytes=M * slot + (1 << 16),
-                         max_batch_deliveries=M + 1024, batch_slots=2, pack_variant=args.variant)
+                         max_batch_deliveries=M + 1024, batch_slots=2, pack_variant=args.variant,
+                         flags=pkg.FLAG_DEVICE_PARSE if args.ingest == "device" else 0)
         conns = eng.add_users_bulk(keys, klen)
         rcpt = rng.integers(0, n, size=M)
         arena = np.zeros((M, slot), dtype=np.uint8)
@@ -192,6 +195,40 @@ def main():
                              "C5 shard, sparse: 2^20 subscribers, 1 K topics (extended ids), 4 uniform subscriptions each, 4 KiB broadcast, %d msgs per step") % M}
         F = 4 + L
     setup_s = time.time() - t_setup
+
+    if args.ingest:
+        # raw frames in pageable host memory → pcdn_receive_frames (tag peek or full parse + copy into
+        # pinned staging) → flush (H2D + kernels) → poll (D2H) → release; wall clock per batch
+        import ctypes as C
+        assert wl == "C4"
+        frames_np = np.ascontiguousarray(arena[:, 4:4 + L])
+        fa = (pkg.Frame * M)()
+        base = frames_np.ctypes.data
+        sender = keys[0].tobytes()
+        for i in range(M):
+            fa[i].sender = sender; fa[i].sender_len = klen; fa[i].origin = 0
+            fa[i].raw = C.cast(base + i * L, C.c_char_p); fa[i].raw_len = L
+        times = []
+        for it in range(2 + args.steps):
+            t0 = time.perf_counter()
+            rc = eng.L.pcdn_receive_frames(eng.h, fa, M, None)
+            assert rc == 0, rc
+            t1 = time.perf_counter()
+            b = eng.flush()
+            res = eng.poll(b)
+            assert res.n_deliveries == M and res.n_msg_errors == 0, (res.n_deliveries, res.n_msg_errors)
+            eng.release_batch(b)
+            torch.cuda.synchronize(dev)
+            t2 = time.perf_counter()
+            if it >= 2:
+                times.append((t1 - t0, t2 - t0))
+        rx = sum(t[0] for t in times) / len(times); tot = sum(t[1] for t in times) / len(times)
+        print(json.dumps({"metric": "C4 ingest of raw frames from host memory (single host thread)", "ingest": args.ingest,
+                          "msgs_per_s": M / tot, "egress_GBps": M * F / tot / 1e9, "host_receive_s_per_batch": rx,
+                          "batch_s": tot, "msgs_per_batch": M, "host_ns_per_frame": rx / M * 1e9,
+                          "h2d_bytes_per_step": M * slot, "d2h_bytes_per_step": 16 * M + M}), flush=True)
+        eng.close()
+        return
 
     prev = 0
     with torch.cuda.stream(stream):
