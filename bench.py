@@ -372,6 +372,33 @@ def main():
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = world * egress_step * e2e_steps / float(t_e2e.item()) / 1e9
+    # ---- for transparency: the same e2e step PLUS reading every framed byte back to host memory ------
+    # (what a host without GPUDirect egress would have to do; PCIe-bound — SURVEY 8f-2 'next' row)
+    drain = None
+    if world == 1 and not args.no_verify:
+        base, rb, mc = eng.ring_info()
+
+        class _Ring:
+            __cuda_array_interface__ = {"shape": (n_conns * rb,), "typestr": "|u1", "data": (base, False), "version": 3}
+
+        ring_flat = torch.as_tensor(_Ring(), device=dev)
+        host_buf = torch.empty(M * rec * n_conns // 8, dtype=torch.uint8).pin_memory()   # 1/8 of a step's bytes at a time
+        with torch.cuda.stream(stream):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            nd = 2
+            for _ in range(nd):
+                r = step_e2e()
+                # the batch occupies M*rec bytes at the same offset of every ring: copy ring by ring region
+                view = ring_flat.view(n_conns, rb)[:, :M * rec]
+                for part in range(8):
+                    c0 = part * (n_conns // 8)
+                    host_buf.view(n_conns // 8, M * rec).copy_(view[c0:c0 + n_conns // 8], non_blocking=True)
+                torch.cuda.synchronize(dev)
+            t1 = time.perf_counter()
+        drain = {"value": egress_step * nd / (t1 - t0) / 1e9, "unit": "GB/s", "d2h_bytes_per_step": M * rec * n_conns,
+                 "note": "every framed byte copied to pinned host memory over PCIe after each batch"}
+        del host_buf
     clocks = sampler.stop()  # sampled from the start of the timed region to the end of the e2e loop (all under load)
     h2d = M * slot + 64 + 22 * M + 64 if (world == 1 or rank == 0) else 0
     d2h = 64 + 16 * n_conns
@@ -410,6 +437,7 @@ def main():
                     "timing": "wall clock between device synchronisations, max over ranks",
                     "note": "framed bytes stay in the HBM rings for NIC hand-off (GPUDirect, SURVEY 8f-2); "
                             "the host reads back counters + span table"},
+            "e2e_full_readback": drain,
             "clocks": clocks,
             "gpu_launches": launches_per_step * args.steps,
         }

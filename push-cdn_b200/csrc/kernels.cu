@@ -215,59 +215,65 @@ __device__ __forceinline__ uint32_t key_word32(const uint8_t* kp, uint32_t j, ui
   return w;
 }
 
-// One warp per message.  Direct messages: hash the recipient key (one 64-bit word per lane,
-// shuffle-reduced), probe both 4-slot buckets with 8 lanes, verify the full key against the key
-// arena, resolve the route (handler.rs:204-236).  Also seeds the (conn, msg) sort arrays.
+// Eight lanes per message, four messages per warp (4x the memory-level parallelism of a warp per
+// message: the kernel is a chain of three dependent DRAM accesses — key, buckets, stored key).
+// Direct messages: hash the recipient key (64-bit words strided over the 8 lanes, xor-shuffle
+// reduced inside the group), probe both 4-slot buckets with the 8 lanes, verify the full key
+// against the key arena, resolve the route (handler.rs:204-236).  Also seeds the (conn, msg) sort.
 __global__ void __launch_bounds__(256) k_direct_lookup(DevState s, BatchIn b, Work w) {
-  const uint32_t m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t lane = lane_id();
-  if (m >= b.n_msgs) return;
-  const bool is_direct = b.kind[m] == 3;
+  const uint32_t lane = lane_id(), grp = lane >> 3, gl = lane & 7;
+  const uint32_t m = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4 + grp;
+  const bool valid = m < b.n_msgs;
+  const bool is_direct = valid && b.kind[m] == 3;
+  const uint32_t gshift = grp * 8;
   uint32_t target = kConnNone;
-  if (is_direct) {
-    const uint32_t klen = b.aux_len[m];
-    const uint8_t* kp = b.arena + b.aux_off[m];
-    const uint32_t nw = (klen + 7) >> 3;
-    uint64_t acc = 0;
-    for (uint32_t i = lane; i < nw; i += 32) {
-      uint64_t wd = (uint64_t)key_word32(kp, 2 * i, klen) | ((uint64_t)key_word32(kp, 2 * i + 1, klen) << 32);
-      acc += key_word_mix(wd, i, s.seed);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    const uint64_t h = key_hash_finish(acc, klen);
-    const uint32_t tag = key_tag(h), b1 = key_bucket(h, s.bucket_mask), b2 = alt_bucket(b1, tag, s.bucket_mask);
-    CuckooEntry e{0, 0, ROUTE_NONE, 0};
-    if (lane < 8) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(&s.cuckoo[(size_t)(lane < 4 ? b1 : b2) * 4 + (lane & 3)]);
-      e.tag = raw.x; e.key_slot = raw.y; e.route = raw.z; e.key_len = raw.w;
-    }
-    bool cand = lane < 8 && e.tag == tag && e.key_len == klen;
-    if (b1 == b2 && lane >= 4) cand = false;
-    uint32_t mask = __ballot_sync(0xffffffffu, cand);
-    uint32_t route = ROUTE_NONE;
-    const uint32_t nw32 = (klen + 3) >> 2;
-    while (mask) {
-      const int src = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const uint32_t kslot = __shfl_sync(0xffffffffu, e.key_slot, src);
-      const uint32_t rt = __shfl_sync(0xffffffffu, e.route, src);
-      const uint32_t* ak = reinterpret_cast<const uint32_t*>(s.keys + (size_t)kslot * s.key_stride);
-      bool eq = true;
-      for (uint32_t i = lane; i < nw32; i += 32) eq = eq && (ak[i] == key_word32(kp, i, klen));
-      if (__all_sync(0xffffffffu, eq)) { route = rt; break; }
-    }
-    if (route != ROUTE_NONE) {
-      if (route & ROUTE_REMOTE) {
-        // owner is another broker: forward unless the message came from a broker (to_user_only)
-        if (!(b.flags[m] & 1)) target = s.owner_conn[route & ~ROUTE_REMOTE];
-      } else {
-        target = route;
-      }
-    }
-    if (target != kConnNone && target >= s.N) target = kConnNone;
+  const uint32_t klen = is_direct ? b.aux_len[m] : 0;
+  const uint8_t* kp = b.arena + (is_direct ? b.aux_off[m] : 0);
+  // hash
+  const uint32_t nw = (klen + 7) >> 3;
+  uint64_t acc = 0;
+  for (uint32_t i = gl; i < nw; i += 8) {
+    uint64_t wd = (uint64_t)key_word32(kp, 2 * i, klen) | ((uint64_t)key_word32(kp, 2 * i + 1, klen) << 32);
+    acc += key_word_mix(wd, i, s.seed);
   }
-  if (lane == 0) {
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  const uint64_t h = key_hash_finish(acc, klen);
+  const uint32_t tag = key_tag(h), b1 = key_bucket(h, s.bucket_mask), b2 = alt_bucket(b1, tag, s.bucket_mask);
+  CuckooEntry e{0, 0, ROUTE_NONE, 0};
+  if (is_direct) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(&s.cuckoo[(size_t)(gl < 4 ? b1 : b2) * 4 + (gl & 3)]);
+    e.tag = raw.x; e.key_slot = raw.y; e.route = raw.z; e.key_len = raw.w;
+  }
+  bool cand = is_direct && e.tag == tag && e.key_len == klen;
+  if (b1 == b2 && gl >= 4) cand = false;
+  uint32_t gmask = (__ballot_sync(0xffffffffu, cand) >> gshift) & 0xFFu;  // this group's candidates
+  uint32_t route = ROUTE_NONE;
+  const uint32_t nw32 = (klen + 3) >> 2;
+  while (__any_sync(0xffffffffu, gmask != 0)) {  // groups advance through their own candidates in lockstep
+    const bool active = gmask != 0;
+    const int src = active ? (int)(gshift + __ffs(gmask) - 1) : (int)lane;
+    if (active) gmask &= gmask - 1;
+    const uint32_t kslot = __shfl_sync(0xffffffffu, e.key_slot, src);
+    const uint32_t rt = __shfl_sync(0xffffffffu, e.route, src);
+    bool eq = true;
+    if (active) {
+      const uint32_t* ak = reinterpret_cast<const uint32_t*>(s.keys + (size_t)kslot * s.key_stride);
+      for (uint32_t i = gl; i < nw32; i += 8) eq = eq && (ak[i] == key_word32(kp, i, klen));
+    }
+    const bool all_eq = ((__ballot_sync(0xffffffffu, eq) >> gshift) & 0xFFu) == 0xFFu;
+    if (active && all_eq) { route = rt; gmask = 0; }
+  }
+  if (route != ROUTE_NONE) {
+    if (route & ROUTE_REMOTE) {
+      // owner is another broker: forward unless the message came from a broker (to_user_only)
+      if (!(b.flags[m] & 1)) target = s.owner_conn[route & ~ROUTE_REMOTE];
+    } else {
+      target = route;
+    }
+  }
+  if (target != kConnNone && target >= s.N) target = kConnNone;
+  if (valid && gl == 0) {
     w.dconn[m] = target;
     if (is_direct) {
       w.D[m] = target != kConnNone ? 1u : 0u;
@@ -355,7 +361,7 @@ void launch_batch_begin(const DevState& s, const Work& w, const BatchIn&, bool h
 
 void launch_direct(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st) {
   const uint32_t n = b.n_msgs;
-  k_direct_lookup<<<(n * 32 + 255) / 256, 256, 0, st>>>(s, b, w);
+  k_direct_lookup<<<(n * 8 + 255) / 256, 256, 0, st>>>(s, b, w);
   uint32_t bits = 1;
   while ((1ull << bits) <= (uint64_t)s.N) bits++;  // keys are in [0, N]
   const uint32_t passes = (bits + 7) / 8;
@@ -428,6 +434,12 @@ void launch_match(const DevState& s, const Work& w, const BatchIn& b, cudaStream
 // =============================================================================== K1p plan
 __device__ __forceinline__ uint32_t frame_vec_bytes(uint32_t raw_len) { return (4u + raw_len + 15u) & ~15u; }
 __device__ __forceinline__ uint32_t frame_units(uint32_t raw_len) { return (4u + raw_len + kUnit - 1u) / kUnit; }
+// recipients per message-major tile: about 2 MB of stores per tile whatever the frame size, so a
+// batch of large frames still splits into enough tiles to balance ~450 persistent CTAs
+__device__ __forceinline__ uint32_t tile_recipients(uint32_t frame_bytes) {
+  const uint32_t chunk = min(frame_bytes, kChunkBytes);
+  return max(64u, min(kTileRecipients, (2u << 20) / chunk));
+}
 
 __global__ void __launch_bounds__(256) k_plan_a(DevState s, BatchIn b, Work w, uint32_t nblk) {
   __shared__ uint32_t sm[9];
@@ -443,7 +455,8 @@ __global__ void __launch_bounds__(256) k_plan_a(DevState s, BatchIn b, Work w, u
     } else {
       cls = CLS_FAT;
       const uint32_t nch = (frame_vec_bytes(len) + kChunkBytes - 1) / kChunkBytes;
-      tiles = nch * ((d + kTileRecipients - 1) / kTileRecipients);
+      const uint32_t tr = tile_recipients(frame_vec_bytes(len));
+      tiles = nch * ((d + tr - 1) / tr);
     }
   }
   uint32_t tot;
@@ -470,29 +483,24 @@ __global__ void __launch_bounds__(256) k_plan_a(DevState s, BatchIn b, Work w, u
     }
   }
 }
+// grid = 4: block q scans the block totals of one of the four planned quantities
 __global__ void __launch_bounds__(256) k_plan_b(Work w, uint32_t nblk) {
   __shared__ uint32_t sm[9];
-  uint32_t totals[4];
-  for (int q = 0; q < 4; q++) {
-    uint32_t* t = w.scan_tmp + (size_t)q * nblk;
-    uint32_t carry = 0;
-    for (uint32_t bb = 0; bb < nblk; bb += 256) {
-      const uint32_t i = bb + threadIdx.x;
-      const uint32_t v = i < nblk ? t[i] : 0;
-      uint32_t tot, ex = block256_excl_scan(v, &tot, sm);
-      if (i < nblk) t[i] = ex + carry;
-      carry += tot;
-    }
-    totals[q] = carry;
+  const uint32_t q = blockIdx.x;
+  uint32_t* t = w.scan_tmp + (size_t)q * nblk;
+  uint32_t carry = 0;
+  for (uint32_t bb = 0; bb < nblk; bb += 256) {
+    const uint32_t i = bb + threadIdx.x;
+    const uint32_t v = i < nblk ? t[i] : 0;
+    uint32_t tot, ex = block256_excl_scan(v, &tot, sm);
+    if (i < nblk) t[i] = ex + carry;
+    carry += tot;
   }
   if (threadIdx.x == 0) {
-    w.stats->n_fat_entries = totals[0];
-    w.stats->n_thin_entries = totals[1];
-    w.stats->n_fat_tiles = totals[2];
-    w.stats->tile_cursor = 0;
-    w.stats->n_cm = totals[3];
-    w.stats->cm_cursor = 0;
-    if (totals[0] > w.cap_fat || totals[1] > w.cap_thin) w.stats->status = 1;  // PCDN_E2BIG
+    if (q == 0) { w.stats->n_fat_entries = carry; if (carry > w.cap_fat) w.stats->status = 1; }   // PCDN_E2BIG
+    if (q == 1) { w.stats->n_thin_entries = carry; if (carry > w.cap_thin) w.stats->status = 1; }
+    if (q == 2) { w.stats->n_fat_tiles = carry; w.stats->tile_cursor = 0; }
+    if (q == 3) { w.stats->n_cm = carry; w.stats->cm_cursor = 0; }
   }
 }
 __global__ void __launch_bounds__(256) k_plan_c(BatchIn b, Work w, uint32_t nblk) {
@@ -515,7 +523,7 @@ void launch_plan(const DevState& s, const Work& w, const BatchIn& b, cudaStream_
   const uint32_t nblk = (b.n_msgs + 255) / 256;
   k_plan_a<<<nblk, 256, 0, st>>>(s, b, w, nblk);
   if (nblk == 1) return;  // finished inside k_plan_a
-  k_plan_b<<<1, 256, 0, st>>>(w, nblk);
+  k_plan_b<<<4, 256, 0, st>>>(w, nblk);
   k_plan_c<<<(b.n_msgs + 1 + 255) / 256, 256, 0, st>>>(b, w, nblk);
 }
 
@@ -672,12 +680,13 @@ __device__ __forceinline__ void pack_fat_phase(const DevState& s, const BatchIn&
         uint32_t lo = 0, hi = b.n_msgs;  // largest m with tbase[m] <= t
         while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (w.tbase[mid] <= t) lo = mid; else hi = mid; }
         const uint32_t m = lo, ltile = t - w.tbase[m], d = w.D[m];
-        const uint32_t ngrp = (d + kTileRecipients - 1) / kTileRecipients;
-        const uint32_t ch = ltile / ngrp, grp = ltile % ngrp;
         const uint32_t fb = frame_vec_bytes(b.raw_len[m]);
+        const uint32_t tr = tile_recipients(fb);
+        const uint32_t ngrp = (d + tr - 1) / tr;
+        const uint32_t ch = ltile / ngrp, grp = ltile % ngrp;
         const uint32_t nbytes = min(kChunkBytes, fb - ch * kChunkBytes);
-        t_info[1] = m; t_info[2] = ch; t_info[3] = grp * kTileRecipients;
-        t_info[4] = min(d, (grp + 1) * kTileRecipients); t_info[5] = nbytes;
+        t_info[1] = m; t_info[2] = ch; t_info[3] = grp * tr;
+        t_info[4] = min(d, (grp + 1) * tr); t_info[5] = nbytes;
         t_info[6] = (m != staged_m || ch != staged_k) ? 1u : 0u;
         staged_m = m; staged_k = ch;
       }
@@ -908,6 +917,8 @@ __device__ __forceinline__ void pack_thin_phase(const DevState& s, const BatchIn
   const uint32_t n = w.stats->n_thin_entries;
   const uint32_t lane = lane_id();
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  // (a variant with four entries in flight per warp measured no faster: the phase is bound by the
+  // scattered sub-KB writes, not by load latency — profiles/r1_cfg_C4*.json)
   for (uint32_t e = gw; e < n; e += nw) {
     const uint4 ent = w.ethin[e];
     if (ent.y == kOffInvalid) continue;
