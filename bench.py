@@ -390,7 +390,8 @@ def main():
             for _ in range(nd):
                 r = step_e2e()
                 # the batch occupies M*rec bytes at the same offset of every ring: copy ring by ring region
-                view = ring_flat.view(n_conns, rb)[:, :M * rec]
+                off = r.spans[0].ring_off
+                view = ring_flat.view(n_conns, rb)[:, off:off + M * rec]
                 for part in range(8):
                     c0 = part * (n_conns // 8)
                     host_buf.view(n_conns // 8, M * rec).copy_(view[c0:c0 + n_conns // 8], non_blocking=True)
