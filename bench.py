@@ -178,8 +178,10 @@ def main():
     import __graft_entry__ as ge
 
     pkg = ge.load_package()
-    if rank == 0 and pkg.needs_build():
-        pkg.build()
+    # build only when the library is missing (file times are meaningless on a copied snapshot, and a
+    # rebuild by rank 0 would race with the other ranks' dlopen)
+    if rank == 0 and not os.path.exists(pkg.LIB_PATH):
+        pkg.build(force=True)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
