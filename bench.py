@@ -241,22 +241,37 @@ def main():
                                d_slot.data_ptr(), d_len.data_ptr(), d_aoff.data_ptr(), d_alen.data_ptr(),
                                d_topics.data_ptr(), M, d_bidx.data_ptr())]
     state = {"prev": 0, "i": 0}
+    # N>1: the NCCL broadcast of step i+1's batch is issued on a side stream as soon as the pack that
+    # last read that ingest buffer has finished, so it overlaps the pack of step i instead of sitting
+    # in front of step i+1's match kernel (ingest pipelining; two ingest buffers).
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    ev_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_free = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(k):
+        with torch.cuda.stream(comm):
+            comm.wait_event(ev_free[k])          # (a never-recorded event does not block)
+            dist.broadcast(d_arenas[k], src=0)   # NCCL ingest over NVLink
+            ev_ready[k].record(comm)
 
     def step_device():
         k = state["i"] & 1
-        state["i"] += 1
         if world > 1:
-            dist.broadcast(d_arenas[k], src=0)  # NCCL ingest over NVLink, on `stream`
+            if state["i"] == 0:
+                prefetch(0)
+            stream.wait_event(ev_ready[k])
+        state["i"] += 1
         b = eng.submit_device(dbs[k])
-        if state["prev"]:
-            eng.release_batch(state["prev"])     # the consumer (NIC hand-off) frees the ring space
-        state["prev"] = b
+        eng.release_batch(b)                     # the consumer (NIC hand-off) frees the ring space
+        if world > 1:
+            ev_free[k].record(stream)            # this batch's pack is done with ingest buffer k
+            prefetch(k ^ 1)                      # next step's batch, overlapping this step's pack
         return b
 
     def drain_device():
-        if state["prev"]:
-            eng.release_batch(state["prev"])
-            state["prev"] = 0
+        if world > 1:
+            torch.cuda.current_stream().wait_stream(comm)
+        state["i"] = 0
 
     def sync_all():
         if world > 1:
