@@ -90,6 +90,11 @@ typedef struct pcdn_config {
   const char* identity;         /* this broker's BrokerIdentifier string "public/private"       */
   uint32_t pack_variant;        /* 0 = default; see DESIGN.md (kernel selection for profiling)  */
   uint32_t flags;               /* PCDN_FLAG_*                                                  */
+  uint64_t global_memory_pool_size; /* Limiter analogue (cdn-proto/src/connection/limiter/mod.rs:56-68,
+                                 * cdn-broker/src/binaries/broker.rs:71-72 default 1 GiB): bytes of inbound frames
+                                 * that may be in flight (accepted, their batch not yet released); 0 = unlimited.
+                                 * The reference awaits the semaphore; here a frame that does not fit is refused
+                                 * with PCDN_EAGAIN and the caller retries after releasing a batch. */
 } pcdn_config;
 
 /* pcdn_config.flags */
@@ -168,6 +173,9 @@ typedef struct pcdn_stats {
   double ms_pack;
   double ms_total;
   uint64_t timed_batches;
+  uint64_t inflight_bytes;      /* bytes currently holding pool permits                               */
+  uint64_t released_batches;
+  double latency_ms_sum;        /* launch → release wall time per batch (the reference's LATENCY histogram observes the permit lifetime, limiter/pool.rs:44-52) */
 } pcdn_stats;
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */
@@ -208,6 +216,25 @@ typedef struct pcdn_user_sync_entry {
 } pcdn_user_sync_entry;
 int pcdn_apply_user_sync(pcdn_engine* e, const char* remote_identity,
                          const pcdn_user_sync_entry* entries, uint32_t n);
+/* ---- inter-broker sync on the same tables ------------------------------------------
+ * The CRDT side of Connections: what cdn-broker/src/tasks/broker/sync.rs sends and what
+ * broker_receive_loop applies (handler.rs:164-188).  Serialisation of these maps on the wire (rkyv)
+ * stays with the host; the engine exchanges plain arrays.  Returned arrays are engine-owned and stay
+ * valid until the next pcdn_get_*_sync call on the same engine. */
+typedef struct pcdn_topic_sync_entry {
+  uint16_t topic;
+  uint8_t status;   /* 0 Subscribed, 1 Unsubscribed, 2 tombstone */
+  uint8_t reserved[5];
+  uint64_t version;
+} pcdn_topic_sync_entry;
+/* Connections::get_full_user_sync mod.rs:131 (full != 0) / get_partial_user_sync :141 (= direct_map.diff()) */
+int pcdn_get_user_sync(pcdn_engine* e, int full, const pcdn_user_sync_entry** out, uint32_t* n);
+/* Connections::apply_topic_sync mod.rs:165-191: merge a peer's TopicSyncMap (conflict identity
+ * `remote_identity`, TopicSyncMap::new(0) in the reference) and (un)subscribe that broker */
+int pcdn_apply_topic_sync(pcdn_engine* e, const char* identifier, uint32_t remote_identity,
+                          const pcdn_topic_sync_entry* entries, uint32_t n);
+/* Connections::get_full_topic_sync mod.rs:194 / get_partial_topic_sync :205-237 */
+int pcdn_get_topic_sync(pcdn_engine* e, int full, const pcdn_topic_sync_entry** out, uint32_t* n);
 /* Bulk form of add_user for table loads (keys are fixed-stride); same semantics, one lock.      */
 int pcdn_add_users_bulk(pcdn_engine* e, const uint8_t* keys, uint32_t key_len, uint32_t key_stride,
                         uint32_t n_users, const uint16_t* topics, const uint32_t* topic_offsets,

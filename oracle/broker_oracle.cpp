@@ -463,6 +463,17 @@ void orc_dmap_put(void* m, const uint8_t* k, uint32_t kl, uint64_t version, cons
 }
 void orc_apply_user_sync(void* h, void* m) { ((Oracle*)h)->apply_user_sync(*(DirectMap*)m); }
 
+// user sync between two oracles: get_full_user_sync mod.rs:131-137 / get_partial_user_sync :141-148
+// (None when empty) → apply_user_sync :154.  Returns 0 when there was nothing to send.
+int orc_user_sync(void* from, void* to, int full, int apply) {
+  Oracle* f = (Oracle*)from;
+  std::optional<DirectMap> m;
+  if (full) { if (!f->direct_map.underlying_map.empty()) m = f->direct_map; }
+  else { DirectMap d = f->direct_map.diff(); if (!d.is_empty()) m = d; }
+  if (!m) return 0;
+  if (apply) ((Oracle*)to)->apply_user_sync(*m);
+  return 1;
+}
 // topic sync between two oracles (cdn-broker/src/connections/mod.rs:410-526 tests)
 // mode 0 = partial, 1 = full.  Returns 0 if there was nothing to sync (None), 1 if applied.
 int orc_topic_sync(void* from, void* to, const char* from_id_in_to, int mode, int apply) {

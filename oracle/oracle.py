@@ -59,6 +59,7 @@ def lib() -> C.CDLL:
             "orc_dmap_put": (None, [vp, u8p, u32, u64, cp]),
             "orc_apply_user_sync": (None, [vp, vp]),
             "orc_topic_sync": (ci, [vp, vp, cp, ci, ci]),
+            "orc_user_sync": (ci, [vp, vp, ci, ci]),
             "orc_apply_topic_list": (None, [vp, cp, u16p, u32]),
             "orc_handle_broadcast_message": (None, [vp, u16p, u32, u8p, u32, ci]),
             "orc_handle_direct_message": (None, [vp, u8p, u32, u8p, u32, ci]),
@@ -205,6 +206,9 @@ class Oracle:
     def apply_topic_list(self, ident: str, topics: Iterable[int]) -> None:
         t, n = _t16(topics)
         self.L.orc_apply_topic_list(self.h, ident.encode(), t, n)
+
+    def user_sync_to(self, other: "Oracle", full: bool = False, apply: bool = True) -> bool:
+        return bool(self.L.orc_user_sync(self.h, other.h, 1 if full else 0, 1 if apply else 0))
 
     def topic_sync_to(self, other: "Oracle", my_id_in_other: str, full: bool = False, apply: bool = True) -> bool:
         return bool(self.L.orc_topic_sync(self.h, other.h, my_id_in_other.encode(), 1 if full else 0, 1 if apply else 0))

@@ -80,7 +80,7 @@ class Config(C.Structure):
         ("max_batch_msgs", C.c_uint32), ("max_batch_bcast", C.c_uint32), ("max_batch_bytes", C.c_uint64),
         ("max_batch_deliveries", C.c_uint64), ("batch_slots", C.c_uint32), ("n_valid_topics", C.c_uint32),
         ("hash_seed", C.c_uint64), ("stream", C.c_void_p), ("identity", C.c_char_p), ("pack_variant", C.c_uint32),
-        ("flags", C.c_uint32),
+        ("flags", C.c_uint32), ("global_memory_pool_size", C.c_uint64),
     ]
 
 
@@ -117,7 +117,8 @@ class Stats(C.Structure):
     _fields_ = [
         ("batches", C.c_uint64), ("msgs", C.c_uint64), ("deliveries", C.c_uint64), ("bytes_out", C.c_uint64),
         ("ms_match", C.c_double), ("ms_plan", C.c_double), ("ms_direct", C.c_double), ("ms_pack", C.c_double),
-        ("ms_total", C.c_double), ("timed_batches", C.c_uint64),
+        ("ms_total", C.c_double), ("timed_batches", C.c_uint64), ("inflight_bytes", C.c_uint64),
+        ("released_batches", C.c_uint64), ("latency_ms_sum", C.c_double),
     ]
 
 
@@ -126,8 +127,18 @@ class Frame(C.Structure):
                 ("raw_len", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class TopicSyncEntry(C.Structure):
+    _fields_ = [("topic", C.c_uint16), ("status", C.c_uint8), ("reserved", C.c_uint8 * 5), ("version", C.c_uint64)]
+
+
 class UserSyncEntry(C.Structure):
     _fields_ = [("key", C.c_char_p), ("key_len", C.c_uint32), ("version", C.c_uint64), ("owner", C.c_char_p)]
+
+
+class UserSyncEntryOut(C.Structure):
+    """same layout, for READING entries the engine returns: `key` may contain NUL bytes, so it must
+    stay a raw address (a c_char_p field would hand back a truncated temporary copy)"""
+    _fields_ = [("key", C.c_void_p), ("key_len", C.c_uint32), ("version", C.c_uint64), ("owner", C.c_char_p)]
 
 
 # every symbol include/pcdn_fanout.h declares: name → (restype, argtypes)
@@ -147,6 +158,9 @@ ABI = {
     "pcdn_subscribe_broker_to": (_ci, [_vp, _cp, _u16p, _u32]),
     "pcdn_unsubscribe_broker_from": (_ci, [_vp, _cp, _u16p, _u32]),
     "pcdn_apply_user_sync": (_ci, [_vp, _cp, C.POINTER(UserSyncEntry), _u32]),
+    "pcdn_get_user_sync": (_ci, [_vp, _ci, C.POINTER(C.POINTER(UserSyncEntry)), C.POINTER(_u32)]),
+    "pcdn_apply_topic_sync": (_ci, [_vp, _cp, _u32, C.POINTER(TopicSyncEntry), _u32]),
+    "pcdn_get_topic_sync": (_ci, [_vp, _ci, C.POINTER(C.POINTER(TopicSyncEntry)), C.POINTER(_u32)]),
     "pcdn_add_users_bulk": (_ci, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
     "pcdn_handle_broadcast_message": (_ci, [_vp, _u16p, _u32, _u8p, _u32, _ci]),
     "pcdn_handle_direct_message": (_ci, [_vp, _u8p, _u32, _u8p, _u32, _ci]),
@@ -297,6 +311,28 @@ class Engine:
             keep.append((key, ob))
             arr[i] = UserSyncEntry(key, len(key), version, ob)
         self._chk(self.L.pcdn_apply_user_sync(self.h, remote_identity.encode(), arr, len(ents)))
+
+    # ---- inter-broker sync (Connections::get_*_sync / apply_topic_sync) ----------------------
+    def get_user_sync(self, full: bool = False):
+        """→ [(key, version, owner or None)] — full map or the diff since the last call"""
+        p, n = C.POINTER(UserSyncEntry)(), C.c_uint32()
+        self._chk(self.L.pcdn_get_user_sync(self.h, int(full), C.byref(p), C.byref(n)))
+        q = C.cast(p, C.POINTER(UserSyncEntryOut))
+        return [(C.string_at(q[i].key, q[i].key_len) if q[i].key_len else b"", q[i].version,
+                 q[i].owner.decode() if q[i].owner is not None else None) for i in range(n.value)]
+
+    def apply_topic_sync(self, ident: str, entries, remote_identity: int = 0) -> None:
+        """entries: [(topic, status 0|1|2, version)] — a peer's TopicSyncMap (or its diff)"""
+        ents = list(entries)
+        arr = (TopicSyncEntry * max(1, len(ents)))()
+        for i, (t, st, ver) in enumerate(ents):
+            arr[i].topic, arr[i].status, arr[i].version = t, st, ver
+        self._chk(self.L.pcdn_apply_topic_sync(self.h, ident.encode(), remote_identity, arr, len(ents)))
+
+    def get_topic_sync(self, full: bool = False):
+        p, n = C.POINTER(TopicSyncEntry)(), C.c_uint32()
+        self._chk(self.L.pcdn_get_topic_sync(self.h, int(full), C.byref(p), C.byref(n)))
+        return [(p[i].topic, p[i].status, p[i].version) for i in range(n.value)]
 
     # ---- data in ----------------------------------------------------------------------------
     def handle_broadcast_message(self, topics: Iterable[int], raw: bytes, to_users_only: bool = False) -> None:

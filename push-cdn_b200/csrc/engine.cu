@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -67,6 +68,8 @@ struct Slot {
   std::vector<uint32_t> slot_off16, raw_len, aux_off, aux_len, bcast_index;
   std::vector<uint16_t> topics;
   uint32_t n_direct = 0;
+  uint64_t ingress_bytes = 0;   // pool permits held by this batch
+  std::chrono::steady_clock::time_point t_launch;
   bool devparse = false;        // some messages carry MSGF_DEVPARSE (k_parse runs first)
   int8_t* h_msg_status = nullptr;  // pinned
   uint32_t n_msg_errors = 0;
@@ -115,8 +118,14 @@ struct pcdn_engine {
   uint32_t* j_kslot = nullptr; uint8_t* j_kbytes = nullptr; size_t j_key_cap = 0;
   std::vector<Upd32> h_u32; std::vector<UpdSlot> h_slot; std::vector<uint32_t> h_kslot; std::vector<uint8_t> h_kbytes;
   bool timing = false;
+  uint64_t inflight_bytes = 0;  // Limiter analogue: accepted frame bytes whose batch is not released yet
   pcdn_stats stats{};
   std::vector<void*> dev_allocs, pin_allocs;
+  // buffers behind pcdn_get_*_sync
+  std::vector<UserSyncEntry> sync_users;
+  std::vector<pcdn_user_sync_entry> sync_users_c;
+  std::vector<TopicSyncEntry> sync_topics;
+  std::vector<pcdn_topic_sync_entry> sync_topics_c;
 };
 
 namespace {
@@ -189,7 +198,7 @@ int flush_journal(pcdn_engine* e) {
 }
 
 void slot_reset_open(Slot& s) {
-  s.arena_used = 0; s.n_direct = 0; s.devparse = false; s.n_msg_errors = 0;
+  s.arena_used = 0; s.n_direct = 0; s.devparse = false; s.n_msg_errors = 0; s.ingress_bytes = 0;
   s.kind.clear(); s.flags.clear(); s.slot_off16.clear(); s.raw_len.clear(); s.aux_off.clear(); s.aux_len.clear();
   s.bcast_index.clear(); s.topics.clear();
   s.polled = false; s.device_input = false; s.timed = false;
@@ -239,6 +248,7 @@ int launch_pipeline(pcdn_engine* e, Slot& s, uint32_t n_direct) {
   CUDA_TRY(cudaMemcpyAsync(s.h_stats, s.w.stats, sizeof(BatchStats), cudaMemcpyDeviceToHost, ps));
   CUDA_TRY(cudaEventRecord(s.ev_done, ps));
   s.state = SLOT_INFLIGHT;
+  s.t_launch = std::chrono::steady_clock::now();
   s.batch_id = e->next_batch_id++;
   s.polled = false;
   e->inflight.push_back(s.batch_id);
@@ -306,6 +316,12 @@ int append_msg(pcdn_engine* e, uint8_t kind, uint8_t flags, const uint16_t* topi
   if (raw_len > 0x1FFFFFFFu) return fail(PCDN_EINVAL, "message larger than MAX_MESSAGE_SIZE (cdn-proto/src/lib.rs:25)");
   if (kind != PCDN_KIND_BROADCAST && kind != PCDN_KIND_DIRECT) return fail(PCDN_EINVAL, "kind must be broadcast or direct");
   const pcdn_config& c = e->cfg;
+  if (c.global_memory_pool_size) {
+    // limiter/mod.rs:56-68: the frame's length in permits must be available before it is accepted
+    if (raw_len > c.global_memory_pool_size) return fail(PCDN_EINVAL, "message larger than the global memory pool");
+    if (e->inflight_bytes + raw_len > c.global_memory_pool_size)
+      return fail(PCDN_EAGAIN, "global memory pool exhausted: release a batch first");
+  }
   const size_t slot_bytes = align_up(4 + (size_t)raw_len, 16);
   size_t need = slot_bytes + (kind == PCDN_KIND_DIRECT ? align_up(recipient_len, 16) : 0);
   if (need + 64 > c.max_batch_bytes) return fail(PCDN_ENOSPC, "message does not fit max_batch_bytes");
@@ -337,6 +353,8 @@ int append_msg(pcdn_engine* e, uint8_t kind, uint8_t flags, const uint16_t* topi
   s.flags.push_back(flags);
   s.slot_off16.push_back((uint32_t)(off / 16));
   s.raw_len.push_back(raw_len);
+  s.ingress_bytes += raw_len;
+  e->inflight_bytes += raw_len;
   if (kind == PCDN_KIND_BROADCAST) {
     s.aux_off.push_back((uint32_t)s.topics.size());
     s.aux_len.push_back(n_topics);
@@ -690,6 +708,50 @@ int pcdn_apply_user_sync(pcdn_engine* e, const char* remote_identity, const pcdn
   GUARD_END
 }
 
+int pcdn_get_user_sync(pcdn_engine* e, int full, const pcdn_user_sync_entry** out, uint32_t* n) {
+  GUARD_BEGIN
+  LOCK;
+  if (full) e->conns->get_full_user_sync(e->sync_users);
+  else e->conns->get_partial_user_sync(e->sync_users);
+  e->sync_users_c.clear();
+  for (const UserSyncEntry& u : e->sync_users)
+    e->sync_users_c.push_back(pcdn_user_sync_entry{(const uint8_t*)u.key.data(), (uint32_t)u.key.size(), u.version,
+                                                   u.has_owner ? u.owner.c_str() : nullptr});
+  *out = e->sync_users_c.data();
+  *n = (uint32_t)e->sync_users_c.size();
+  return 0;
+  GUARD_END
+}
+int pcdn_apply_topic_sync(pcdn_engine* e, const char* identifier, uint32_t remote_identity,
+                          const pcdn_topic_sync_entry* entries, uint32_t n) {
+  GUARD_BEGIN
+  LOCK;
+  int rc = before_state_change(e);
+  if (rc) return rc;
+  std::vector<TopicSyncEntry> v;
+  v.reserve(n);
+  for (uint32_t i = 0; i < n; i++) v.push_back(TopicSyncEntry{entries[i].topic, entries[i].status, entries[i].version});
+  rc = e->conns->apply_topic_sync(identifier, remote_identity, v);
+  return rc ? fail(rc, "topic id out of range") : 0;
+  GUARD_END
+}
+int pcdn_get_topic_sync(pcdn_engine* e, int full, const pcdn_topic_sync_entry** out, uint32_t* n) {
+  GUARD_BEGIN
+  LOCK;
+  if (full) e->conns->get_full_topic_sync(e->sync_topics);
+  else e->conns->get_partial_topic_sync(e->sync_topics);
+  e->sync_topics_c.clear();
+  for (const TopicSyncEntry& t : e->sync_topics) {
+    pcdn_topic_sync_entry c{};
+    c.topic = t.topic; c.status = t.status; c.version = t.version;
+    e->sync_topics_c.push_back(c);
+  }
+  *out = e->sync_topics_c.data();
+  *n = (uint32_t)e->sync_topics_c.size();
+  return 0;
+  GUARD_END
+}
+
 // ---- data in ----------------------------------------------------------------------------------
 int pcdn_handle_broadcast_message(pcdn_engine* e, const uint16_t* topics, uint32_t n_topics, const uint8_t* raw,
                                   uint32_t raw_len, int to_users_only) {
@@ -946,6 +1008,11 @@ int pcdn_release_batch(pcdn_engine* e, uint64_t batch_id) {
   CUDA_TRY(cudaGetLastError());
   e->inflight.erase(e->inflight.begin());
   s->state = SLOT_FREE;
+  // the last 'clone' of every frame of this batch is gone: permits back to the pool (pool.rs:44-52)
+  e->inflight_bytes -= std::min(e->inflight_bytes, s->ingress_bytes);
+  s->ingress_bytes = 0;
+  e->stats.released_batches++;
+  e->stats.latency_ms_sum += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s->t_launch).count();
   return 0;
   GUARD_END
 }
@@ -953,6 +1020,7 @@ int pcdn_release_batch(pcdn_engine* e, uint64_t batch_id) {
 // ---- introspection ----------------------------------------------------------------------------
 int pcdn_get_stats(pcdn_engine* e, pcdn_stats* out) {
   LOCK;
+  e->stats.inflight_bytes = e->inflight_bytes;
   *out = e->stats;
   return 0;
 }

@@ -151,6 +151,7 @@ Connections::Connections(HostTables& t, const char* identity)
   owners_.push_back(identity_);
   owner_ids_[identity_.str()] = 0;
   conn_kind_.assign(t_.g.max_conns, CONN_FREE);
+  topic_key_count_.assign(t_.g.T, 0);
 }
 
 int Connections::alloc_conn(int kind, uint32_t* conn) {
@@ -231,7 +232,10 @@ int Connections::remove_user(const std::string& key) {
     free_conn(conn);
     users_.erase(u);
   }
-  if (kt != user_topics_.end()) user_topics_.erase(kt);  // broadcast_map.users.remove_key
+  if (kt != user_topics_.end()) {  // broadcast_map.users.remove_key
+    for (uint16_t t : kt->second) topic_key_count_[t]--;
+    user_topics_.erase(kt);
+  }
   // direct_map.remove_if_equals(key, identity) versioned_map.rs:128-136
   auto d = direct_map_.find(key);
   if (d != direct_map_.end() && d->second.has && d->second.owner == 0) dm_modify_local(key, false, 0);
@@ -252,6 +256,7 @@ int Connections::add_user(const std::string& key, const uint16_t* topics, uint32
   for (uint32_t i = 0; i < n; i++) {
     bool added;
     set_insert(set, topics[i], &added);
+    if (added) topic_key_count_[topics[i]]++;
     t_.set_bit(topics[i], c, true);
   }
   if ((rc = update_route(key))) {
@@ -272,6 +277,7 @@ int Connections::subscribe_user_to(const std::string& key, const uint16_t* topic
   for (uint32_t i = 0; i < n; i++) {
     bool added;
     set_insert(set, topics[i], &added);
+    if (added) topic_key_count_[topics[i]]++;
     if (u != users_.end()) t_.set_bit(topics[i], u->second, true);
   }
   return 0;
@@ -287,6 +293,7 @@ int Connections::unsubscribe_user_from(const std::string& key, const uint16_t* t
     auto it = std::lower_bound(v.begin(), v.end(), topics[i]);
     if (it != v.end() && *it == topics[i]) {
       v.erase(it);
+      topic_key_count_[topics[i]]--;
       if (u != users_.end() && topics[i] < t_.g.T) t_.set_bit(topics[i], u->second, false);
     }
   }
@@ -323,7 +330,7 @@ int Connections::add_broker(const char* ident, uint32_t* conn) {
   remove_broker(ident);
   uint32_t c;
   if ((rc = alloc_conn(CONN_BROKER, &c))) return rc;
-  brokers_[id] = BrokerRec{c, owner};
+  brokers_[id] = BrokerRec{c, owner, TopicVersionedMap()};  // topic_sync_map: TopicSyncMap::new(0) mod.rs:271
   t_.set_broker(c, true);
   t_.set_owner_conn(owner, c);
   if (conn) *conn = c;
@@ -396,6 +403,102 @@ int Connections::apply_user_sync(const char* remote_identity, const std::vector<
     if (r && !rc) rc = r;
   }
   return rc;
+}
+
+// ---- TopicVersionedMap = VersionedMap<Topic, SubscriptionStatus, u32> ---------------------------
+void TopicVersionedMap::insert(uint16_t t, uint8_t status) {
+  auto it = map.find(t);
+  if (it != map.end()) {
+    if (!locally_modified.count(t)) it->second.version += 1;
+    it->second.status = status;
+  } else {
+    map.emplace(t, VV{1, status});
+  }
+  locally_modified.insert(t);
+}
+void TopicVersionedMap::diff(std::vector<TopicSyncEntry>& out) {
+  out.clear();
+  std::unordered_set<uint16_t> mod;
+  mod.swap(locally_modified);
+  for (uint16_t t : mod) {
+    auto it = map.find(t);
+    if (it == map.end()) continue;
+    out.push_back(TopicSyncEntry{t, it->second.status, it->second.version});
+    if (it->second.status == 2) map.erase(it);
+  }
+}
+void TopicVersionedMap::full(std::vector<TopicSyncEntry>& out) const {
+  out.clear();
+  for (auto& kv : map) out.push_back(TopicSyncEntry{kv.first, kv.second.status, kv.second.version});
+}
+void TopicVersionedMap::merge(uint32_t remote_identity, const std::vector<TopicSyncEntry>& remote,
+                              std::vector<std::pair<uint16_t, uint8_t>>& changes) {
+  changes.clear();
+  for (const TopicSyncEntry& r : remote) {
+    auto it = map.find(r.topic);
+    if (it != map.end()) {
+      const bool take = r.version > it->second.version ||
+                        (r.version == it->second.version && remote_identity > conflict_identity);
+      if (!take) continue;
+      if (r.status != 2) { it->second.status = r.status; it->second.version = r.version; }
+      else map.erase(it);
+      locally_modified.erase(r.topic);
+      changes.emplace_back(r.topic, r.status);
+    } else if (r.status != 2) {
+      map.emplace(r.topic, VV{r.version, r.status});
+      changes.emplace_back(r.topic, r.status);
+    }
+  }
+}
+
+// Connections::get_full_user_sync mod.rs:131-137 (None when empty = empty list)
+void Connections::get_full_user_sync(std::vector<UserSyncEntry>& out) const {
+  out.clear();
+  for (auto& kv : direct_map_)
+    out.push_back(UserSyncEntry{kv.first, kv.second.version, kv.second.has, kv.second.has ? owners_[kv.second.owner].str() : ""});
+}
+// Connections::get_partial_user_sync mod.rs:141-148 = VersionedMap::diff versioned_map.rs:169-195
+void Connections::get_partial_user_sync(std::vector<UserSyncEntry>& out) {
+  out.clear();
+  std::unordered_set<std::string> mod;
+  mod.swap(locally_modified_);
+  for (const std::string& k : mod) {
+    auto it = direct_map_.find(k);
+    if (it == direct_map_.end()) continue;
+    out.push_back(UserSyncEntry{k, it->second.version, it->second.has, it->second.has ? owners_[it->second.owner].str() : ""});
+    if (!it->second.has) direct_map_.erase(it);  // tombstones are dropped once they have been sent
+  }
+}
+// Connections::apply_topic_sync mod.rs:165-191
+int Connections::apply_topic_sync(const char* ident, uint32_t remote_identity, const std::vector<TopicSyncEntry>& e) {
+  std::string id = BrokerIdent::parse(ident).str();
+  auto b = brokers_.find(id);
+  if (b == brokers_.end()) { remove_broker(ident); return 0; }
+  for (const TopicSyncEntry& x : e)
+    if (x.topic >= t_.g.T) return PCDN_EINVAL;
+  std::vector<std::pair<uint16_t, uint8_t>> changed;
+  b->second.topic_sync_map.merge(remote_identity, e, changed);
+  for (auto& c : changed) {
+    if (c.second == 0) subscribe_broker_to(ident, &c.first, 1);
+    else unsubscribe_broker_from(ident, &c.first, 1);
+  }
+  return 0;
+}
+// Connections::get_full_topic_sync mod.rs:194-200
+void Connections::get_full_topic_sync(std::vector<TopicSyncEntry>& out) const { topic_sync_map_.full(out); }
+// Connections::get_partial_topic_sync mod.rs:205-237
+void Connections::get_partial_topic_sync(std::vector<TopicSyncEntry>& out) {
+  out.clear();
+  std::vector<uint16_t> added, removed;
+  for (uint32_t t = 0; t < t_.g.T; t++) {
+    const bool now = topic_key_count_[t] != 0, before = previous_subscribed_topics_.count((uint16_t)t) != 0;
+    if (now && !before) added.push_back((uint16_t)t);
+    if (!now && before) removed.push_back((uint16_t)t);
+  }
+  if (added.empty() && removed.empty()) return;
+  for (uint16_t t : added) { previous_subscribed_topics_.insert(t); topic_sync_map_.insert(t, 0); }
+  for (uint16_t t : removed) { previous_subscribed_topics_.erase(t); topic_sync_map_.insert(t, 1); }
+  topic_sync_map_.diff(out);
 }
 
 // Connections::get_interested_by_topic mod.rs:94-124 on the bitmap mirror

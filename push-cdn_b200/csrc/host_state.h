@@ -84,6 +84,27 @@ struct UserSyncEntry {
   std::string owner;
 };
 
+// one entry of a TopicSyncMap = VersionedMap<Topic, SubscriptionStatus, u32> (broadcast/mod.rs:19-25)
+struct TopicSyncEntry {
+  uint16_t topic;
+  uint8_t status;    // 0 Subscribed, 1 Unsubscribed, 2 tombstone (value None)
+  uint64_t version;
+};
+
+// VersionedMap<Topic, SubscriptionStatus, u32> (versioned_map.rs:39-270), small and dense
+struct TopicVersionedMap {
+  struct VV { uint64_t version; uint8_t status; };  // status 2 = None
+  std::unordered_map<uint16_t, VV> map;
+  std::unordered_set<uint16_t> locally_modified;
+  uint32_t conflict_identity = 0;
+  void insert(uint16_t t, uint8_t status);                                  // modify_local :84-113
+  void diff(std::vector<TopicSyncEntry>& out);                              // :169-195
+  void full(std::vector<TopicSyncEntry>& out) const;
+  // merge :202-269 → changed (topic, new status or 2)
+  void merge(uint32_t remote_identity, const std::vector<TopicSyncEntry>& remote,
+             std::vector<std::pair<uint16_t, uint8_t>>& changes);
+};
+
 class Connections {
  public:
   Connections(HostTables& t, const char* identity);
@@ -98,6 +119,12 @@ class Connections {
   int subscribe_broker_to(const char* ident, const uint16_t* topics, uint32_t n);            // :354
   int unsubscribe_broker_from(const char* ident, const uint16_t* topics, uint32_t n);        // :372
   int apply_user_sync(const char* remote_identity, const std::vector<UserSyncEntry>& e);     // :154
+  // -- inter-broker sync: what the sync task sends / receives -----------------------
+  void get_full_user_sync(std::vector<UserSyncEntry>& out) const;                             // :131
+  void get_partial_user_sync(std::vector<UserSyncEntry>& out);                                // :141 (direct_map.diff())
+  int apply_topic_sync(const char* ident, uint32_t remote_identity, const std::vector<TopicSyncEntry>& e);  // :165
+  void get_full_topic_sync(std::vector<TopicSyncEntry>& out) const;                           // :194
+  void get_partial_topic_sync(std::vector<TopicSyncEntry>& out);                              // :205
 
   // -- lookups on the mirror (tests / debug; the data path does these on the GPU) --------------
   void interested(const uint16_t* topics, uint32_t n, bool to_users_only,
@@ -111,7 +138,7 @@ class Connections {
 
  private:
   struct VV { uint64_t version; bool has; uint32_t owner; };  // VersionedValue<BrokerIdentifier>
-  struct BrokerRec { uint32_t conn; uint32_t owner; };
+  struct BrokerRec { uint32_t conn; uint32_t owner; TopicVersionedMap topic_sync_map; };  // Broker mod.rs:34-38
   HostTables& t_;
   BrokerIdent identity_;
   std::unordered_map<std::string, uint32_t> users_;                         // users :45
@@ -122,6 +149,9 @@ class Connections {
   std::unordered_map<std::string, std::vector<uint16_t>> broker_topics_;    // broadcast_map.brokers key_to_values
   std::unordered_map<std::string, uint32_t> owner_ids_;                     // identifier → owner index (0 = self)
   std::vector<BrokerIdent> owners_;
+  std::vector<uint32_t> topic_key_count_;   // |value_to_keys[t]| of broadcast_map.users (keys, connected or not)
+  TopicVersionedMap topic_sync_map_;        // broadcast_map.topic_sync_map
+  std::unordered_set<uint16_t> previous_subscribed_topics_;
   std::vector<uint8_t> conn_kind_;
   std::vector<uint32_t> free_conns_;
   uint32_t next_conn_ = 0;

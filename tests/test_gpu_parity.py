@@ -278,3 +278,26 @@ def test_batch_capacity_rejected_not_truncated(pcdn):
         w.both("unsubscribe_user_from", (i + 100).to_bytes(8, "little"), [0])
     w.bcast([0], raw)
     assert w.check() == 499
+
+
+def test_global_memory_pool_backpressure(pcdn):
+    """Limiter analogue (cdn-proto/src/connection/limiter/mod.rs:56-68): inbound bytes are admitted
+    against a global budget and given back when their batch is released"""
+    w = World(pcdn, global_memory_pool_size=10_000, max_conns=64)
+    a = w.add_user(b"a" * 8, [0])
+    raw = orc.broadcast_frame([0], b"x" * 3000)       # L = 3056
+    for _ in range(3):
+        w.e.handle_broadcast_message([0], raw)
+    with pytest.raises(pcdn.PcdnError) as ei:
+        w.e.handle_broadcast_message([0], raw)         # 4 x 3056 > 10 000
+    assert ei.value.code == -11                        # PCDN_EAGAIN: the reference would await the semaphore
+    assert w.e.stats().inflight_bytes == 3 * len(raw)
+    got = w.e.drain()                                  # poll + release → permits returned
+    assert got[a] == [raw] * 3
+    st = w.e.stats()
+    assert st.inflight_bytes == 0 and st.released_batches == 1 and st.latency_ms_sum > 0
+    w.e.handle_broadcast_message([0], raw)             # admitted again
+    assert w.e.drain()[a] == [raw]
+    with pytest.raises(pcdn.PcdnError) as ei:
+        w.e.handle_broadcast_message([0], orc.broadcast_frame([0], b"y" * 20000))
+    assert ei.value.code == -1                         # can never fit
