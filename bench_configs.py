@@ -86,7 +86,7 @@ def zipf_p(n, s=0.99):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", required=True, choices=["C3", "C4", "C5dense", "C5sparse"])
+    ap.add_argument("--workload", required=True, choices=["C3", "C4", "C5dense", "C5sparse", "latency"])
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--variant", type=int, default=0)
@@ -104,6 +104,41 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     wl = args.workload
     t_setup = time.time()
+
+    if wl == "latency":
+        # one message at a time through the host-buffer API: submit → poll (counters + span table back)
+        out = {"metric": "single-message fan-out latency, host buffers in, pcdn_submit → pcdn_poll complete (wall clock)", "unit": "us", "cases": []}
+        for n in (128, 1 << 14, 1 << 20):
+            rng = np.random.default_rng(9)
+            keys = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+            keys[:, :8] = np.arange(n, dtype=np.uint64).view(np.uint8).reshape(n, 8)
+            raw = B.broadcast_frame(0, bytes(1024))
+            rec = (4 + len(raw) + 31) // 32 * 32
+            eng = pkg.Engine(device=0, stream=stream.cuda_stream, max_conns=n, max_topics=16, max_keys=n, max_key_len=32,
+                             ring_bytes_per_conn=16 * rec, max_batch_msgs=64, max_batch_bcast=16, max_batch_bytes=1 << 20,
+                             max_batch_deliveries=n + 1024, batch_slots=2, pack_variant=args.variant)
+            eng.add_users_bulk(keys, 32, np.zeros(n, dtype=np.uint16), np.arange(n + 1, dtype=np.uint32))
+            rcpt = keys[n // 2].tobytes()
+            tmpl, roff, poff = direct_frame_template(32, 512)
+            draw = bytearray(tmpl); draw[roff:roff + 32] = rcpt; draw = bytes(draw)
+            for name, msgs in (("broadcast 1 KiB to all %d subscribers" % n, [("b", [0], raw, False)]),
+                               ("direct 512 B to one of %d users" % n, [("d", rcpt, draw, False)])):
+                ts = []
+                for it in range(220):
+                    t0 = time.perf_counter()
+                    b = eng.submit(msgs)
+                    r = eng.poll(b)
+                    t1 = time.perf_counter()
+                    eng.release_batch(b)
+                    if it >= 20:
+                        ts.append((t1 - t0) * 1e6)
+                assert r.n_deliveries == (n if msgs[0][0] == "b" else 1)
+                ts.sort()
+                out["cases"].append({"case": name, "p50_us": ts[len(ts) // 2], "p99_us": ts[int(len(ts) * 0.99)], "min_us": ts[0],
+                                     "deliveries": int(r.n_deliveries)})
+            eng.close()
+        print(json.dumps(out), flush=True)
+        return
 
     if wl == "C4":
         n, klen, K = 1 << 20, 128, 512

@@ -224,6 +224,7 @@ int launch_pipeline(pcdn_engine* e, Slot& s, uint32_t n_direct) {
   cudaStream_t st = e->stream, ps = (e->cfg.pack_variant & 8) ? e->pack_stream : e->stream, cs = e->copy_stream;
   const bool has_direct = n_direct > 0;
   s.timed = e->timing;
+  if (++s.w.stamp == 0) s.w.stamp = 1;  // validity stamp of this batch's direct buckets
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[0], st));
   launch_batch_begin(e->dev, s.w, s.in, has_direct, st);
   if (s.devparse) launch_parse(e->dev, s.w, s.in, st);
@@ -508,6 +509,9 @@ int init_device(pcdn_engine* e) {
     DEV_ALLOC(w.hist_tmp, 256 * ntiles / 1024 + 2);
     DEV_ALLOC(w.dstart, (size_t)g.N + 1);
     DEV_ALLOC(w.dend, (size_t)g.N + 1);
+    DEV_ALLOC(w.dstamp, (size_t)g.N + 1);
+    CUDA_TRY(cudaMemsetAsync(w.dstamp, 0, ((size_t)g.N + 1) * 4, e->stream));
+    w.stamp = 0;
     DEV_ALLOC(w.batch_units, g.N);
     DEV_ALLOC(w.spans, (size_t)2 * g.N);
     DEV_ALLOC(w.overflow, g.N);

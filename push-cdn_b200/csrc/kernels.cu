@@ -341,27 +341,54 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict
   }
 }
 
-// sorted keys → [dstart, dend) per connection (arrays pre-zeroed)
+// sorted keys → [dstart, dend) per connection.  The bounds of a connection are valid for this batch
+// iff dstamp[conn] == stamp (a per-slot batch counter): nothing has to be cleared between batches.
 __global__ void k_bucket_bounds(const uint32_t* __restrict__ skey, uint32_t n, uint32_t* __restrict__ dstart,
-                                uint32_t* __restrict__ dend) {
+                                uint32_t* __restrict__ dend, uint32_t* __restrict__ dstamp, uint32_t stamp) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t k = skey[i];
-  if (i == 0 || skey[i - 1] != k) dstart[k] = i;
+  if (i == 0 || skey[i - 1] != k) { dstart[k] = i; dstamp[k] = stamp; }
   if (i + 1 == n || skey[i + 1] != k) dend[k] = i + 1;
 }
 
-void launch_batch_begin(const DevState& s, const Work& w, const BatchIn&, bool has_direct, cudaStream_t st) {
-  cudaMemsetAsync(w.stats, 0, sizeof(BatchStats), st);
-  if (has_direct) {
-    cudaMemsetAsync(w.dstart, 0, (size_t)(s.N + 1) * 4, st);
-    cudaMemsetAsync(w.dend, 0, (size_t)(s.N + 1) * 4, st);
+// Small batches (<= 2048 messages): one block sorts the 64-bit composites (conn << 32 | msg) with a
+// bitonic network in shared memory — one launch instead of the ~15 of the multi-pass radix sort,
+// which is what a latency-sensitive batch of a few votes needs.  The composite key makes the
+// result (conn, msg)-ordered by construction.
+constexpr uint32_t kSmallSort = 2048;
+__global__ void __launch_bounds__(256) k_sort_small(uint32_t* __restrict__ skey, uint32_t* __restrict__ sval, uint32_t n) {
+  __shared__ unsigned long long a[kSmallSort];
+  for (uint32_t i = threadIdx.x; i < kSmallSort; i += 256)
+    a[i] = i < n ? (((unsigned long long)skey[i] << 32) | sval[i]) : ~0ull;
+  __syncthreads();
+  for (uint32_t k = 2; k <= kSmallSort; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t t = threadIdx.x; t < kSmallSort / 2; t += 256) {
+        const uint32_t i = 2 * t - (t & (j - 1));  // index of the lower element of pair t
+        const uint32_t l = i + j;
+        const bool up = (i & k) == 0;
+        const unsigned long long x = a[i], y = a[l];
+        if ((x > y) == up) { a[i] = y; a[l] = x; }
+      }
+      __syncthreads();
+    }
   }
+  for (uint32_t i = threadIdx.x; i < n; i += 256) { skey[i] = (uint32_t)(a[i] >> 32); sval[i] = (uint32_t)a[i]; }
+}
+
+void launch_batch_begin(const DevState&, const Work& w, const BatchIn&, bool, cudaStream_t st) {
+  cudaMemsetAsync(w.stats, 0, sizeof(BatchStats), st);
 }
 
 void launch_direct(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st) {
   const uint32_t n = b.n_msgs;
   k_direct_lookup<<<(n * 8 + 255) / 256, 256, 0, st>>>(s, b, w);
+  if (n <= kSmallSort) {
+    k_sort_small<<<1, 256, 0, st>>>(w.skey[0], w.sval[0], n);
+    k_bucket_bounds<<<(n + 255) / 256, 256, 0, st>>>(w.skey[0], n, w.dstart, w.dend, w.dstamp, w.stamp);
+    return;
+  }
   uint32_t bits = 1;
   while ((1ull << bits) <= (uint64_t)s.N) bits++;  // keys are in [0, N]
   const uint32_t passes = (bits + 7) / 8;
@@ -378,7 +405,7 @@ void launch_direct(const DevState& s, const Work& w, const BatchIn& b, cudaStrea
     cudaMemcpyAsync(w.skey[0], w.skey[1], (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(w.sval[0], w.sval[1], (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
   }
-  k_bucket_bounds<<<(n + 255) / 256, 256, 0, st>>>(w.skey[0], n, w.dstart, w.dend);
+  k_bucket_bounds<<<(n + 255) / 256, 256, 0, st>>>(w.skey[0], n, w.dstart, w.dend, w.dstamp, w.stamp);
 }
 
 // =============================================================================== K1a topic match
@@ -566,7 +593,7 @@ __global__ void __launch_bounds__(256) k_offsets(DevState s, BatchIn b, Work w, 
   k.pt = s.ptail[c]; k.us = s.used[c]; k.bu = 0;
   k.s1_off = 0; k.s1_units = 0; k.s1_rec = 0; k.s2_units = 0; k.s2_rec = 0; k.ovf = 0; k.in2 = 0; k.bytes = 0;
   uint32_t dp = 0, de = 0;
-  if (has_direct) { dp = w.dstart[c]; de = w.dend[c]; }
+  if (has_direct && w.dstamp[c] == w.stamp) { dp = w.dstart[c]; de = w.dend[c]; }
   const uint32_t* dmsg = w.sval[0];
 
   // direct hit (always the thin list, rank 0)

@@ -122,6 +122,8 @@ struct Work {
   uint32_t* hist_tmp;    // scan scratch
   uint32_t* dstart;      // [N+1]
   uint32_t* dend;        // [N+1]
+  uint32_t* dstamp;      // [N+1] dstart/dend of a connection are valid iff dstamp == stamp
+  uint32_t stamp;        // per-slot batch counter (never 0)
   // outputs
   uint32_t* batch_units; // [N] units consumed by this batch per connection (for release)
   Span* spans;           // [2*max_conns]

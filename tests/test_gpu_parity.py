@@ -301,3 +301,25 @@ def test_global_memory_pool_backpressure(pcdn):
     with pytest.raises(pcdn.PcdnError) as ei:
         w.e.handle_broadcast_message([0], orc.broadcast_frame([0], b"y" * 20000))
     assert ei.value.code == -1                         # can never fit
+
+
+def test_edge_cases(pcdn):
+    """empty topic list (legal on the wire, routes to nobody — SURVEY App. B), zero-length raw through
+    the ABI, 200 topics in one message, a 1.5 MB frame (94 staging chunks), 1-byte and 128-byte keys,
+    broadcast whose only subscriber is a peer broker, empty batch"""
+    w = World(pcdn, max_conns=512, ring_bytes_per_conn=4 << 20, max_batch_bytes=64 << 20, max_batch_deliveries=1 << 16)
+    for i in range(100):
+        w.add_user(bytes([i + 1]) * (1 if i % 2 else 128), list(range(i % 7, 200, 7)))
+    w.add_broker("only/broker", [201])
+    assert w.e.flush() == 0                                            # empty batch: nothing launched
+    w.bcast([], orc.broadcast_frame([], b"to nobody"))
+    w.bcast([3], b"")                                                  # zero-length raw is still a frame: header only
+    w.bcast(list(range(200)), orc.broadcast_frame(list(range(200)), b"everyone once"))
+    big = orc.broadcast_frame([5], bytes(range(256)) * 6000)           # 1.5 MB, 2 capnp segments
+    w.bcast([5], big)
+    w.bcast([201], orc.broadcast_frame([201], b"for the mesh"))
+    w.bcast([201], orc.broadcast_frame([201], b"not for brokers"), True)
+    w.direct(bytes([2]), orc.direct_frame(bytes([2]), b"one-byte key"))
+    w.direct(bytes([3]) * 128, orc.direct_frame(bytes([3]) * 128, big[:70000]))
+    n = w.check()
+    assert n > 150
