@@ -260,7 +260,11 @@ int pcdn_broker_receive(pcdn_engine* e, const char* identifier, const uint8_t* r
                         uint32_t raw_len);
 /* Many inbound frames in one call (one lock, no per-call FFI cost): frame i enters
  * user_receive_loop (origin 0, `sender` = that user's key) or broker_receive_loop (origin 1).
- * rc_out[i] (optional) gets what pcdn_user_receive / pcdn_broker_receive would have returned. */
+ * rc_out[i] (optional) gets what pcdn_user_receive / pcdn_broker_receive would have returned.
+ * Returns the number of frames consumed (== n unless a capacity condition — no free batch slot,
+ * global memory pool exhausted — stopped it: drain a batch and call again with the rest) or a
+ * negative code when not even the first frame could be taken.  Large calls are parsed and copied
+ * by several host threads (PCDN_INGEST_THREADS, default min(16, cores)); order is preserved. */
 typedef struct pcdn_frame {
   const uint8_t* sender;
   uint32_t sender_len;

@@ -28,7 +28,7 @@ SOURCES = ["engine.cu", "kernels.cu", "host_state.cpp", "frame_parse.cpp"]
 HEADERS = ["kernels.cuh", "host_state.h", "frame_parse.h", "frame_parse_core.h", "hash.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC,-pthread", "-shared",
 ]
 
 KIND_DIRECT, KIND_BROADCAST, KIND_SUBSCRIBE, KIND_UNSUBSCRIBE = 3, 4, 5, 6
@@ -356,8 +356,34 @@ class Engine:
         for i, (sender, origin, raw) in enumerate(frames):
             arr[i] = Frame(sender, len(sender), origin, raw, len(raw), 0)
         rcs = (C.c_int32 * max(1, n))()
-        self._chk(self.L.pcdn_receive_frames(self.h, arr, n, rcs))
+        done = self._chk(self.L.pcdn_receive_frames(self.h, arr, n, rcs))
+        if done != n:
+            raise PcdnError(-11, f"only {done} of {n} frames consumed: drain a batch and resubmit the rest")
         return [rcs[i] for i in range(n)]
+
+    def receive_frames_all(self, frames: Sequence[Tuple[bytes, int, bytes]]):
+        """like receive_frames, but when the engine stops early (all batch slots in flight, memory
+        pool exhausted) it drains the outstanding batches and resumes — the loop a broker's ingest
+        task runs.  Returns (per-frame return codes, {conn: delivered frames})."""
+        n = len(frames)
+        arr = (Frame * max(1, n))()
+        for i, (sender, origin, raw) in enumerate(frames):
+            arr[i] = Frame(sender, len(sender), origin, raw, len(raw), 0)
+        rcs = (C.c_int32 * max(1, n))()
+        out: Dict[int, List[bytes]] = {}
+        pos = 0
+        while pos < n:
+            done = self.L.pcdn_receive_frames(self.h, C.cast(C.byref(arr, pos * C.sizeof(Frame)), C.POINTER(Frame)), n - pos,
+                                              C.cast(C.byref(rcs, pos * 4), C.POINTER(C.c_int32)))
+            if done < 0 and done != -11:
+                self._chk(done)
+            pos += max(done, 0)
+            if pos < n:
+                for conn, fr in self.drain().items():
+                    out.setdefault(conn, []).extend(fr)
+        for conn, fr in self.drain().items():
+            out.setdefault(conn, []).extend(fr)
+        return [rcs[i] for i in range(n)], out
 
     def flush(self) -> int:
         b = C.c_uint64(0)

@@ -15,6 +15,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "frame_parse.h"
@@ -843,20 +844,186 @@ int pcdn_broker_receive(pcdn_engine* e, const char* /*identifier*/, const uint8_
   GUARD_END
 }
 
+// ---- multi-threaded ingest of many frames -----------------------------------------------------
+extern "C++" {
+namespace {
+
+struct FramePlan {
+  int8_t kind;        // 3 / 4 routable; -1 = needs the sequential path (state change, other kinds); -2 = protocol error
+  int32_t rc;
+  uint32_t f0_off, f0_len, ntopics;
+  uint32_t msg_idx, topic_off, bcast_pos;
+  uint64_t arena_off;
+};
+
+template <class F>
+void parallel_for(uint32_t n, uint32_t nthreads, F f) {
+  if (n < 2048 || nthreads <= 1) { f(0u, n); return; }
+  std::vector<std::thread> th;
+  const uint32_t per = (n + nthreads - 1) / nthreads;
+  for (uint32_t t = 1; t < nthreads; t++) {
+    const uint32_t lo = t * per, hi = std::min(n, lo + per);
+    if (lo < hi) th.emplace_back([=] { f(lo, hi); });
+  }
+  f(0u, std::min(n, per));
+  for (auto& x : th) x.join();
+}
+
+uint32_t ingest_threads() {
+  static uint32_t n = [] {
+    if (const char* e = std::getenv("PCDN_INGEST_THREADS")) return (uint32_t)std::max(1, atoi(e));
+    return std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  }();
+  return n;
+}
+
+// One receive-loop iteration per frame, in order; returns the number of frames consumed (a capacity
+// condition — no free batch slot, memory pool exhausted — stops early) or a negative error when
+// nothing could be consumed.  Large calls run in three phases per run of routable frames:
+//   A (parallel)  parse (host mode) or tag peek (device-parse mode) of every frame
+//   scan (serial) a few integer adds per frame: placement in the open batch, capacity, ordering
+//   B (parallel)  copy of the raw bytes into the pinned arena + descriptor fill by index
+// Frames that change state (Subscribe/Unsubscribe) or need the exact synchronous error path end a
+// run and go through user_receive_locked / broker_receive_locked, so R12 ordering is untouched.
+int receive_frames_locked(pcdn_engine* e, const pcdn_frame* frames, uint32_t n, int32_t* rc_out) {
+  const pcdn_config& c = e->cfg;
+  const bool dev = (c.flags & PCDN_FLAG_DEVICE_PARSE) != 0;
+  const uint32_t T = ingest_threads();
+  if (n < 2048 || T <= 1 || !e->has_device) {
+    for (uint32_t i = 0; i < n; i++) {
+      const pcdn_frame& f = frames[i];
+      int rc = f.origin ? broker_receive_locked(e, f.raw, f.raw_len) : user_receive_locked(e, f.sender, f.sender_len, f.raw, f.raw_len);
+      if (rc_out) rc_out[i] = rc;
+      if (rc == PCDN_EAGAIN || rc == PCDN_ECUDA || rc == PCDN_ENODEV) return i ? (int)i : rc;
+    }
+    return (int)n;
+  }
+  std::vector<FramePlan> plan(n);
+  // ---- phase A
+  parallel_for(n, T, [&](uint32_t lo, uint32_t hi) {
+    for (uint32_t i = lo; i < hi; i++) {
+      const pcdn_frame& f = frames[i];
+      FramePlan& p = plan[i];
+      p.kind = -1; p.rc = 0; p.f0_off = p.f0_len = p.ntopics = 0;
+      if (f.raw_len > 0x1FFFFFFFu || align_up(4 + (size_t)f.raw_len, 16) + 64 > c.max_batch_bytes) continue;  // sequential path reports it
+      if (dev) {
+        const int k = peek_kind_core(f.raw, f.raw_len);
+        if (k == PCDN_KIND_DIRECT || k == PCDN_KIND_BROADCAST) p.kind = (int8_t)k;
+        continue;
+      }
+      ParsedFrame pf;
+      if (!parse_frame(f.raw, f.raw_len, &pf)) { p.kind = -2; p.rc = PCDN_EPARSE; continue; }
+      if (pf.kind == PCDN_KIND_DIRECT) {
+        p.kind = 3; p.f0_off = pf.f0_off; p.f0_len = pf.f0_len > c.max_key_len ? 0 : pf.f0_len;
+      } else if (pf.kind == PCDN_KIND_BROADCAST) {
+        if (pf.f0_len > 8192) { p.kind = -2; p.rc = PCDN_EPARSE; continue; }
+        uint32_t cnt = pf.f0_len;
+        if (!f.origin) {  // user-origin: Topic::prune
+          cnt = 0;
+          for (uint32_t k = 0; k < pf.f0_len; k++) cnt += topic_kept(f.raw + pf.f0_off, k, c.n_valid_topics) ? 1u : 0u;
+          if (cnt == 0) { p.kind = -2; p.rc = PCDN_EPRUNE; continue; }
+        }
+        p.kind = 4; p.f0_off = pf.f0_off; p.f0_len = pf.f0_len; p.ntopics = cnt;
+      }
+    }
+  });
+  uint32_t i = 0;
+  while (i < n) {
+    FramePlan& p0 = plan[i];
+    if (p0.kind == -2) { if (rc_out) rc_out[i] = p0.rc; i++; continue; }
+    if (p0.kind == -1) {
+      const pcdn_frame& f = frames[i];
+      int rc = f.origin ? broker_receive_locked(e, f.raw, f.raw_len) : user_receive_locked(e, f.sender, f.sender_len, f.raw, f.raw_len);
+      if (rc_out) rc_out[i] = rc;
+      if (rc == PCDN_EAGAIN || rc == PCDN_ECUDA || rc == PCDN_ENODEV) return i ? (int)i : rc;
+      i++;
+      continue;
+    }
+    // ---- a run of routable frames starting at i: placement scan
+    int rc = acquire_open_slot(e);
+    if (rc) return i ? (int)i : rc;
+    Slot& s = e->slots[e->open_slot];
+    uint32_t nm = (uint32_t)s.kind.size(), nb = (uint32_t)s.bcast_index.size(), nt = (uint32_t)s.topics.size(), nd = 0;
+    uint64_t used = s.arena_used, ingress = 0;
+    const uint32_t m0 = nm, b0 = nb, t0 = nt;
+    uint32_t j = i;
+    bool full = false;
+    for (; j < n; j++) {
+      FramePlan& p = plan[j];
+      if (p.kind == -2) continue;
+      if (p.kind == -1) break;
+      const pcdn_frame& f = frames[j];
+      const uint64_t sb = align_up(4 + (size_t)f.raw_len, 16);
+      if (nm >= c.max_batch_msgs || used + sb + 64 > c.max_batch_bytes || (p.kind == 4 && nb >= c.max_batch_bcast) ||
+          (uint64_t)nt + p.ntopics > e->topics_cap) { full = true; break; }
+      if (c.global_memory_pool_size && e->inflight_bytes + ingress + f.raw_len > c.global_memory_pool_size) { full = true; break; }
+      p.msg_idx = nm++; p.arena_off = used; used += sb; ingress += f.raw_len;
+      if (p.kind == 4) { p.bcast_pos = nb++; p.topic_off = nt; nt += dev ? 0 : p.ntopics; }
+      else nd++;
+    }
+    if (j == i) {  // nothing fits: the open batch is full (or the pool is) — launch it and retry, or give up
+      if (s.kind.empty()) return i ? (int)i : fail(PCDN_EAGAIN, "global memory pool exhausted: release a batch first");
+      if ((rc = flush_open(e, nullptr))) return i ? (int)i : rc;
+      continue;
+    }
+    // ---- phase B: descriptors by index + raw bytes
+    s.kind.resize(nm); s.flags.resize(nm); s.slot_off16.resize(nm); s.raw_len.resize(nm); s.aux_off.resize(nm); s.aux_len.resize(nm);
+    s.bcast_index.resize(nb); s.topics.resize(nt);
+    parallel_for(j - i, T, [&](uint32_t lo, uint32_t hi) {
+      for (uint32_t q = i + lo; q < i + hi; q++) {
+        const FramePlan& p = plan[q];
+        if (p.kind < 0) continue;
+        const pcdn_frame& f = frames[q];
+        const uint32_t m = p.msg_idx;
+        const size_t sb = align_up(4 + (size_t)f.raw_len, 16);
+        uint8_t* dst = s.h_arena + p.arena_off;
+        std::memset(dst, 0, 4);
+        if (f.raw_len) std::memcpy(dst + 4, f.raw, f.raw_len);
+        std::memset(dst + 4 + f.raw_len, 0, sb - 4 - f.raw_len);
+        s.kind[m] = (uint8_t)p.kind;
+        uint8_t fl = f.origin ? MSGF_USERS_ONLY : 0;
+        if (dev) fl |= MSGF_DEVPARSE | ((p.kind == 4 && !f.origin) ? MSGF_PRUNE : 0);
+        s.flags[m] = fl;
+        s.slot_off16[m] = (uint32_t)(p.arena_off / 16);
+        s.raw_len[m] = f.raw_len;
+        if (p.kind == 4) {
+          s.bcast_index[p.bcast_pos] = m;
+          s.aux_off[m] = p.topic_off;
+          s.aux_len[m] = dev ? 0 : p.ntopics;
+          if (!dev) {
+            uint32_t k = p.topic_off;
+            for (uint32_t t = 0; t < p.f0_len; t++)
+              if (f.origin || topic_kept(f.raw + p.f0_off, t, c.n_valid_topics)) s.topics[k++] = f.raw[p.f0_off + t];
+          }
+        } else {
+          s.aux_off[m] = dev ? 0 : (uint32_t)(p.arena_off + 4 + p.f0_off);  // recipient read in place (word aligned)
+          s.aux_len[m] = dev ? 0 : p.f0_len;
+        }
+      }
+    });
+    if (rc_out)
+      for (uint32_t q = i; q < j; q++) rc_out[q] = plan[q].kind == -2 ? plan[q].rc : 0;
+    s.arena_used = used;
+    s.n_direct += nd;
+    s.ingress_bytes += ingress;
+    e->inflight_bytes += ingress;
+    if (dev && nm > m0) s.devparse = true;
+    (void)b0; (void)t0;
+    i = j;
+    if (full) {
+      if ((rc = flush_open(e, nullptr))) return (int)i;
+    }
+  }
+  return (int)n;
+}
+
+}  // namespace
+}  // extern "C++"
+
 int pcdn_receive_frames(pcdn_engine* e, const pcdn_frame* frames, uint32_t n, int32_t* rc_out) {
   GUARD_BEGIN
   LOCK;
-  int first_err = 0;
-  for (uint32_t i = 0; i < n; i++) {
-    const pcdn_frame& f = frames[i];
-    int rc = f.origin ? broker_receive_locked(e, f.raw, f.raw_len) : user_receive_locked(e, f.sender, f.sender_len, f.raw, f.raw_len);
-    if (rc_out) rc_out[i] = rc;
-    // capacity problems stop the call (the caller polls/releases and resumes at i); protocol errors
-    // of a single frame (the reference would drop that peer) do not
-    if (rc == PCDN_EAGAIN || rc == PCDN_ENOSPC || rc == PCDN_ECUDA || rc == PCDN_ENODEV) return rc;
-    if (rc < 0 && !first_err) first_err = rc;
-  }
-  return 0;
+  return receive_frames_locked(e, frames, n, rc_out);
   GUARD_END
 }
 
