@@ -86,7 +86,7 @@ def zipf_p(n, s=0.99):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", required=True, choices=["C3", "C4", "C5dense", "C5sparse", "latency"])
+    ap.add_argument("--workload", required=True, choices=["C3", "C4", "C5dense", "C5sparse", "latency", "churn"])
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--variant", type=int, default=0)
@@ -138,6 +138,60 @@ def main():
                                      "deliveries": int(r.n_deliveries)})
             eng.close()
         print(json.dumps(out), flush=True)
+        return
+
+    if wl == "churn":
+        # config C2 with connection / subscription churn between batches: every step 40 (un)subscribes and
+        # 10 disconnect+connect pairs go through the state ABI (host mirror → journal → k_apply_* on the stream)
+        n, M = 1 << 20, 8
+        rng = np.random.default_rng(11)
+        keys = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        keys[:, :8] = np.arange(n, dtype=np.uint64).view(np.uint8).reshape(n, 8)
+        frames = [B.broadcast_frame(0, bytes(((i * 131 + m) & 0xFF) for i in range(1024))) for m in range(M)]
+        L = len(frames[0]); slot = (4 + L + 15) // 16 * 16; rec = (4 + L + 31) // 32 * 32
+        eng = pkg.Engine(device=0, stream=stream.cuda_stream, max_conns=n, max_topics=256, max_keys=n + 4096, max_key_len=32,
+                         ring_bytes_per_conn=16 * rec, max_batch_msgs=64, max_batch_bcast=16, max_batch_bytes=1 << 20,
+                         max_batch_deliveries=M * n + 1024, batch_slots=4, pack_variant=args.variant)
+        eng.add_users_bulk(keys, 32, np.zeros(n, dtype=np.uint16), np.arange(n + 1, dtype=np.uint32))
+        arena = np.zeros(M * slot + 64, dtype=np.uint8)
+        for m, fr in enumerate(frames):
+            arena[m * slot + 4:m * slot + 4 + L] = np.frombuffer(fr, dtype=np.uint8)
+        db = DeviceBatch(pkg, torch, dev, arena, np.full(M, 4), np.zeros(M), np.arange(M) * (slot // 16), np.full(M, L), np.arange(M),
+                         np.ones(M), np.zeros(M), np.arange(M))
+        kb = [keys[i].tobytes() for i in range(4096)]
+        res = {}
+        for churn in (False, True):
+            it = 0
+            def step():
+                nonlocal it
+                if churn:
+                    base = (it * 50) % 4000
+                    for q in range(40):
+                        k = kb[base + q]
+                        (eng.unsubscribe_user_from if it & 1 else eng.subscribe_user_to)(k, [0])
+                    for q in range(40, 50):
+                        k = kb[base + q]
+                        eng.remove_user(k)
+                        eng.add_user(k, [0])
+                it += 1
+                b = eng.submit_device(db.db)
+                eng.release_batch(b)
+            with torch.cuda.stream(stream):
+                for _ in range(4):
+                    step()
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0 = time.perf_counter()
+                e0.record(stream)
+                for _ in range(args.steps * 2):
+                    step()
+                e1.record(stream)
+                torch.cuda.synchronize(dev)
+                t1 = time.perf_counter()
+            ms = e0.elapsed_time(e1) / (args.steps * 2)
+            res["churn" if churn else "steady"] = {"ms_per_step": ms, "GBps": M * n * (4 + L) / ms / 1e6, "wall_ms_per_step": (t1 - t0) * 1e3 / (args.steps * 2)}
+        print(json.dumps({"metric": "C2 with table churn between batches (40 (un)subscribes + 10 disconnect/connect per step)", **res}), flush=True)
+        eng.close()
         return
 
     if wl == "C4":

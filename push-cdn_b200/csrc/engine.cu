@@ -113,7 +113,10 @@ struct pcdn_engine {
   uint64_t next_batch_id = 1;
   std::vector<uint64_t> inflight;  // submit order
   size_t desc_cap = 0, topics_cap = 0;
-  // journal device buffers
+  // journal staging (pinned + device), reuse guarded by an event
+  uint8_t* jstage_h = nullptr; uint8_t* jstage_d = nullptr; size_t jstage_cap = 0;
+  cudaEvent_t ev_journal = nullptr; bool ev_journal_pending = false;
+  // (legacy separate journal buffers, unused)
   Upd32* j_u32 = nullptr; size_t j_u32_cap = 0;
   UpdSlot* j_slot = nullptr; size_t j_slot_cap = 0;
   uint32_t* j_kslot = nullptr; uint8_t* j_kbytes = nullptr; size_t j_key_cap = 0;
@@ -130,16 +133,6 @@ struct pcdn_engine {
 };
 
 namespace {
-
-int grow(pcdn_engine* e, void** p, size_t* cap, size_t need, size_t elem) {
-  if (need <= *cap) return 0;
-  size_t ncap = std::max(need, *cap * 2 + 1024);
-  if (*p) { cudaStreamSynchronize(e->stream); cudaFree(*p); *p = nullptr; }
-  cudaError_t err = cudaMalloc(p, ncap * elem);
-  if (err != cudaSuccess) { *cap = 0; return fail(PCDN_ENOMEM, std::string("journal cudaMalloc: ") + cudaGetErrorString(err)); }
-  *cap = ncap;
-  return 0;
-}
 
 // Upload changed table words/slots/keys and apply them on the engine stream (K4).  Stream order
 // gives R12: every earlier batch sees the old tables, every later batch the new ones.
@@ -169,31 +162,40 @@ int flush_journal(pcdn_engine* e) {
     e->h_kbytes.resize(at + g.key_stride);
     std::memcpy(&e->h_kbytes[at], &t.keys[(size_t)k * g.key_stride], g.key_stride);
   }
-  int rc;
-  if ((rc = grow(e, (void**)&e->j_u32, &e->j_u32_cap, e->h_u32.size(), sizeof(Upd32)))) return rc;
-  if ((rc = grow(e, (void**)&e->j_slot, &e->j_slot_cap, e->h_slot.size(), sizeof(UpdSlot)))) return rc;
-  if (e->h_kslot.size() > e->j_key_cap) {
-    size_t ncap = std::max(e->h_kslot.size(), e->j_key_cap * 2 + 256);
-    cudaStreamSynchronize(st);
-    if (e->j_kslot) cudaFree(e->j_kslot);
-    if (e->j_kbytes) cudaFree(e->j_kbytes);
-    e->j_kslot = nullptr; e->j_kbytes = nullptr; e->j_key_cap = 0;
-    CUDA_TRY(cudaMalloc((void**)&e->j_kslot, ncap * 4));
-    CUDA_TRY(cudaMalloc((void**)&e->j_kbytes, ncap * g.key_stride));
-    e->j_key_cap = ncap;
+  // One pinned staging block [Upd32 | UpdSlot | key slots | key bytes] → one H2D copy → apply kernels.
+  // The staging block is reused by the next flush; an event (not a stream sync) guards it, so table
+  // churn at control-plane rate never stalls the batches already queued on the stream.
+  const size_t b_u32 = align_up(e->h_u32.size() * sizeof(Upd32), 16), b_slot = align_up(e->h_slot.size() * sizeof(UpdSlot), 16);
+  const size_t b_ks = align_up(e->h_kslot.size() * 4, 16), b_kb = align_up(e->h_kbytes.size(), 16);
+  const size_t total = b_u32 + b_slot + b_ks + b_kb;
+  if (total) {
+    if (e->ev_journal_pending) { CUDA_TRY(cudaEventSynchronize(e->ev_journal)); e->ev_journal_pending = false; }
+    if (total > e->jstage_cap) {
+      const size_t ncap = std::max(total, e->jstage_cap * 2 + (1 << 16));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      if (e->jstage_h) cudaFreeHost(e->jstage_h);
+      if (e->jstage_d) cudaFree(e->jstage_d);
+      e->jstage_h = nullptr; e->jstage_d = nullptr; e->jstage_cap = 0;
+      CUDA_TRY(cudaMallocHost((void**)&e->jstage_h, ncap));
+      CUDA_TRY(cudaMalloc((void**)&e->jstage_d, ncap));
+      e->jstage_cap = ncap;
+    }
+    uint8_t* h = e->jstage_h;
+    if (b_u32) std::memcpy(h, e->h_u32.data(), e->h_u32.size() * sizeof(Upd32));
+    if (b_slot) std::memcpy(h + b_u32, e->h_slot.data(), e->h_slot.size() * sizeof(UpdSlot));
+    if (b_ks) std::memcpy(h + b_u32 + b_slot, e->h_kslot.data(), e->h_kslot.size() * 4);
+    if (b_kb) std::memcpy(h + b_u32 + b_slot + b_ks, e->h_kbytes.data(), e->h_kbytes.size());
+    CUDA_TRY(cudaMemcpyAsync(e->jstage_d, h, total, cudaMemcpyHostToDevice, st));
+    uint8_t* d = e->jstage_d;
+    launch_apply_updates(e->dev, (const Upd32*)d, (uint32_t)e->h_u32.size(), (const UpdSlot*)(d + b_u32), (uint32_t)e->h_slot.size(),
+                         (const uint32_t*)(d + b_u32 + b_slot), d + b_u32 + b_slot + b_ks, (uint32_t)e->h_kslot.size(), st);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(e->ev_journal, st));
+    e->ev_journal_pending = true;
   }
-  if (!e->h_u32.empty()) CUDA_TRY(cudaMemcpyAsync(e->j_u32, e->h_u32.data(), e->h_u32.size() * sizeof(Upd32), cudaMemcpyHostToDevice, st));
-  if (!e->h_slot.empty()) CUDA_TRY(cudaMemcpyAsync(e->j_slot, e->h_slot.data(), e->h_slot.size() * sizeof(UpdSlot), cudaMemcpyHostToDevice, st));
-  if (!e->h_kslot.empty()) {
-    CUDA_TRY(cudaMemcpyAsync(e->j_kslot, e->h_kslot.data(), e->h_kslot.size() * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(e->j_kbytes, e->h_kbytes.data(), e->h_kbytes.size(), cudaMemcpyHostToDevice, st));
-  }
-  launch_apply_updates(e->dev, e->j_u32, (uint32_t)e->h_u32.size(), e->j_slot, (uint32_t)e->h_slot.size(), e->j_kslot,
-                       e->j_kbytes, (uint32_t)e->h_kslot.size(), st);
-  CUDA_TRY(cudaGetLastError());
-  // pageable sources were consumed by the async copies (staged) — but the journal vectors are
-  // reused only after this point by the next flush, which is fine for staged copies.
-  CUDA_TRY(cudaStreamSynchronize(st));  // control-plane rate; keeps host vectors' lifetime trivial
+  // whole-table uploads come from pageable vectors (staged by the runtime before the call returns);
+  // they only happen on bulk loads, where one synchronisation is irrelevant
+  if (full_keys || full_sub || full_slots) CUDA_TRY(cudaStreamSynchronize(st));
   t.clear_dirty();
   return 0;
 }
@@ -402,6 +404,9 @@ void destroy_engine(pcdn_engine* e) {
     }
     for (void* p : e->dev_allocs) cudaFree(p);
     for (void* p : e->pin_allocs) cudaFreeHost(p);
+    if (e->jstage_h) cudaFreeHost(e->jstage_h);
+    if (e->jstage_d) cudaFree(e->jstage_d);
+    if (e->ev_journal) cudaEventDestroy(e->ev_journal);
     if (e->j_u32) cudaFree(e->j_u32);
     if (e->j_slot) cudaFree(e->j_slot);
     if (e->j_kslot) cudaFree(e->j_kslot);
@@ -441,6 +446,7 @@ int init_device(pcdn_engine* e) {
   if (c.stream) { e->stream = (cudaStream_t)c.stream; e->own_stream = false; }
   else { CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true; }
   CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&e->ev_journal, cudaEventDisableTiming));
   {
     // highest priority: when a pack and the (small) control kernels of the next batch become
     // runnable together, the pack's persistent CTAs must be placed first and evenly over the SMs
