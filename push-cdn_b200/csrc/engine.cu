@@ -1103,25 +1103,47 @@ int pcdn_next_batch(pcdn_engine* e, uint64_t* batch_id) {
 
 int pcdn_poll(pcdn_engine* e, uint64_t batch_id, pcdn_batch_result* out, int block) {
   GUARD_BEGIN
-  LOCK;
-  Slot* s = find_slot(e, batch_id);
-  if (!s) return fail(PCDN_ENOENT, "unknown batch id");
-  if (!s->polled) {
-    if (!block) {
-      cudaError_t q = cudaEventQuery(s->ev_done);
-      if (q == cudaErrorNotReady) return 1;
-      CUDA_TRY(q);
+  // The blocking waits happen OUTSIDE the engine lock, so ingest threads keep appending to the next
+  // batch while an egress thread waits for this one (one poller per batch).
+  cudaEvent_t ev_early = nullptr, ev_done = nullptr;
+  bool wait = false;
+  {
+    std::lock_guard<std::mutex> g(e->mu);
+    Slot* s = find_slot(e, batch_id);
+    if (!s) return fail(PCDN_ENOENT, "unknown batch id");
+    if (!s->polled) {
+      if (!block) {
+        cudaError_t q = cudaEventQuery(s->ev_done);
+        if (q == cudaErrorNotReady) return 1;
+        CUDA_TRY(q);
+      }
+      ev_early = s->ev_early; ev_done = s->ev_done; wait = true;
     }
+  }
+  uint32_t nsp = 0, nov = 0;
+  bool devparse = false;
+  if (wait) {
     // 1. counters as of k_offsets → exact size of the span table; its D2H overlaps the pack
-    CUDA_TRY(cudaEventSynchronize(s->ev_early));
-    const uint32_t nsp = std::min<uint32_t>(s->h_early->n_spans, 2 * e->geo.max_conns);
-    const uint32_t nov = std::min<uint32_t>(s->h_early->n_overflow, e->geo.max_conns);
-    if (nsp) CUDA_TRY(cudaMemcpyAsync(s->h_spans, s->w.spans, (size_t)nsp * sizeof(Span), cudaMemcpyDeviceToHost, e->copy_stream));
-    if (nov) CUDA_TRY(cudaMemcpyAsync(s->h_overflow, s->w.overflow, (size_t)nov * 4, cudaMemcpyDeviceToHost, e->copy_stream));
+    CUDA_TRY(cudaEventSynchronize(ev_early));
+    {
+      std::lock_guard<std::mutex> g(e->mu);
+      Slot* s = find_slot(e, batch_id);
+      if (!s) return fail(PCDN_ENOENT, "batch released while it was being polled");
+      nsp = std::min<uint32_t>(s->h_early->n_spans, 2 * e->geo.max_conns);
+      nov = std::min<uint32_t>(s->h_early->n_overflow, e->geo.max_conns);
+      devparse = s->devparse;
+      if (nsp) CUDA_TRY(cudaMemcpyAsync(s->h_spans, s->w.spans, (size_t)nsp * sizeof(Span), cudaMemcpyDeviceToHost, e->copy_stream));
+      if (nov) CUDA_TRY(cudaMemcpyAsync(s->h_overflow, s->w.overflow, (size_t)nov * 4, cudaMemcpyDeviceToHost, e->copy_stream));
+    }
     // 2. the pack itself (ring bytes are valid after this)
-    CUDA_TRY(cudaEventSynchronize(s->ev_done));
-    if (s->devparse) CUDA_TRY(cudaMemcpyAsync(s->h_msg_status, s->w.msg_status, s->in.n_msgs, cudaMemcpyDeviceToHost, e->copy_stream));
-    if (nsp || nov || s->devparse) CUDA_TRY(cudaStreamSynchronize(e->copy_stream));
+    CUDA_TRY(cudaEventSynchronize(ev_done));
+  }
+  std::lock_guard<std::mutex> _g(e->mu);
+  Slot* s = find_slot(e, batch_id);
+  if (!s) return fail(PCDN_ENOENT, "batch released while it was being polled");
+  if (wait && !s->polled) {
+    if (devparse) CUDA_TRY(cudaMemcpyAsync(s->h_msg_status, s->w.msg_status, s->in.n_msgs, cudaMemcpyDeviceToHost, e->copy_stream));
+    if (nsp || nov || devparse) CUDA_TRY(cudaStreamSynchronize(e->copy_stream));
     if (s->devparse) { s->n_msg_errors = 0; for (uint32_t i = 0; i < s->in.n_msgs; i++) s->n_msg_errors += s->h_msg_status[i] != 0; }
     const BatchStats& bs = *s->h_stats;
     s->polled = true;

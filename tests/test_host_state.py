@@ -226,3 +226,29 @@ def test_prune_and_dispatch_errors(pcdn):
     assert e.user_receive(b"u", orc.serialize(orc.KIND_UNSUBSCRIBE, bytes([1]))) == 0
     assert e.debug_interested([1]) == []
     assert e.user_receive(b"u", orc.broadcast_frame([7], b"x")) == -8      # only invalid topics
+
+
+def test_state_calls_from_many_threads(pcdn):
+    """the engine serialises callers internally (one mutex = the reference's RwLock<Connections>):
+    concurrent add/subscribe/remove from several host threads leave a consistent table"""
+    import threading
+
+    e = pcdn.Engine(device=-1, max_conns=8192, max_keys=16384, max_key_len=16)
+
+    def work(t):
+        for i in range(1500):
+            k = bytes([t]) + i.to_bytes(4, "little")
+            e.add_user(k, [t % 8])
+            e.subscribe_user_to(k, [(t + 1) % 8])
+            if i % 3 == 0:
+                e.remove_user(k)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert e.num_users() == (4 * 1000, 0)
+    assert [len(e.debug_interested([t])) for t in range(5)] == [1000, 2000, 2000, 2000, 1000]
+    for t in range(4):
+        for i in (1, 2, 4, 1498):
+            assert e.debug_route(bytes([t]) + i.to_bytes(4, "little"))[0] == 1
+        assert e.debug_route(bytes([t]) + (3).to_bytes(4, "little")) == (0, -1)
