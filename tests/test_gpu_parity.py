@@ -323,3 +323,62 @@ def test_edge_cases(pcdn):
     w.direct(bytes([3]) * 128, orc.direct_frame(bytes([3]) * 128, big[:70000]))
     n = w.check()
     assert n > 100
+
+
+def test_concurrent_ingest_and_egress_threads(pcdn):
+    """one host thread feeds frames (pcdn_user_receive + flush), another polls / reads / releases
+    batches at the same time (the engine locks internally; pcdn_poll waits outside the lock).
+    Per-connection delivery order must still be the order in which the frames were handed over."""
+    import threading
+    import time
+
+    rng = random.Random(21)
+    w = World(pcdn, max_conns=1024, ring_bytes_per_conn=1 << 20, batch_slots=4, max_batch_msgs=256)
+    keys = [i.to_bytes(8, "little") for i in range(600)]
+    for k in keys:
+        w.add_user(k, [x for x in range(6) if rng.random() < 0.3])
+    frames = []
+    for j in range(3000):
+        if rng.random() < 0.5:
+            raw = orc.broadcast_frame([rng.randrange(6)], j.to_bytes(4, "little") * rng.randrange(1, 40))
+        else:
+            raw = orc.direct_frame(rng.choice(keys), j.to_bytes(4, "little") * rng.randrange(1, 40))
+        frames.append((rng.choice(keys), raw))
+        w.o.user_receive(frames[-1][0], raw)
+    got, done, errs = {}, threading.Event(), []
+
+    def consumer():
+        try:
+            while True:
+                b = w.e.next_batch()
+                if not b:
+                    if done.is_set() and not w.e.next_batch():
+                        return
+                    time.sleep(0.0005)
+                    continue
+                res = w.e.poll(b)
+                for conn, fr in w.e.collect_frames(res).items():
+                    got.setdefault(conn, []).extend(fr)
+                w.e.release_batch(b)
+        except Exception as ex:  # pragma: no cover
+            errs.append(ex)
+
+    t = threading.Thread(target=consumer)
+    t.start()
+    for i, (sender, raw) in enumerate(frames):
+        while True:
+            rc = w.e.user_receive(sender, raw)
+            if rc != -11:          # PCDN_EAGAIN: all batch slots in flight — the consumer will free one
+                break
+            time.sleep(0.0002)
+        assert rc == 0
+        if i % 97 == 0:
+            w.e.flush()
+    w.e.flush()
+    done.set()
+    t.join(60)
+    assert not errs and not t.is_alive()
+    want = w.expect()
+    assert set(got) == set(want)
+    for c in want:
+        assert got[c] == want[c], c
