@@ -116,10 +116,6 @@ struct pcdn_engine {
   // journal staging (pinned + device), reuse guarded by an event
   uint8_t* jstage_h = nullptr; uint8_t* jstage_d = nullptr; size_t jstage_cap = 0;
   cudaEvent_t ev_journal = nullptr; bool ev_journal_pending = false;
-  // (legacy separate journal buffers, unused)
-  Upd32* j_u32 = nullptr; size_t j_u32_cap = 0;
-  UpdSlot* j_slot = nullptr; size_t j_slot_cap = 0;
-  uint32_t* j_kslot = nullptr; uint8_t* j_kbytes = nullptr; size_t j_key_cap = 0;
   std::vector<Upd32> h_u32; std::vector<UpdSlot> h_slot; std::vector<uint32_t> h_kslot; std::vector<uint8_t> h_kbytes;
   bool timing = false;
   uint64_t inflight_bytes = 0;  // Limiter analogue: accepted frame bytes whose batch is not released yet
@@ -407,10 +403,6 @@ void destroy_engine(pcdn_engine* e) {
     if (e->jstage_h) cudaFreeHost(e->jstage_h);
     if (e->jstage_d) cudaFree(e->jstage_d);
     if (e->ev_journal) cudaEventDestroy(e->ev_journal);
-    if (e->j_u32) cudaFree(e->j_u32);
-    if (e->j_slot) cudaFree(e->j_slot);
-    if (e->j_kslot) cudaFree(e->j_kslot);
-    if (e->j_kbytes) cudaFree(e->j_kbytes);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->pack_stream) cudaStreamDestroy(e->pack_stream);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);

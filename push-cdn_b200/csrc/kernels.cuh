@@ -1,17 +1,20 @@
 // kernels.cuh — device-side data layout and kernel launchers of the fan-out engine (sm_100a).
 //
 // Per batch the engine runs (all on one stream, no host round trip in between):
-//   K3  direct_lookup   warp per direct message: cuckoo probe pubkey → route → target connection
-//       sort            stable LSD radix sort of (target conn, msg index) → per-connection buckets
-//   K1a topic_match     OR of subscription-bitmap rows per broadcast → match words + popcount ranks
-//   K1p plan            D_m per message, fat/thin class, scatter-list bases, pack tiles (prefix sums)
-//   K1b offsets         thread per connection walks the batch IN ORDER (R9), assigns ring offsets
-//                       and emits the compacted (connection, offset) scatter list per message
-//   K2a pack_fat        CTA stages a frame chunk in shared memory with one TMA bulk copy, patches
-//                       the big-endian length prefix, replicates it to every recipient (16 B stores
-//                       or TMA bulk stores)
-//   K2b pack_thin       warp per (message, recipient) for messages with few recipients
-//   K4  apply_updates   scatter of changed table words/slots (subscribe, add/remove, direct map)
+//   K0  k_parse         (device-parse mode) thread per frame: Cap'n Proto walk, Topic::prune, recipient
+//   K3  k_direct_lookup 8 lanes per direct message: cuckoo probe pubkey → route → target connection
+//       sort            stable (conn, msg) order: one-block bitonic (<= 2048 msgs) or 8-bit LSD radix
+//   K1a k_match         OR of subscription-bitmap rows per broadcast → match words + popcount ranks
+//   K1p k_plan_*        D_m per message, class (thin / message-major / connection-major), scatter-list
+//                       bases and pack tiles by prefix sums (one launch when <= 256 messages)
+//   K1b k_offsets       thread per connection walks the batch IN ORDER (R9), assigns ring offsets and
+//                       writes each offset at its deterministic rank in the per-message scatter list
+//   K2  k_pack          persistent CTAs, three phases: connection-major (groups of <= 8 small frames
+//                       staged by TMA, one TMA bulk store per contiguous run of a connection's
+//                       records), message-major (16 KiB chunks staged once per CTA, replicated to
+//                       ~2 MB worth of recipients per tile), thin (warp per delivery)
+//   K4  k_apply_*       scatter of changed table words/slots (subscribe, add/remove, direct map)
+//       k_release       ring space of a consumed batch goes back to the connections
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
