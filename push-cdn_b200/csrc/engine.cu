@@ -453,6 +453,7 @@ int init_device(pcdn_engine* e) {
   d.bucket_mask = g.bucket_mask; d.key_stride = g.key_stride; d.seed = g.seed;
   d.ring_bytes = c.ring_bytes_per_conn; d.ring_units = (uint32_t)(c.ring_bytes_per_conn / kUnit);
   d.cm_enable = (c.pack_variant & 2) ? 0 : 1;
+  d.fat_tile_bytes = (128u << 10) << ((c.pack_variant >> 4) & 15u);  // A/B: bits 4-7 double the tile
   d.n_valid_topics = c.n_valid_topics;
   d.max_key_len = c.max_key_len;
   DEV_ALLOC(d.sub, (size_t)g.T * g.W);

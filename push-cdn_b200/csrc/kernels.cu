@@ -307,37 +307,56 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict
                                                       uint32_t* __restrict__ kout, uint32_t* __restrict__ vout,
                                                       uint32_t n, uint32_t shift, const uint32_t* __restrict__ hist,
                                                       uint32_t ntiles) {
-  __shared__ uint32_t run[256];      // next output position per digit for this tile
-  __shared__ uint32_t wcnt[8][256];  // per-warp digit counts of the current round
-  __shared__ uint32_t woff[8][256];  // per-warp output start per digit
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  // The tile's 2048 items are taken as 8 rounds x 8 warps x 32 lanes in index order.  Every
+  // (round, warp) cell counts its digits with one match_any; one pass of "thread = digit" turns the
+  // 64 cells of each digit into exclusive offsets; then all 8 rounds scatter.  Three barriers per
+  // tile and all 16 loads of a thread in flight at once (the per-round version had 32 barriers).
+  __shared__ uint32_t run[256];       // output position of the tile's first item of each digit
+  __shared__ uint16_t cnt[64][256];   // per (round, warp) cell: digit count, then exclusive prefix
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, lt = (1u << lane) - 1u;
+  {
+    uint4* z = reinterpret_cast<uint4*>(&cnt[0][0]);
+#pragma unroll
+    for (int k = 0; k < 8; k++) z[k * 256 + threadIdx.x] = make_uint4(0, 0, 0, 0);
+  }
   run[threadIdx.x] = hist[threadIdx.x * ntiles + blockIdx.x];
   const uint32_t base = blockIdx.x * kSortTile;
+  uint32_t key[8], val[8];
+#pragma unroll
   for (int r = 0; r < 8; r++) {
+    const uint32_t i = base + r * 256 + threadIdx.x;
+    key[r] = i < n ? kin[i] : 0;
+    val[r] = i < n ? vin[i] : 0;
+  }
+  __syncthreads();
+  uint32_t rk[8];  // rank of the item among equal digits of its cell
 #pragma unroll
-    for (int k = 0; k < 8; k++) wcnt[k][threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t i = base + r * 256 + threadIdx.x;  // index order inside the tile is preserved
-    const bool valid = i < n;
-    const uint32_t key = valid ? kin[i] : 0, val = valid ? vin[i] : 0;
-    const uint32_t d = (key >> shift) & 255u;
+  for (int r = 0; r < 8; r++) {
+    const bool valid = base + r * 256 + threadIdx.x < n;
+    const uint32_t d = (key[r] >> shift) & 255u;
     const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xFFFFFFFFu);
-    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-    if (valid && rank == 0) wcnt[warp][d] = __popc(peers);
-    __syncthreads();
-    {  // thread = digit: prefix over the 8 warps (warp order = index order)
-      uint32_t off = run[threadIdx.x];
+    rk[r] = __popc(peers & lt);
+    if (valid && rk[r] == 0) cnt[r * 8 + warp][d] = (uint16_t)__popc(peers);
+  }
+  __syncthreads();
+  {  // thread = digit: exclusive prefix over the 64 cells (cell order = index order → stable)
+    uint32_t off = 0;
+#pragma unroll 8
+    for (int k = 0; k < 64; k++) {
+      const uint32_t c = cnt[k][threadIdx.x];
+      cnt[k][threadIdx.x] = (uint16_t)off;
+      off += c;
+    }
+  }
+  __syncthreads();
 #pragma unroll
-      for (int k = 0; k < 8; k++) { woff[k][threadIdx.x] = off; off += wcnt[k][threadIdx.x]; }
-      run[threadIdx.x] = off;
+  for (int r = 0; r < 8; r++) {
+    if (base + r * 256 + threadIdx.x < n) {
+      const uint32_t d = (key[r] >> shift) & 255u;
+      const uint32_t pos = run[d] + cnt[r * 8 + warp][d] + rk[r];
+      kout[pos] = key[r];
+      vout[pos] = val[r];
     }
-    __syncthreads();
-    if (valid) {
-      const uint32_t pos = woff[warp][d] + rank;
-      kout[pos] = key;
-      vout[pos] = val;
-    }
-    __syncthreads();
   }
 }
 
@@ -463,9 +482,9 @@ __device__ __forceinline__ uint32_t frame_vec_bytes(uint32_t raw_len) { return (
 __device__ __forceinline__ uint32_t frame_units(uint32_t raw_len) { return (4u + raw_len + kUnit - 1u) / kUnit; }
 // recipients per message-major tile: about 2 MB of stores per tile whatever the frame size, so a
 // batch of large frames still splits into enough tiles to balance ~450 persistent CTAs
-__device__ __forceinline__ uint32_t tile_recipients(uint32_t frame_bytes) {
+__device__ __forceinline__ uint32_t tile_recipients(uint32_t frame_bytes, uint32_t tile_bytes) {
   const uint32_t chunk = min(frame_bytes, kChunkBytes);
-  return max(64u, min(kTileRecipients, (2u << 20) / chunk));
+  return max(32u, min(kTileRecipients, tile_bytes / chunk));
 }
 
 __global__ void __launch_bounds__(256) k_plan_a(DevState s, BatchIn b, Work w, uint32_t nblk) {
@@ -482,7 +501,7 @@ __global__ void __launch_bounds__(256) k_plan_a(DevState s, BatchIn b, Work w, u
     } else {
       cls = CLS_FAT;
       const uint32_t nch = (frame_vec_bytes(len) + kChunkBytes - 1) / kChunkBytes;
-      const uint32_t tr = tile_recipients(frame_vec_bytes(len));
+      const uint32_t tr = tile_recipients(frame_vec_bytes(len), s.fat_tile_bytes);
       tiles = nch * ((d + tr - 1) / tr);
     }
   }
@@ -559,7 +578,7 @@ struct ConnCursor {
   uint32_t pt, us, bu;          // ring tail, units in use, units consumed by this batch
   uint32_t s1_off, s1_units, s1_rec, s2_units, s2_rec;
   uint32_t ovf, in2;
-  unsigned long long bytes;
+  uint32_t bytes;  // 4 + len summed over this batch's records: < ring bytes < 2^32
 };
 // reserve `u` units for one record; records never straddle the ring end
 __device__ __forceinline__ uint32_t alloc_record(ConnCursor& k, uint32_t u, uint32_t R, uint32_t raw_len) {
@@ -573,7 +592,7 @@ __device__ __forceinline__ uint32_t alloc_record(ConnCursor& k, uint32_t u, uint
   if (!k.in2) { if (!k.s1_rec) k.s1_off = at; k.s1_units += u; k.s1_rec++; }
   else { k.s2_units += u; k.s2_rec++; }
   k.pt = at + u;
-  k.bytes += 4ull + raw_len;
+  k.bytes += 4u + raw_len;
   return at;
 }
 
@@ -581,7 +600,8 @@ __device__ __forceinline__ uint32_t alloc_record(ConnCursor& k, uint32_t u, uint
 // hits from the connection's sorted bucket), so a connection's records are laid out in batch order
 // (R9) with no atomics, and writes each (conn, offset) into the per-message scatter list at its
 // deterministic rank (block base + word prefix + lane rank).
-__global__ void __launch_bounds__(256) k_offsets(DevState s, BatchIn b, Work w, int has_direct, uint32_t max_conns) {
+template <bool HAS_DIRECT>
+__global__ void __launch_bounds__(256) k_offsets(DevState s, BatchIn b, Work w, uint32_t max_conns) {
   __shared__ uint32_t sm[9];
   __shared__ unsigned long long red[2][8];
   __shared__ uint32_t span_base;
@@ -593,7 +613,7 @@ __global__ void __launch_bounds__(256) k_offsets(DevState s, BatchIn b, Work w, 
   k.pt = s.ptail[c]; k.us = s.used[c]; k.bu = 0;
   k.s1_off = 0; k.s1_units = 0; k.s1_rec = 0; k.s2_units = 0; k.s2_rec = 0; k.ovf = 0; k.in2 = 0; k.bytes = 0;
   uint32_t dp = 0, de = 0;
-  if (has_direct && w.dstamp[c] == w.stamp) { dp = w.dstart[c]; de = w.dend[c]; }
+  if (HAS_DIRECT && w.dstamp[c] == w.stamp) { dp = w.dstart[c]; de = w.dend[c]; }
   const uint32_t* dmsg = w.sval[0];
 
   // direct hit (always the thin list, rank 0)
@@ -632,7 +652,7 @@ __global__ void __launch_bounds__(256) k_offsets(DevState s, BatchIn b, Work w, 
       hits &= hits - 1;
       const uint32_t word = __shfl_sync(0xffffffffu, Bw, i), p = __shfl_sync(0xffffffffu, pre, i);
       const uint32_t mb = m_mb[i];
-      while (dp < de && dmsg[dp] < mb) { emit_direct(dmsg[dp]); dp++; }  // keep batch order (R9)
+      if (HAS_DIRECT) while (dp < de && dmsg[dp] < mb) { emit_direct(dmsg[dp]); dp++; }  // keep batch order (R9)
       if ((word >> lane) & 1u) {
         const uint32_t rank = p + __popc(word & lt), len = m_len[i];
         const uint32_t off = alloc_record(k, frame_units(len), R, len);
@@ -643,7 +663,7 @@ __global__ void __launch_bounds__(256) k_offsets(DevState s, BatchIn b, Work w, 
       }
     }
   }
-  while (dp < de) { emit_direct(dmsg[dp]); dp++; }
+  if (HAS_DIRECT) while (dp < de) { emit_direct(dmsg[dp]); dp++; }
 
   s.ptail[c] = k.pt;
   s.used[c] = k.us;
@@ -654,12 +674,10 @@ __global__ void __launch_bounds__(256) k_offsets(DevState s, BatchIn b, Work w, 
   uint32_t tot, ex = block256_excl_scan(nsp, &tot, sm);
   if (threadIdx.x == 0) span_base = tot ? atomicAdd(&w.stats->n_spans, tot) : 0;
   // block reduction of deliveries / bytes
-  unsigned long long nrec = k.s1_rec + k.s2_rec, by = k.bytes;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    nrec += __shfl_xor_sync(0xffffffffu, nrec, o);
-    by += __shfl_xor_sync(0xffffffffu, by, o);
-  }
+  // (redux.sync on 32-bit halves: a warp's record count fits 32 bits, its byte count may not)
+  const unsigned long long nrec = __reduce_add_sync(0xffffffffu, k.s1_rec + k.s2_rec);
+  const unsigned long long by = (unsigned long long)__reduce_add_sync(0xffffffffu, k.bytes & 0xFFFFu) +
+                                ((unsigned long long)__reduce_add_sync(0xffffffffu, k.bytes >> 16) << 16);
   if (lane == 0) { red[0][threadIdx.x >> 5] = nrec; red[1][threadIdx.x >> 5] = by; }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -678,7 +696,8 @@ __global__ void __launch_bounds__(256) k_offsets(DevState s, BatchIn b, Work w, 
   }
 }
 void launch_offsets(const DevState& s, const Work& w, const BatchIn& b, bool has_direct, cudaStream_t st) {
-  k_offsets<<<s.N / 256, 256, 0, st>>>(s, b, w, has_direct ? 1 : 0, s.N);
+  if (has_direct) k_offsets<true><<<s.N / 256, 256, 0, st>>>(s, b, w, s.N);
+  else k_offsets<false><<<s.N / 256, 256, 0, st>>>(s, b, w, s.N);
 }
 
 // =============================================================================== K2a pack (fat)
@@ -708,7 +727,7 @@ __device__ __forceinline__ void pack_fat_phase(const DevState& s, const BatchIn&
         while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (w.tbase[mid] <= t) lo = mid; else hi = mid; }
         const uint32_t m = lo, ltile = t - w.tbase[m], d = w.D[m];
         const uint32_t fb = frame_vec_bytes(b.raw_len[m]);
-        const uint32_t tr = tile_recipients(fb);
+        const uint32_t tr = tile_recipients(fb, s.fat_tile_bytes);
         const uint32_t ngrp = (d + tr - 1) / tr;
         const uint32_t ch = ltile / ngrp, grp = ltile % ngrp;
         const uint32_t nbytes = min(kChunkBytes, fb - ch * kChunkBytes);
@@ -973,7 +992,7 @@ __device__ __forceinline__ void pack_thin_phase(const DevState& s, const BatchIn
 // work from its own cursor, so CTAs drift from phase to phase without a grid barrier; the phases
 // write disjoint records).
 template <int VARIANT>
-__global__ void __launch_bounds__(256) k_pack(DevState s, BatchIn b, Work w) {
+__global__ void __launch_bounds__(256) k_pack(DevState s, BatchIn b, Work w, int do_thin) {
   __shared__ __align__(128) uint8_t buf[kCmGroup * kCmMaxBytes];  // 32 KB; the fat phase uses the first 16 KB
   __shared__ __align__(8) uint64_t bars[2];
   if (w.stats->status) return;
@@ -986,31 +1005,47 @@ __global__ void __launch_bounds__(256) k_pack(DevState s, BatchIn b, Work w) {
   pack_cm_phase<VARIANT>(s, b, w, buf, &bars[0]);
   __syncthreads();
   pack_fat_phase<VARIANT>(s, b, w, buf, &bars[1]);
+  if (do_thin) pack_thin_phase(s, b, w);
+}
+// Batches dominated by direct messages run the thin phase as its own launch at full occupancy
+// (no shared memory, 8 CTAs per SM): a warp per record is a chain of two dependent DRAM reads
+// (scatter entry, frame) before its stores, so the phase scales with warps in flight — 24 → 48
+// warps per SM measured +25 % on the 1 M x 512 B direct workload (profiles/r1_sweep_secondary.txt).
+__global__ void __launch_bounds__(256, 8) k_pack_thin(DevState s, BatchIn b, Work w) {
+  if (w.stats->status) return;
   pack_thin_phase(s, b, w);
 }
 
 int pack_setup() { return 0; }
 
 void launch_pack(const DevState& s, const Work& w, const BatchIn& b, uint32_t variant, int n_sms, cudaStream_t st) {
+  const bool thin_separate = b.n_msgs - b.n_bcast >= kThinSeparateMin;
   // Default (variant 0): TMA bulk stores, 3 CTAs per SM — the best of the sweep in profiles/.
   // A/B switches for profiling: bit 2 = st.global.cs.v4 stores instead of bulk stores; bit 1 = no
   // connection-major class (DevState::cm_enable, read by k_plan_a); bits 8+ = CTAs per SM.
   const uint32_t ctas_per_sm = (variant >> 8) ? (variant >> 8) : 3;
   const uint32_t grid = (uint32_t)n_sms * ctas_per_sm;
-  if (variant & 4) k_pack<0><<<grid, 256, 0, st>>>(s, b, w);
-  else k_pack<1><<<grid, 256, 0, st>>>(s, b, w);
+  if (variant & 4) k_pack<0><<<grid, 256, 0, st>>>(s, b, w, thin_separate ? 0 : 1);
+  else k_pack<1><<<grid, 256, 0, st>>>(s, b, w, thin_separate ? 0 : 1);
+  if (thin_separate) k_pack_thin<<<(uint32_t)n_sms * 8, 256, 0, st>>>(s, b, w);
 }
 
 // =============================================================================== release
-__global__ void k_release(DevState s, const uint32_t* __restrict__ batch_units) {
-  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < s.N) {
-    const uint32_t u = batch_units[c];
-    if (u) s.used[c] -= u;
+// four connections per thread (N is a multiple of 8192; both arrays are separate allocations)
+__global__ void __launch_bounds__(256) k_release(DevState s, const uint32_t* __restrict__ batch_units) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i * 4 < s.N) {
+    const uint4 u = reinterpret_cast<const uint4*>(batch_units)[i];
+    if (u.x | u.y | u.z | u.w) {
+      uint4* p = reinterpret_cast<uint4*>(s.used) + i;
+      uint4 v = *p;
+      v.x -= u.x; v.y -= u.y; v.z -= u.z; v.w -= u.w;
+      *p = v;
+    }
   }
 }
 void launch_release(const DevState& s, const uint32_t* batch_units, cudaStream_t st) {
-  k_release<<<(s.N + 255) / 256, 256, 0, st>>>(s, batch_units);
+  k_release<<<(s.N / 4 + 255) / 256, 256, 0, st>>>(s, batch_units);
 }
 
 }  // namespace pcdn

@@ -34,6 +34,7 @@ constexpr uint32_t kBlockWords = 256;        // bitmap words per match block (81
 // connection by connection, so that one connection's records form ONE contiguous run in its ring
 constexpr uint32_t kCmGroup = 8;             // messages staged together in shared memory
 constexpr uint32_t kCmMaxBytes = 4096;       // largest padded record that takes the cm path
+constexpr uint32_t kThinSeparateMin = 2048;  // direct messages in a batch from which the thin pack gets its own launch
 constexpr uint32_t kCmTileWords = 16;        // bitmap words (512 connections) per cm tile
 constexpr uint32_t kCmDenseShift = 4;        // cm needs D >= N/16 recipients
 enum : uint8_t { CLS_THIN = 0, CLS_FAT = 1, CLS_CM = 2 };
@@ -59,6 +60,7 @@ struct DevState {
   uint32_t N, W, T, nblk;
   uint32_t bucket_mask, key_stride;
   uint32_t ring_units;   // ring_bytes / 32
+  uint32_t fat_tile_bytes;  // bytes of stores per message-major pack tile
   uint32_t cm_enable;    // connection-major pack class on (default) / off (A/B profiling)
   uint32_t n_valid_topics;  // Topic::prune validity bound (0 = all)
   uint32_t max_key_len;
