@@ -124,24 +124,30 @@ def reference_arm(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    cal = run_cpu_reference(N_CONNS, PAYLOAD, 1, 1, 0, cores)
-    per_msg = max(cal["seconds"], 1e-3)
+    # default shape = config C2; `--conns 128 --msgs 1` is BASELINE config C1 (the reference's own
+    # CPU-runnable broadcast bench scaled to 128 subscribers x 1 KiB), `--conns 2 --payload 10000` its
+    # literal shape (cdn-broker/benches/broadcast.rs:58-62)
+    n_conns, payload = args.conns, args.payload
+    cores = min(cores, max(1, n_conns // 1024))  # the port starts its worker threads per step: tiny shapes run serially
+    cal = run_cpu_reference(n_conns, payload, 1, 1, 0, cores)
+    per_msg = max(cal["seconds"], 1e-6)
     budget = 150.0
-    msgs = MSGS_PER_STEP
+    msgs = args.msgs
     while msgs > 1 and per_msg * msgs * (args.steps + args.warmup) > budget:
         msgs //= 2
-    r = run_cpu_reference(N_CONNS, PAYLOAD, msgs, args.steps, args.warmup, cores)
+    r = run_cpu_reference(n_conns, payload, msgs, args.steps, args.warmup, cores)
     gbps = r["gbps"]
     line = {
         "impl": "reference", "metric": METRIC, "value": gbps, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "deliveries_per_s": r["deliveries_per_s"],
-        "config": {"workload": "C2: 2^20 subscribers, 1 topic, 1 KiB broadcast", "n_conns": N_CONNS, "payload": PAYLOAD,
+        "config": {"workload": "C2: 2^20 subscribers, 1 topic, 1 KiB broadcast" if (n_conns, payload) == (N_CONNS, PAYLOAD) else
+                   "%d subscribers, 1 topic, %d B broadcast" % (n_conns, payload), "n_conns": n_conns, "payload": payload,
                    "msgs_per_step": msgs, "note": "C++ restatement of cdn-broker's CPU path (reference is Rust, not buildable here); "
-                   "bounded sample: %d of %d messages per step" % (msgs, MSGS_PER_STEP)},
+                   "bounded sample: %d of %d messages per step" % (msgs, args.msgs)},
         "cpu_baseline": {"value": gbps, "unit": "GB/s", "cores": r["threads"], "kind": "port",
-                         "sample": "%d msgs x 2^20 subscribers per step, %d steps" % (msgs, args.steps),
+                         "sample": "%d msgs x %d subscribers per step, %d steps" % (msgs, n_conns, args.steps),
                          "stage12_s": r["stage12_s"], "stage3_s": r["stage3_s"]},
         "e2e": {"value": gbps, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -60,3 +60,17 @@ def test_c5_4k_broadcast(pcdn, dense):
         w.bcast([t], orc.broadcast_frame([t], bytes([m]) * 4096))
     n = w.check()
     assert n == 48000 if dense else n > 10000
+
+
+@pytest.mark.parametrize("n_users,k", [(128, 1024), (2, 10000)])
+def test_c1_reference_bench_shape(pcdn, n_users, k):
+    """config 1 — the reference's own CPU bench shape (cdn-broker/benches/broadcast.rs:50-75) through the
+    GPU engine: every subscriber including the sender gets the identical bytes, one message per batch"""
+    w = World(pcdn, max_conns=256, ring_bytes_per_conn=1 << 16)
+    for i in range(n_users):
+        w.add_user(i.to_bytes(8, "little"), [0])
+    raw = orc.broadcast_frame([0], bytes((i * 7 + 1) & 0xFF for i in range(k)))
+    for _ in range(3):
+        assert w.e.user_receive((0).to_bytes(8, "little"), raw) == 0
+        assert w.o.user_receive((0).to_bytes(8, "little"), raw) == 0
+        assert w.check() == n_users

@@ -307,3 +307,22 @@ def test_send_failure_removes_peer():
     o.handle_broadcast_message([0], raw)
     assert o.stream(a) == b"" and o.frames(b) == [raw]
     assert o.num_users() == 1 and o.route(b"a" * 8) == (0, -1)
+
+
+@pytest.mark.parametrize("n_users,k", [(128, 1024), (2, 10000)])
+def test_c1_reference_bench_shape(n_users, k):
+    """BASELINE config C1 — the reference's own CPU-runnable case (cdn-broker/benches/broadcast.rs:50-75:
+    users subscribed to one topic, user 0 sends a broadcast, every subscriber INCLUDING the sender
+    receives the identical bytes) at 128 x 1 KiB, and the bench's literal 2 x 10 000 B shape"""
+    o = orc.Oracle("/", 0)
+    conns = [o.add_user(i.to_bytes(8, "little"), [0]) for i in range(n_users)]   # tests/mod.rs:111-115 keys
+    raw = orc.broadcast_frame([0], bytes((i * 7 + 1) & 0xFF for i in range(k)))
+    for _ in range(3):
+        assert o.user_receive((0).to_bytes(8, "little"), raw) == 0               # user 0 is the sender
+    L = len(raw)
+    if k <= 8000:   # single segment (SURVEY Appendix B); larger payloads leave the encoder in 2 segments
+        assert L == 8 * (6 + 1 + (k + 7) // 8)
+    for c in conns:
+        assert o.frames(c) == [raw] * 3
+        assert o.stream(c) == (L.to_bytes(4, "big") + raw) * 3                   # protocols/mod.rs:366-385
+    assert o.bytes_sent() == 3 * n_users * L
