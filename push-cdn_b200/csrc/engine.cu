@@ -305,8 +305,12 @@ int flush_open(pcdn_engine* e, uint64_t* batch_id) {
 
 // R12: a table mutation must not be visible to messages already handed to the engine
 int before_state_change(pcdn_engine* e) {
-  if (e->open_slot >= 0 && !e->slots[e->open_slot].kind.empty()) return flush_open(e, nullptr);
-  return 0;
+  int rc = 0;
+  if (e->open_slot >= 0 && !e->slots[e->open_slot].kind.empty()) rc = flush_open(e, nullptr);
+  // connection-id quarantine (host_state.h): ids freed now may be named by spans of batches <= fence_now
+  e->conns->fence_now = e->next_batch_id - 1;
+  e->conns->oldest_unreleased = e->inflight.empty() ? ~0ull : e->inflight.front();
+  return rc;
 }
 
 // append one message to the open batch (flushing a full batch first)

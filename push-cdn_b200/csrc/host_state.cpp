@@ -156,16 +156,21 @@ Connections::Connections(HostTables& t, const char* identity)
 
 int Connections::alloc_conn(int kind, uint32_t* conn) {
   uint32_t c;
+  while (!quarantine_.empty() && quarantine_.front().second < oldest_unreleased) {
+    free_conns_.push_back(quarantine_.front().first);
+    quarantine_.pop_front();
+  }
   if (!free_conns_.empty()) { c = free_conns_.back(); free_conns_.pop_back(); }
   else if (next_conn_ < t_.g.max_conns) c = next_conn_++;
-  else return PCDN_ENOSPC;
+  else return quarantine_.empty() ? PCDN_ENOSPC : PCDN_EAGAIN;  // ids come back when older batches are released
   conn_kind_[c] = (uint8_t)kind;
   *conn = c;
   return 0;
 }
 void Connections::free_conn(uint32_t conn) {
   conn_kind_[conn] = CONN_FREE;
-  free_conns_.push_back(conn);
+  if (oldest_unreleased <= fence_now) quarantine_.emplace_back(conn, fence_now);  // an unreleased batch may name it
+  else free_conns_.push_back(conn);
 }
 int Connections::owner_id(const BrokerIdent& b, uint32_t* id) {
   std::string s = b.str();
@@ -247,6 +252,13 @@ int Connections::add_user(const std::string& key, const uint16_t* topics, uint32
   if (key.size() > t_.g.max_key_len) return PCDN_EKEYLEN;
   int rc = check_topics(topics, n);
   if (rc) return rc;
+  {  // refuse BEFORE kicking the same-key user when no connection id could be handed out afterwards
+    const bool quarantining = oldest_unreleased <= fence_now;
+    const bool have = !free_conns_.empty() || next_conn_ < t_.g.max_conns ||
+                      (!quarantine_.empty() && quarantine_.front().second < oldest_unreleased) ||
+                      (users_.count(key) && !quarantining);
+    if (!have) return (quarantine_.empty() && !users_.count(key)) ? PCDN_ENOSPC : PCDN_EAGAIN;
+  }
   remove_user(key);
   uint32_t c;
   if ((rc = alloc_conn(CONN_USER, &c))) return rc;

@@ -9,6 +9,7 @@
 // on the engine stream before the next batch's kernels).
 #pragma once
 #include <cstdint>
+#include <deque>
 #include <string>
 #include <unordered_map>
 #include <unordered_set>
@@ -126,6 +127,14 @@ class Connections {
   void get_full_topic_sync(std::vector<TopicSyncEntry>& out) const;                           // :194
   void get_partial_topic_sync(std::vector<TopicSyncEntry>& out);                              // :205
 
+  // -- connection-id quarantine ------------------------------------------------------------------
+  // Spans of an unreleased batch name connections by id.  An id freed by remove_user / a kick /
+  // remove_broker is therefore not handed out again until every batch launched before the removal
+  // has been released (the analogue of the reference dropping a Connection only after its queued
+  // Bytes are gone, protocols/mod.rs:287-306).  The engine sets both values before each state call.
+  uint64_t fence_now = 0;                  // id of the newest launched batch
+  uint64_t oldest_unreleased = ~0ull;      // id of the oldest batch not yet released (~0: none)
+
   // -- lookups on the mirror (tests / debug; the data path does these on the GPU) --------------
   void interested(const uint16_t* topics, uint32_t n, bool to_users_only,
                   std::vector<uint32_t>& conns) const;                                       // :94
@@ -154,6 +163,7 @@ class Connections {
   std::unordered_set<uint16_t> previous_subscribed_topics_;
   std::vector<uint8_t> conn_kind_;
   std::vector<uint32_t> free_conns_;
+  std::deque<std::pair<uint32_t, uint64_t>> quarantine_;  // (conn, fence): reusable once oldest_unreleased > fence
   uint32_t next_conn_ = 0;
 
   int alloc_conn(int kind, uint32_t* conn);

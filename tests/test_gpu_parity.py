@@ -382,3 +382,48 @@ def test_concurrent_ingest_and_egress_threads(pcdn):
     assert set(got) == set(want)
     for c in want:
         assert got[c] == want[c], c
+
+
+def test_connection_id_quarantined_until_batches_released(pcdn):
+    """spans name connections by id: an id freed by a disconnect / kick must not be handed to another
+    user while a batch launched before the removal is still unreleased (its records belong to the old
+    socket — protocols/mod.rs:287-306 soft_close drains them, nobody else may receive them)"""
+    e = pcdn.Engine(max_conns=8192, max_topics=256, max_keys=64, ring_bytes_per_conn=1 << 16, batch_slots=4)
+    A, Bk, Ck = b"A" * 8, b"B" * 8, b"C" * 8
+    a = e.add_user(A, [0])
+    raw1 = orc.broadcast_frame([0], b"for A only")
+    e.handle_broadcast_message([0], raw1)
+    b1 = e.flush()
+    e.remove_user(A)                       # A disconnects; batch b1 (unreleased) still names id `a`
+    b = e.add_user(Bk, [0])
+    assert b != a
+    a2 = e.add_user(A, [0])                # A reconnects: also a fresh id
+    assert a2 not in (a, b)
+    k = e.add_user(A, [0])                 # double connect: kicks a2, which is quarantined too
+    assert k not in (a, b, a2)
+    raw2 = orc.broadcast_frame([0], b"second")
+    e.handle_broadcast_message([0], raw2)
+    b2 = e.flush()
+    r1 = e.poll(b1)
+    assert e.collect_frames(r1) == {a: [raw1]}
+    r2 = e.poll(b2)
+    assert e.collect_frames(r2) == {b: [raw2], k: [raw2]}
+    e.release_batch(b1)
+    e.release_batch(b2)
+    c = e.add_user(Ck, [0])                # everything released: freed ids circulate again
+    assert c in (a, a2)
+    e.close()
+
+    # a full table: the kick would need a second id while the first is still named by a live batch
+    e = pcdn.Engine(max_conns=2, max_topics=256, max_keys=64, ring_bytes_per_conn=1 << 16, batch_slots=4)
+    e.add_user(A, [0]); e.add_user(Bk, [0])
+    e.handle_broadcast_message([0], raw1)
+    b1 = e.flush()
+    with pytest.raises(pcdn.PcdnError) as ei:
+        e.add_user(A, [0])
+    assert ei.value.code == -11            # PCDN_EAGAIN
+    assert e.num_users()[0] == 2           # refused before the kick: A is still connected
+    e.poll(b1); e.release_batch(b1)
+    e.add_user(A, [0])                     # now the kick + re-add goes through
+    assert e.num_users()[0] == 2
+    e.close()
