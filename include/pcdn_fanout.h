@@ -187,7 +187,11 @@ const char* pcdn_last_error(void);
 
 /* ---- state in: Connections::* (cdn-broker/src/connections/mod.rs) ------------------------- */
 /* Connections::add_user mod.rs:278-304 — kicks an existing user with the same key, registers the
- * connection, direct_map[key]=self, subscribes to `topics`.  Returns the dense connection id.   */
+ * connection, direct_map[key]=self, subscribes to `topics`.  Returns the dense connection id.
+ * Connection ids name rings and appear in spans: an id freed by a disconnect or a kick is not
+ * handed out again until every batch launched before that removal has been released, so the host
+ * can keep one id -> socket table.  PCDN_EAGAIN (before anything is changed) when the table is
+ * full and the only free ids are still held back that way; PCDN_ENOSPC when it is simply full.   */
 int pcdn_add_user(pcdn_engine* e, const uint8_t* key, uint32_t key_len, const uint16_t* topics,
                   uint32_t n_topics, pcdn_conn* out_conn);
 /* Connections::remove_user mod.rs:330-351 */
