@@ -1016,13 +1016,12 @@ __global__ void __launch_bounds__(256, 8) k_pack_thin(DevState s, BatchIn b, Wor
   pack_thin_phase(s, b, w);
 }
 
-int pack_setup() { return 0; }
-
 void launch_pack(const DevState& s, const Work& w, const BatchIn& b, uint32_t variant, int n_sms, cudaStream_t st) {
   const bool thin_separate = b.n_msgs - b.n_bcast >= kThinSeparateMin;
   // Default (variant 0): TMA bulk stores, 3 CTAs per SM — the best of the sweep in profiles/.
   // A/B switches for profiling: bit 2 = st.global.cs.v4 stores instead of bulk stores; bit 1 = no
-  // connection-major class (DevState::cm_enable, read by k_plan_a); bits 8+ = CTAs per SM.
+  // connection-major class (DevState::cm_enable, read by k_plan_a); bits 4-7 = log2 multiplier of
+  // the 128 KB message-major tile (DevState::fat_tile_bytes); bits 8+ = CTAs per SM.
   const uint32_t ctas_per_sm = (variant >> 8) ? (variant >> 8) : 3;
   const uint32_t grid = (uint32_t)n_sms * ctas_per_sm;
   if (variant & 4) k_pack<0><<<grid, 256, 0, st>>>(s, b, w, thin_separate ? 0 : 1);

@@ -154,6 +154,5 @@ void launch_offsets(const DevState& s, const Work& w, const BatchIn& b, bool has
 void launch_pack(const DevState& s, const Work& w, const BatchIn& b, uint32_t variant, int n_sms, cudaStream_t st);
 void launch_release(const DevState& s, const uint32_t* batch_units, cudaStream_t st);
 size_t sort_tiles(uint32_t n);
-int pack_setup();  // sets kernel attributes (dynamic smem); returns cudaError
 
 }  // namespace pcdn
