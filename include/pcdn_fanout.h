@@ -105,7 +105,12 @@ enum {
    * the per-message outcome comes back in pcdn_batch_result.msg_status.  Other kinds keep the host
    * path.  Deviation: a malformed / all-topics-invalid frame is reported after the batch instead of
    * synchronously, so later frames of that sender inside the same batch are still routed. */
-  PCDN_FLAG_DEVICE_PARSE = 1
+  PCDN_FLAG_DEVICE_PARSE = 1,
+  /* Engines with <= 65536 connection slots let the offsets kernel write the span table and the
+   * overflow list straight into mapped pinned host memory (no D2H copies, one event to wait for:
+   * the latency path of small brokers).  This flag forces the staged path of large engines (span
+   * table built in HBM, copied out while the pack is still running) regardless of size. */
+  PCDN_FLAG_STAGED_SPANS = 2
 };
 
 /* One routed message.  `raw` is the inbound frame body and is forwarded verbatim (R1). */

@@ -34,6 +34,7 @@ NVCC_FLAGS = [
 KIND_DIRECT, KIND_BROADCAST, KIND_SUBSCRIBE, KIND_UNSUBSCRIBE = 3, 4, 5, 6
 TO_USERS_ONLY = 1
 FLAG_DEVICE_PARSE = 1
+FLAG_STAGED_SPANS = 2   # force the large-engine span path (table in HBM + D2H) on a small engine
 RECORD_ALIGN = 32
 CONN_NONE = 0xFFFFFFFF
 

@@ -54,9 +54,22 @@ int pin_alloc(T** p, size_t n) {
   return 0;
 }
 
+// pinned + mapped: the device writes through *dev_alias (same bytes the host reads through *p)
+template <typename T>
+int pin_alloc_mapped(T** p, T** dev_alias, size_t n) {
+  *p = nullptr;
+  if (!n) n = 1;
+  cudaError_t e = cudaHostAlloc((void**)p, n * sizeof(T), cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)dev_alias, (void*)*p, 0);
+  if (e != cudaSuccess) return fail(PCDN_ENOMEM, std::string("cudaHostAlloc(mapped) ") + std::to_string(n * sizeof(T)) + " B: " + cudaGetErrorString(e));
+  return 0;
+}
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 enum SlotState { SLOT_FREE = 0, SLOT_OPEN = 1, SLOT_INFLIGHT = 2 };
+// engines up to this many connection slots publish spans directly into mapped host memory
+constexpr uint32_t kDirectPublishMaxConns = 8192;  // (16 K connections already measured slower than the staged D2H)
 
 struct Slot {
   int state = SLOT_FREE;
@@ -82,6 +95,7 @@ struct Slot {
   BatchIn in{};
   // results
   BatchStats* h_stats = nullptr;  // pinned: final counters (after the pack)
+  BatchStats* d_stats_pub = nullptr;  // direct publish: device alias of h_stats (mapped)
   BatchStats* h_early = nullptr;  // pinned: counters as of k_offsets (n_spans, n_overflow are final there)
   Span* h_spans = nullptr;        // pinned
   uint32_t* h_overflow = nullptr; // pinned
@@ -102,6 +116,7 @@ struct pcdn_engine {
   std::unique_ptr<HostTables> tables;
   std::unique_ptr<Connections> conns;
   bool has_device = false;
+  bool direct_publish = false;  // spans / overflow list written by the device into mapped host memory
   int n_sms = 148;
   // main stream: uploads, table updates, direct/match/plan/offsets, release.  pack stream: k_pack, so
   // that the control kernels of batch n+1 overlap the HBM-bound pack of batch n.  copy stream: D2H.
@@ -220,32 +235,46 @@ int launch_pipeline(pcdn_engine* e, Slot& s, uint32_t n_direct) {
   // Default: the pack runs on the main stream.  A/B switch (pack_variant bit 3): run it on the
   // high-priority pack stream so the next batch's control kernels overlap it — measured SLOWER for
   // the bulk-store pack (profiles/r1_sweep_overlap.txt), so it stays opt-in.
-  cudaStream_t st = e->stream, ps = (e->cfg.pack_variant & 8) ? e->pack_stream : e->stream, cs = e->copy_stream;
+  const bool dp = e->direct_publish;
+  cudaStream_t st = e->stream, ps = (!dp && (e->cfg.pack_variant & 8)) ? e->pack_stream : e->stream, cs = e->copy_stream;
   const bool has_direct = n_direct > 0;
   s.timed = e->timing;
   if (++s.w.stamp == 0) s.w.stamp = 1;  // validity stamp of this batch's direct buckets
+  // latency path of the smallest geometry: match + plan + offsets in one cluster launch that also
+  // zeroes / publishes the counters (kernels.cu: k_ctrl_small)
+  const bool fused = dp && e->geo.N == kSmallCtrlConns && s.in.n_msgs <= kSmallCtrlMsgs;
+  const bool zero_in_kernel = fused && !has_direct && !s.devparse;
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[0], st));
-  launch_batch_begin(e->dev, s.w, s.in, has_direct, st);
+  if (!zero_in_kernel) launch_batch_begin(e->dev, s.w, s.in, has_direct, st);
   if (s.devparse) launch_parse(e->dev, s.w, s.in, st);
   if (has_direct) launch_direct(e->dev, s.w, s.in, st);
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[1], st));
-  launch_match(e->dev, s.w, s.in, st);
-  if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[2], st));
-  launch_plan(e->dev, s.w, s.in, st);
-  launch_offsets(e->dev, s.w, s.in, has_direct, st);
-  if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[3], st));
-  CUDA_TRY(cudaEventRecord(s.ev_ctrl, st));
-  // the span table is final once k_offsets is done: its counters go home while the pack runs
-  CUDA_TRY(cudaStreamWaitEvent(cs, s.ev_ctrl, 0));
-  CUDA_TRY(cudaMemcpyAsync(s.h_early, s.w.stats, sizeof(BatchStats), cudaMemcpyDeviceToHost, cs));
-  CUDA_TRY(cudaEventRecord(s.ev_early, cs));
-  // pack on its own stream (packs of successive batches stay ordered among themselves)
-  CUDA_TRY(cudaStreamWaitEvent(ps, s.ev_ctrl, 0));
+  if (fused) {
+    launch_ctrl_small(e->dev, s.w, s.in, has_direct, zero_in_kernel, s.d_stats_pub, st);
+    if (s.timed) { CUDA_TRY(cudaEventRecord(s.ev[2], st)); CUDA_TRY(cudaEventRecord(s.ev[3], st)); }
+  } else {
+    launch_match(e->dev, s.w, s.in, st);
+    if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[2], st));
+    launch_plan(e->dev, s.w, s.in, st);
+    launch_offsets(e->dev, s.w, s.in, has_direct, st);
+    if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[3], st));
+  }
+  if (!dp) {
+    CUDA_TRY(cudaEventRecord(s.ev_ctrl, st));
+    // the span table is final once k_offsets is done: its counters go home while the pack runs
+    CUDA_TRY(cudaStreamWaitEvent(cs, s.ev_ctrl, 0));
+    CUDA_TRY(cudaMemcpyAsync(s.h_early, s.w.stats, sizeof(BatchStats), cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaEventRecord(s.ev_early, cs));
+    // pack on its own stream (packs of successive batches stay ordered among themselves)
+    if (ps != st) CUDA_TRY(cudaStreamWaitEvent(ps, s.ev_ctrl, 0));
+  }
+  // (direct publish: k_offsets wrote spans / overflow into mapped host memory; everything stays
+  //  on one stream and the host waits for ev_done only)
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[4], ps));
   launch_pack(e->dev, s.w, s.in, e->cfg.pack_variant, e->n_sms, ps);
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[5], ps));
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(s.h_stats, s.w.stats, sizeof(BatchStats), cudaMemcpyDeviceToHost, ps));
+  if (!fused) CUDA_TRY(cudaMemcpyAsync(s.h_stats, s.w.stats, sizeof(BatchStats), cudaMemcpyDeviceToHost, ps));
   CUDA_TRY(cudaEventRecord(s.ev_done, ps));
   s.state = SLOT_INFLIGHT;
   s.t_launch = std::chrono::steady_clock::now();
@@ -272,27 +301,37 @@ int flush_open(pcdn_engine* e, uint64_t* batch_id) {
   size_t o_bidx = o_alen + (size_t)n * 4, o_top = align_up(o_bidx + s.bcast_index.size() * 4, 16);
   size_t total = align_up(o_top + s.topics.size() * 2, 16);
   if (total > e->desc_cap) return fail(PCDN_ENOSPC, "descriptor block overflow");
-  std::memcpy(s.h_desc + o_kind, s.kind.data(), n);
-  std::memcpy(s.h_desc + o_flags, s.flags.data(), n);
-  std::memcpy(s.h_desc + o_slot, s.slot_off16.data(), (size_t)n * 4);
-  std::memcpy(s.h_desc + o_len, s.raw_len.data(), (size_t)n * 4);
-  std::memcpy(s.h_desc + o_aoff, s.aux_off.data(), (size_t)n * 4);
-  std::memcpy(s.h_desc + o_alen, s.aux_len.data(), (size_t)n * 4);
-  if (!s.bcast_index.empty()) std::memcpy(s.h_desc + o_bidx, s.bcast_index.data(), s.bcast_index.size() * 4);
-  if (!s.topics.empty()) std::memcpy(s.h_desc + o_top, s.topics.data(), s.topics.size() * 2);
-  CUDA_TRY(cudaMemcpyAsync(s.d_arena, s.h_arena, align_up(s.arena_used, 16), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(s.d_desc, s.h_desc, total, cudaMemcpyHostToDevice, st));
+  // Small batches ride in ONE host→device copy: the descriptor block is appended to the frame arena
+  // when it fits there (one DMA + one API call less on the latency path); otherwise two copies.
+  const size_t doff = align_up(s.arena_used, 256);
+  const bool one_copy = doff + total <= (size_t)e->cfg.max_batch_bytes + 64 && doff + total <= (64u << 10);
+  uint8_t* hd = one_copy ? s.h_arena + doff : s.h_desc;
+  uint8_t* dd = one_copy ? s.d_arena + doff : s.d_desc;
+  std::memcpy(hd + o_kind, s.kind.data(), n);
+  std::memcpy(hd + o_flags, s.flags.data(), n);
+  std::memcpy(hd + o_slot, s.slot_off16.data(), (size_t)n * 4);
+  std::memcpy(hd + o_len, s.raw_len.data(), (size_t)n * 4);
+  std::memcpy(hd + o_aoff, s.aux_off.data(), (size_t)n * 4);
+  std::memcpy(hd + o_alen, s.aux_len.data(), (size_t)n * 4);
+  if (!s.bcast_index.empty()) std::memcpy(hd + o_bidx, s.bcast_index.data(), s.bcast_index.size() * 4);
+  if (!s.topics.empty()) std::memcpy(hd + o_top, s.topics.data(), s.topics.size() * 2);
+  if (one_copy) {
+    CUDA_TRY(cudaMemcpyAsync(s.d_arena, s.h_arena, doff + total, cudaMemcpyHostToDevice, st));
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(s.d_arena, s.h_arena, align_up(s.arena_used, 16), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s.d_desc, s.h_desc, total, cudaMemcpyHostToDevice, st));
+  }
   s.in.n_msgs = n;
   s.in.n_bcast = (uint32_t)s.bcast_index.size();
   s.in.arena = s.d_arena;
-  s.in.kind = s.d_desc + o_kind;
-  s.in.flags = s.d_desc + o_flags;
-  s.in.slot_off16 = (const uint32_t*)(s.d_desc + o_slot);
-  s.in.raw_len = (const uint32_t*)(s.d_desc + o_len);
-  s.in.aux_off = (const uint32_t*)(s.d_desc + o_aoff);
-  s.in.aux_len = (const uint32_t*)(s.d_desc + o_alen);
-  s.in.bcast_index = (const uint32_t*)(s.d_desc + o_bidx);
-  s.in.topics = (const uint16_t*)(s.d_desc + o_top);
+  s.in.kind = dd + o_kind;
+  s.in.flags = dd + o_flags;
+  s.in.slot_off16 = (const uint32_t*)(dd + o_slot);
+  s.in.raw_len = (const uint32_t*)(dd + o_len);
+  s.in.aux_off = (const uint32_t*)(dd + o_aoff);
+  s.in.aux_len = (const uint32_t*)(dd + o_alen);
+  s.in.bcast_index = (const uint32_t*)(dd + o_bidx);
+  s.in.topics = (const uint16_t*)(dd + o_top);
   s.device_input = false;
   rc = launch_pipeline(e, s, s.n_direct);
   if (rc) return rc;
@@ -451,6 +490,7 @@ int init_device(pcdn_engine* e) {
     CUDA_TRY(cudaStreamCreateWithPriority(&e->pack_stream, cudaStreamNonBlocking, hi));
   }
   e->has_device = true;
+  e->direct_publish = g.N <= kDirectPublishMaxConns && !(c.flags & PCDN_FLAG_STAGED_SPANS);
 
   DevState& d = e->dev;
   d.N = g.N; d.W = g.W; d.T = g.T; d.nblk = g.W / kBlockWords;
@@ -517,15 +557,29 @@ int init_device(pcdn_engine* e) {
     CUDA_TRY(cudaMemsetAsync(w.dstamp, 0, ((size_t)g.N + 1) * 4, e->stream));
     w.stamp = 0;
     DEV_ALLOC(w.batch_units, g.N);
-    DEV_ALLOC(w.spans, (size_t)2 * g.N);
-    DEV_ALLOC(w.overflow, g.N);
+    if (e->direct_publish) {
+      int _rc = pin_alloc_mapped(&s.h_spans, &w.spans, (size_t)2 * g.N);
+      if (_rc) return _rc;
+      e->pin_allocs.push_back((void*)s.h_spans);
+      if ((_rc = pin_alloc_mapped(&s.h_overflow, &w.overflow, (size_t)g.N))) return _rc;
+      e->pin_allocs.push_back((void*)s.h_overflow);
+    } else {
+      DEV_ALLOC(w.spans, (size_t)2 * g.N);
+      DEV_ALLOC(w.overflow, g.N);
+      PIN_ALLOC(s.h_spans, (size_t)2 * g.max_conns);
+      PIN_ALLOC(s.h_overflow, g.max_conns);
+    }
     DEV_ALLOC(w.msg_status, M);
     PIN_ALLOC(s.h_msg_status, M);
     DEV_ALLOC(w.stats, 1);
-    PIN_ALLOC(s.h_stats, 1);
+    if (e->direct_publish) {
+      int _rc = pin_alloc_mapped(&s.h_stats, &s.d_stats_pub, 1);
+      if (_rc) return _rc;
+      e->pin_allocs.push_back((void*)s.h_stats);
+    } else {
+      PIN_ALLOC(s.h_stats, 1);
+    }
     PIN_ALLOC(s.h_early, 1);
-    PIN_ALLOC(s.h_spans, (size_t)2 * g.max_conns);
-    PIN_ALLOC(s.h_overflow, g.max_conns);
     CUDA_TRY(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&s.ev_ctrl, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&s.ev_early, cudaEventDisableTiming));
@@ -1121,8 +1175,9 @@ int pcdn_poll(pcdn_engine* e, uint64_t batch_id, pcdn_batch_result* out, int blo
   bool devparse = false;
   if (wait) {
     // 1. counters as of k_offsets → exact size of the span table; its D2H overlaps the pack
-    CUDA_TRY(cudaEventSynchronize(ev_early));
-    {
+    //    (direct publish: the table is already in host memory when ev_done fires)
+    if (!e->direct_publish) {
+      CUDA_TRY(cudaEventSynchronize(ev_early));
       std::lock_guard<std::mutex> g(e->mu);
       Slot* s = find_slot(e, batch_id);
       if (!s) return fail(PCDN_ENOENT, "batch released while it was being polled");
@@ -1131,6 +1186,11 @@ int pcdn_poll(pcdn_engine* e, uint64_t batch_id, pcdn_batch_result* out, int blo
       devparse = s->devparse;
       if (nsp) CUDA_TRY(cudaMemcpyAsync(s->h_spans, s->w.spans, (size_t)nsp * sizeof(Span), cudaMemcpyDeviceToHost, e->copy_stream));
       if (nov) CUDA_TRY(cudaMemcpyAsync(s->h_overflow, s->w.overflow, (size_t)nov * 4, cudaMemcpyDeviceToHost, e->copy_stream));
+    } else {
+      std::lock_guard<std::mutex> g(e->mu);
+      Slot* s = find_slot(e, batch_id);
+      if (!s) return fail(PCDN_ENOENT, "batch released while it was being polled");
+      devparse = s->devparse;
     }
     // 2. the pack itself (ring bytes are valid after this)
     CUDA_TRY(cudaEventSynchronize(ev_done));

@@ -20,23 +20,28 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
   return v;
 }
 
-// exclusive scan over a 256-thread block; *total = block sum.  `sm` needs 9 words.
-__device__ __forceinline__ uint32_t block256_excl_scan(uint32_t v, uint32_t* total, uint32_t* sm) {
+// exclusive scan over a CTA of NW warps; *total = CTA sum.  `sm` needs NW+1 words (NW <= 32).
+template <int NW>
+__device__ __forceinline__ uint32_t cta_excl_scan(uint32_t v, uint32_t* total, uint32_t* sm) {
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
   uint32_t incl = warp_incl_scan(v);
   if (lane == 31) sm[warp] = incl;
   __syncthreads();
   if (warp == 0) {
-    uint32_t x = lane < 8 ? sm[lane] : 0;
+    uint32_t x = lane < NW ? sm[lane] : 0;
     uint32_t xi = warp_incl_scan(x);
-    if (lane < 8) sm[lane] = xi - x;
-    if (lane == 7) sm[8] = xi;
+    if (lane < NW) sm[lane] = xi - x;
+    if (lane == NW - 1) sm[NW] = xi;
   }
   __syncthreads();
   uint32_t r = incl - v + sm[warp];
-  *total = sm[8];
+  *total = sm[NW];
   __syncthreads();
   return r;
+}
+// 256-thread block; `sm` needs 9 words
+__device__ __forceinline__ uint32_t block256_excl_scan(uint32_t v, uint32_t* total, uint32_t* sm) {
+  return cta_excl_scan<8>(v, total, sm);
 }
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
@@ -429,11 +434,8 @@ void launch_direct(const DevState& s, const Work& w, const BatchIn& b, cudaStrea
 
 // =============================================================================== K1a topic match
 // grid (W/256, n_bcast): thread = one 32-connection word of one broadcast message.
-__global__ void __launch_bounds__(256) k_match(DevState s, BatchIn b, Work w) {
-  __shared__ uint32_t sm[9];
-  const uint32_t j = blockIdx.y;
-  const uint32_t wd = blockIdx.x * kBlockWords + threadIdx.x;  // W is a multiple of 256
-  const uint32_t m = b.bcast_index[j];
+// match word `wd` (32 connections) of message m: OR of its topics' bitmap rows (a2)
+__device__ __forceinline__ uint32_t match_word(const DevState& s, const BatchIn& b, uint32_t m, uint32_t wd) {
   const uint32_t toff = b.aux_off[m], tn = b.aux_len[m];
   const uint32_t fl = b.flags[m];
   uint32_t word = 0;
@@ -451,6 +453,13 @@ __global__ void __launch_bounds__(256) k_match(DevState s, BatchIn b, Work w) {
     }
   }
   if (fl & MSGF_USERS_ONLY) word &= ~s.brk[wd];  // to_users_only (connections/mod.rs:111)
+  return word;
+}
+__global__ void __launch_bounds__(256) k_match(DevState s, BatchIn b, Work w) {
+  __shared__ uint32_t sm[9];
+  const uint32_t j = blockIdx.y;
+  const uint32_t wd = blockIdx.x * kBlockWords + threadIdx.x;  // W is a multiple of 256
+  const uint32_t word = match_word(s, b, b.bcast_index[j], wd);
   w.B[(size_t)j * s.W + wd] = word;
   uint32_t tot, ex = block256_excl_scan(__popc(word), &tot, sm);
   w.wpre[(size_t)j * s.W + wd] = (uint16_t)ex;
@@ -487,11 +496,9 @@ __device__ __forceinline__ uint32_t tile_recipients(uint32_t frame_bytes, uint32
   return max(32u, min(kTileRecipients, tile_bytes / chunk));
 }
 
-__global__ void __launch_bounds__(256) k_plan_a(DevState s, BatchIn b, Work w, uint32_t nblk) {
-  __shared__ uint32_t sm[9];
-  const uint32_t m = blockIdx.x * 256 + threadIdx.x;
-  const bool valid = m < b.n_msgs;
-  const uint32_t d = valid ? w.D[m] : 0;
+// pack class of a message with d recipients, and its number of message-major tiles
+__device__ __forceinline__ void plan_classify(const DevState& s, const BatchIn& b, uint32_t m, uint32_t d, uint32_t* cls_out,
+                                              uint32_t* tiles_out) {
   uint32_t cls = CLS_THIN, tiles = 0;
   if (d >= kFatMin) {
     const uint32_t len = b.raw_len[m];
@@ -505,6 +512,16 @@ __global__ void __launch_bounds__(256) k_plan_a(DevState s, BatchIn b, Work w, u
       tiles = nch * ((d + tr - 1) / tr);
     }
   }
+  *cls_out = cls; *tiles_out = tiles;
+}
+
+__global__ void __launch_bounds__(256) k_plan_a(DevState s, BatchIn b, Work w, uint32_t nblk) {
+  __shared__ uint32_t sm[9];
+  const uint32_t m = blockIdx.x * 256 + threadIdx.x;
+  const bool valid = m < b.n_msgs;
+  const uint32_t d = valid ? w.D[m] : 0;
+  uint32_t cls, tiles;
+  plan_classify(s, b, m, d, &cls, &tiles);
   uint32_t tot;
   uint32_t e0 = block256_excl_scan(cls != CLS_THIN ? d : 0, &tot, sm);
   if (threadIdx.x == 0) w.scan_tmp[blockIdx.x] = tot;
@@ -600,13 +617,16 @@ __device__ __forceinline__ uint32_t alloc_record(ConnCursor& k, uint32_t u, uint
 // hits from the connection's sorted bucket), so a connection's records are laid out in batch order
 // (R9) with no atomics, and writes each (conn, offset) into the per-message scatter list at its
 // deterministic rank (block base + word prefix + lane rank).
-template <bool HAS_DIRECT>
-__global__ void __launch_bounds__(256) k_offsets(DevState s, BatchIn b, Work w, uint32_t max_conns) {
-  __shared__ uint32_t sm[9];
-  __shared__ unsigned long long red[2][8];
+// (body shared by k_offsets — 256-thread CTAs, any N — and the fused small-engine control kernel —
+//  eight 1024-thread CTAs of one cluster, N = 8192; NT = threads per CTA, c = this thread's connection)
+template <bool HAS_DIRECT, int NT>
+__device__ __forceinline__ void offsets_body(const DevState& s, const BatchIn& b, const Work& w, uint32_t max_conns,
+                                             uint32_t c) {
+  constexpr int NW = NT / 32;
+  __shared__ uint32_t sm[NW + 1];
+  __shared__ unsigned long long red[2][NW];
   __shared__ uint32_t span_base;
-  if (w.stats->status) return;  // batch rejected (E2BIG): leave all cursors untouched
-  const uint32_t c = blockIdx.x * 256 + threadIdx.x;  // N is a multiple of 8192
+  if (w.stats->status) return;  // batch rejected (E2BIG): leave all cursors untouched (uniform over the grid)
   const uint32_t wd = c >> 5, lane = c & 31, lt = (1u << lane) - 1u;
   const uint32_t R = s.ring_units;
   ConnCursor k;
@@ -671,7 +691,7 @@ __global__ void __launch_bounds__(256) k_offsets(DevState s, BatchIn b, Work w, 
 
   // spans: one per contiguous run (two when the ring wrapped inside the batch)
   const uint32_t nsp = (k.s1_rec ? 1u : 0u) + (k.s2_rec ? 1u : 0u);
-  uint32_t tot, ex = block256_excl_scan(nsp, &tot, sm);
+  uint32_t tot, ex = cta_excl_scan<NW>(nsp, &tot, sm);
   if (threadIdx.x == 0) span_base = tot ? atomicAdd(&w.stats->n_spans, tot) : 0;
   // block reduction of deliveries / bytes
   // (redux.sync on 32-bit halves: a warp's record count fits 32 bits, its byte count may not)
@@ -682,7 +702,7 @@ __global__ void __launch_bounds__(256) k_offsets(DevState s, BatchIn b, Work w, 
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned long long a = 0, bb = 0;
-    for (int i = 0; i < 8; i++) { a += red[0][i]; bb += red[1][i]; }
+    for (int i = 0; i < NW; i++) { a += red[0][i]; bb += red[1][i]; }
     if (a) { atomicAdd(&w.stats->n_deliveries, a); atomicAdd(&w.stats->bytes_out, bb); }
   }
   if (nsp) {
@@ -695,9 +715,101 @@ __global__ void __launch_bounds__(256) k_offsets(DevState s, BatchIn b, Work w, 
     if (i < max_conns) w.overflow[i] = c;
   }
 }
+template <bool HAS_DIRECT>
+__global__ void __launch_bounds__(256) k_offsets(DevState s, BatchIn b, Work w, uint32_t max_conns) {
+  offsets_body<HAS_DIRECT, 256>(s, b, w, max_conns, blockIdx.x * 256 + threadIdx.x);  // N is a multiple of 8192
+}
 void launch_offsets(const DevState& s, const Work& w, const BatchIn& b, bool has_direct, cudaStream_t st) {
   if (has_direct) k_offsets<true><<<s.N / 256, 256, 0, st>>>(s, b, w, s.N);
   else k_offsets<false><<<s.N / 256, 256, 0, st>>>(s, b, w, s.N);
+}
+
+// =============================================================================== fused control (small engines)
+// The smallest geometry (N = 8192 connections, W = 256 words, one 256-word block per message) with a
+// batch of at most kSmallCtrlMsgs messages is the latency regime of a real broker (a few hundred
+// consensus nodes, one vote or proposal at a time).  There the regular pipeline is a chain of five
+// tiny dependent launches; here match, plan and offsets run in ONE launch on one cluster of eight
+// 1024-thread CTAs — a thread per connection — with cluster barriers where the pipeline has kernel
+// boundaries.  It writes exactly the arrays k_match / k_match_base / k_plan_a / k_offsets write (the
+// pack kernel and the host cannot tell the difference), zeroes the batch counters itself when no
+// earlier kernel of the batch needs them, and publishes the final counters into mapped host memory.
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <bool HAS_DIRECT>
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(1024, 1)
+k_ctrl_small(DevState s, BatchIn b, Work w, int zero_stats, BatchStats* publish) {
+  __shared__ uint32_t sm[33];
+  __shared__ uint32_t gbase[5];
+  const uint32_t tid = threadIdx.x, rank = blockIdx.x;  // grid = one cluster
+  if (zero_stats && rank == 0 && tid < sizeof(BatchStats) / 4) reinterpret_cast<uint32_t*>(w.stats)[tid] = 0;
+
+  // ---- match (= k_match + k_match_base with nblk == 1): four messages per pass, 256 words each
+  {
+    const uint32_t q = tid >> 8, wd = tid & 255u;
+    for (uint32_t j0 = rank * 4; j0 < b.n_bcast; j0 += 32) {  // trip count is uniform inside a CTA
+      const uint32_t j = j0 + q;
+      const bool live = j < b.n_bcast;
+      const uint32_t m = live ? b.bcast_index[j] : 0;
+      const uint32_t word = live ? match_word(s, b, m, wd) : 0;
+      uint32_t tot, ex = cta_excl_scan<32>(__popc(word), &tot, sm);
+      if (wd == 0) gbase[q] = ex;
+      if (tid == 0) gbase[4] = tot;
+      __syncthreads();
+      if (live) {
+        w.B[(size_t)j * s.W + wd] = word;
+        w.wpre[(size_t)j * s.W + wd] = (uint16_t)(ex - gbase[q]);
+        if (wd == 0) {
+          const uint32_t d = gbase[q + 1] - gbase[q];
+          w.cnt[j] = d; w.base[j] = 0;  // nblk == 1
+          w.D[m] = d; w.jidx[m] = j;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  cluster_sync_all();
+
+  // ---- plan (= the single-block case of k_plan_a) on CTA 0
+  if (rank == 0) {
+    const uint32_t m = tid;
+    const bool valid = m < b.n_msgs;
+    const uint32_t d = valid ? w.D[m] : 0;
+    uint32_t cls, tiles;
+    plan_classify(s, b, m, d, &cls, &tiles);
+    uint32_t t0, t1, t2, t3;
+    const uint32_t e0 = cta_excl_scan<32>(cls != CLS_THIN ? d : 0, &t0, sm);
+    const uint32_t e1 = cta_excl_scan<32>(cls == CLS_THIN ? d : 0, &t1, sm);
+    const uint32_t e2 = cta_excl_scan<32>(tiles, &t2, sm);
+    const uint32_t e3 = cta_excl_scan<32>(cls == CLS_CM ? 1u : 0u, &t3, sm);
+    if (valid) {
+      w.eb_fat[m] = e0; w.eb_thin[m] = e1; w.tbase[m] = e2; w.cm_rank[m] = e3; w.cls[m] = (uint8_t)cls;
+      if (cls == CLS_CM) w.cm_list[e3] = m;
+    }
+    if (tid == 0) {
+      w.stats->n_fat_entries = t0; w.stats->n_thin_entries = t1; w.stats->n_fat_tiles = t2; w.stats->tile_cursor = 0;
+      w.stats->n_cm = t3; w.stats->cm_cursor = 0;
+      if (t0 > w.cap_fat || t1 > w.cap_thin) w.stats->status = 1;  // PCDN_E2BIG
+      const uint32_t n = b.n_msgs;
+      w.eb_fat[n] = t0; w.eb_thin[n] = t1; w.tbase[n] = t2; w.cm_rank[n] = t3;
+    }
+  }
+  cluster_sync_all();
+
+  // ---- offsets: thread = connection
+  offsets_body<HAS_DIRECT, 1024>(s, b, w, s.N, rank * 1024 + tid);
+
+  // ---- final counters straight into the host's (mapped, pinned) result block
+  if (publish) {
+    cluster_sync_all();
+    if (rank == 0 && tid < sizeof(BatchStats) / 4)
+      reinterpret_cast<uint32_t*>(publish)[tid] = __ldcg(reinterpret_cast<const uint32_t*>(w.stats) + tid);
+  }
+}
+void launch_ctrl_small(const DevState& s, const Work& w, const BatchIn& b, bool has_direct, bool zero_stats,
+                       BatchStats* publish, cudaStream_t st) {
+  if (has_direct) k_ctrl_small<true><<<8, 1024, 0, st>>>(s, b, w, zero_stats ? 1 : 0, publish);
+  else k_ctrl_small<false><<<8, 1024, 0, st>>>(s, b, w, zero_stats ? 1 : 0, publish);
 }
 
 // =============================================================================== K2a pack (fat)

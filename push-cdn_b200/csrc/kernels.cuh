@@ -34,6 +34,8 @@ constexpr uint32_t kBlockWords = 256;        // bitmap words per match block (81
 // connection by connection, so that one connection's records form ONE contiguous run in its ring
 constexpr uint32_t kCmGroup = 8;             // messages staged together in shared memory
 constexpr uint32_t kCmMaxBytes = 4096;       // largest padded record that takes the cm path
+constexpr uint32_t kSmallCtrlConns = 8192;    // geometry served by the fused control kernel (one thread per connection)
+constexpr uint32_t kSmallCtrlMsgs = 64;       // largest batch it takes
 constexpr uint32_t kThinSeparateMin = 2048;  // direct messages in a batch from which the thin pack gets its own launch
 constexpr uint32_t kCmTileWords = 16;        // bitmap words (512 connections) per cm tile
 constexpr uint32_t kCmDenseShift = 4;        // cm needs D >= N/16 recipients
@@ -151,6 +153,9 @@ void launch_direct(const DevState& s, const Work& w, const BatchIn& b, cudaStrea
 void launch_match(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st);
 void launch_plan(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st);
 void launch_offsets(const DevState& s, const Work& w, const BatchIn& b, bool has_direct, cudaStream_t st);
+// fused match + plan + offsets for N == kSmallCtrlConns and n_msgs <= kSmallCtrlMsgs (one cluster launch)
+void launch_ctrl_small(const DevState& s, const Work& w, const BatchIn& b, bool has_direct, bool zero_stats,
+                       BatchStats* publish, cudaStream_t st);
 void launch_pack(const DevState& s, const Work& w, const BatchIn& b, uint32_t variant, int n_sms, cudaStream_t st);
 void launch_release(const DevState& s, const uint32_t* batch_units, cudaStream_t st);
 size_t sort_tiles(uint32_t n);

@@ -27,10 +27,12 @@ def _mutate(rng, raw):
     return bytes(raw)
 
 
-@pytest.mark.parametrize("seed", [0, 1])
+@pytest.mark.parametrize("seed", [0, 1, 2])
 def test_frames_through_receive_loops(pcdn, seed):
     rng = random.Random(seed)
-    w = World(pcdn, n_valid_topics=12, flags=pcdn.FLAG_DEVICE_PARSE, ring_bytes_per_conn=1 << 20)
+    # seed 2 also forces the large-engine span path (span table staged in HBM, copied out during the pack)
+    w = World(pcdn, n_valid_topics=12, flags=pcdn.FLAG_DEVICE_PARSE | (pcdn.FLAG_STAGED_SPANS if seed == 2 else 0),
+              ring_bytes_per_conn=1 << 20)
     keys = []
     for i in range(1200):
         k = rng.getrandbits(64).to_bytes(8, "little") * rng.choice([1, 4, 16])
@@ -78,8 +80,9 @@ def test_frames_through_receive_loops(pcdn, seed):
     assert total_err > 5
 
 
-def test_msg_status_codes(pcdn):
-    w = World(pcdn, n_valid_topics=2, flags=pcdn.FLAG_DEVICE_PARSE)
+@pytest.mark.parametrize("staged", [False, True])
+def test_msg_status_codes(pcdn, staged):
+    w = World(pcdn, n_valid_topics=2, flags=pcdn.FLAG_DEVICE_PARSE | (pcdn.FLAG_STAGED_SPANS if staged else 0))
     a = w.add_user(b"a" * 8, [0, 1])
     good = orc.broadcast_frame([0], b"ok")
     bad_topics = orc.broadcast_frame([9, 9, 7], b"nope")

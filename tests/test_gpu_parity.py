@@ -113,13 +113,18 @@ def payload(rng, n):
     return bytes(rng.getrandbits(8) for _ in range(min(n, 64))) * (n // 64 + 1)
 
 
-@pytest.mark.parametrize("variant", [0, 4, 2])
+@pytest.mark.parametrize("variant", [0, 4, 2, "staged"])
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_random_mixed_batches(pcdn, seed, variant):
     """users + peer brokers, multi-topic broadcasts (fat and thin recipient sets), directs to local,
-    remote and unknown keys, frame sizes from 0 B to 3 staging chunks, several batches"""
+    remote and unknown keys, frame sizes from 0 B to 3 staging chunks, several batches.
+    Small engines publish spans straight into mapped host memory; "staged" forces the span path of
+    large engines (table in HBM, copied out while the pack runs) on the same workload."""
     rng = random.Random(seed)
-    w = World(pcdn, pack_variant=variant, ring_bytes_per_conn=1 << 20)
+    if variant == "staged":
+        w = World(pcdn, flags=pcdn.FLAG_STAGED_SPANS, ring_bytes_per_conn=1 << 20)
+    else:
+        w = World(pcdn, pack_variant=variant, ring_bytes_per_conn=1 << 20)
     keys = []
     for i in range(1500):
         k = rng.getrandbits(64).to_bytes(8, "little") * rng.choice([1, 4, 16])
@@ -213,10 +218,11 @@ def test_ring_wrap_and_release(pcdn):
         w.check()
 
 
-def test_ring_overflow_reports_connection(pcdn):
+@pytest.mark.parametrize("staged", [False, True])
+def test_ring_overflow_reports_connection(pcdn, staged):
     """a slow consumer (nothing released) overflows its ring: deliveries stop at the overflow point,
     the connection is reported so the host can remove it (the R13 analogue); others are unaffected"""
-    w = World(pcdn, ring_bytes_per_conn=4096, max_conns=64)
+    w = World(pcdn, ring_bytes_per_conn=4096, max_conns=64, flags=pcdn.FLAG_STAGED_SPANS if staged else 0)
     a = w.add_user(b"slow" * 2, [0])
     b = w.add_user(b"fast" * 2, [1])
     frames = [orc.broadcast_frame([0], bytes([i]) * 900) for i in range(8)]
