@@ -243,11 +243,11 @@ int launch_pipeline(pcdn_engine* e, Slot& s, uint32_t n_direct) {
   // latency path of the smallest geometry: match + plan + offsets in one cluster launch that also
   // zeroes / publishes the counters (kernels.cu: k_ctrl_small)
   const bool fused = dp && e->geo.N == kSmallCtrlConns && s.in.n_msgs <= kSmallCtrlMsgs;
-  const bool zero_in_kernel = fused && !has_direct && !s.devparse;
+  const bool zero_in_kernel = fused && !s.devparse;  // (k_parse counts into the batch counters before the fused kernel)
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[0], st));
   if (!zero_in_kernel) launch_batch_begin(e->dev, s.w, s.in, has_direct, st);
   if (s.devparse) launch_parse(e->dev, s.w, s.in, st);
-  if (has_direct) launch_direct(e->dev, s.w, s.in, st);
+  if (has_direct && !fused) launch_direct(e->dev, s.w, s.in, st);  // fused: lookup + sort inside k_ctrl_small
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[1], st));
   if (fused) {
     launch_ctrl_small(e->dev, s.w, s.in, has_direct, zero_in_kernel, s.d_stats_pub, st);

@@ -225,9 +225,10 @@ __device__ __forceinline__ uint32_t key_word32(const uint8_t* kp, uint32_t j, ui
 // Direct messages: hash the recipient key (64-bit words strided over the 8 lanes, xor-shuffle
 // reduced inside the group), probe both 4-slot buckets with the 8 lanes, verify the full key
 // against the key arena, resolve the route (handler.rs:204-236).  Also seeds the (conn, msg) sort.
-__global__ void __launch_bounds__(256) k_direct_lookup(DevState s, BatchIn b, Work w) {
+// (gtid = global thread index: 8 consecutive threads serve message gtid / 8)
+__device__ __forceinline__ void direct_lookup_body(const DevState& s, const BatchIn& b, const Work& w, uint32_t gtid) {
   const uint32_t lane = lane_id(), grp = lane >> 3, gl = lane & 7;
-  const uint32_t m = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4 + grp;
+  const uint32_t m = (gtid >> 5) * 4 + grp;
   const bool valid = m < b.n_msgs;
   const bool is_direct = valid && b.kind[m] == 3;
   const uint32_t gshift = grp * 8;
@@ -287,6 +288,9 @@ __global__ void __launch_bounds__(256) k_direct_lookup(DevState s, BatchIn b, Wo
     w.skey[0][m] = (is_direct && target != kConnNone) ? target : s.N;
     w.sval[0][m] = m;
   }
+}
+__global__ void __launch_bounds__(256) k_direct_lookup(DevState s, BatchIn b, Work w) {
+  direct_lookup_body(s, b, w, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // ---- stable LSD radix sort of (target conn, msg index), 8-bit digits ---------------------------
@@ -743,6 +747,32 @@ k_ctrl_small(DevState s, BatchIn b, Work w, int zero_stats, BatchStats* publish)
   __shared__ uint32_t gbase[5];
   const uint32_t tid = threadIdx.x, rank = blockIdx.x;  // grid = one cluster
   if (zero_stats && rank == 0 && tid < sizeof(BatchStats) / 4) reinterpret_cast<uint32_t*>(w.stats)[tid] = 0;
+
+  // ---- direct messages (= k_direct_lookup + k_sort_small + k_bucket_bounds) on CTA 0; at most
+  //      kSmallCtrlMsgs of them, so the stable (connection, message) sort is a rank count
+  if (HAS_DIRECT && rank == 0) {
+    __shared__ uint32_t skey_s[kSmallCtrlMsgs], sorted_s[kSmallCtrlMsgs];
+    __syncthreads();  // counters are zero before the lookup counts dropped messages
+    direct_lookup_body(s, b, w, tid);  // 1024 threads = 128 messages
+    __syncthreads();
+    const uint32_t n = b.n_msgs;
+    if (tid < n) skey_s[tid] = w.skey[0][tid];
+    __syncthreads();
+    if (tid < n) {
+      const uint32_t key = skey_s[tid];
+      uint32_t r = 0;
+      for (uint32_t o = 0; o < n; o++) r += (skey_s[o] < key || (skey_s[o] == key && o < tid)) ? 1u : 0u;
+      sorted_s[r] = key;
+      w.skey[0][r] = key;
+      w.sval[0][r] = tid;
+    }
+    __syncthreads();
+    if (tid < n) {
+      const uint32_t key = sorted_s[tid];
+      if (tid == 0 || sorted_s[tid - 1] != key) { w.dstart[key] = tid; w.dstamp[key] = w.stamp; }
+      if (tid + 1 == n || sorted_s[tid + 1] != key) w.dend[key] = tid + 1;
+    }
+  }
 
   // ---- match (= k_match + k_match_base with nblk == 1): four messages per pass, 256 words each
   {
