@@ -12,7 +12,10 @@
 //   K2  k_pack          persistent CTAs, three phases: connection-major (groups of <= 8 small frames
 //                       staged by TMA, one TMA bulk store per contiguous run of a connection's
 //                       records), message-major (16 KiB chunks staged once per CTA, replicated to
-//                       ~2 MB worth of recipients per tile), thin (warp per delivery)
+//                       ~128 KB worth of recipients per tile), thin (warp per delivery; its own
+//                       full-occupancy launch k_pack_thin for batches of >= 2048 direct messages)
+//   K1s k_ctrl_small    latency path (N = 8192 connection slots, <= 64 messages): K3 + sort + K1a +
+//                       K1p + K1b in ONE cluster launch, counters/spans published to mapped host memory
 //   K4  k_apply_*       scatter of changed table words/slots (subscribe, add/remove, direct map)
 //       k_release       ring space of a consumed batch goes back to the connections
 #pragma once
