@@ -753,7 +753,7 @@ k_ctrl_small(DevState s, BatchIn b, Work w, int zero_stats, BatchStats* publish)
   if (HAS_DIRECT && rank == 0) {
     __shared__ uint32_t skey_s[kSmallCtrlMsgs], sorted_s[kSmallCtrlMsgs];
     __syncthreads();  // counters are zero before the lookup counts dropped messages
-    direct_lookup_body(s, b, w, tid);  // 1024 threads = 128 messages
+    for (uint32_t g0 = 0; g0 < b.n_msgs * 8; g0 += 1024) direct_lookup_body(s, b, w, g0 + tid);  // 128 messages per pass
     __syncthreads();
     const uint32_t n = b.n_msgs;
     if (tid < n) skey_s[tid] = w.skey[0][tid];

@@ -433,3 +433,29 @@ def test_connection_id_quarantined_until_batches_released(pcdn):
     e.add_user(A, [0])                     # now the kick + re-add goes through
     assert e.num_users()[0] == 2
     e.close()
+
+
+@pytest.mark.parametrize("staged", [False, True])
+def test_small_engine_batch_sizes_across_the_fused_limit(pcdn, staged):
+    """an 8192-slot engine routes batches of <= 256 messages through the fused control kernel
+    (k_ctrl_small) and larger ones through the regular pipeline; both must agree with the oracle at
+    and around the limit (1, 2, 255, 256, 257, 700 messages; broadcasts, directs incl. a hot
+    recipient and unknown keys)"""
+    rng = random.Random(11)
+    w = World(pcdn, ring_bytes_per_conn=1 << 20, max_batch_msgs=1024, max_batch_bcast=1024,
+              flags=pcdn.FLAG_STAGED_SPANS if staged else 0)
+    keys = [rng.getrandbits(64).to_bytes(8, "little") * 4 for _ in range(700)]
+    for k in keys:
+        w.add_user(k, [t for t in range(8) if rng.random() < (0.5 if t == 0 else 0.05)])
+    w.add_broker("p/q", [0, 3])
+    hot = keys[5]
+    for n in (1, 2, 255, 256, 257, 700, 3):
+        for j in range(n):
+            r = rng.random()
+            if r < 0.4:
+                t = [rng.randrange(8)] + ([0] if rng.random() < 0.3 else [])
+                w.bcast(t, orc.broadcast_frame(t, payload(rng, rng.choice([0, 5, 300, 1500]))), rng.random() < 0.2)
+            else:
+                rc = hot if r < 0.6 else rng.choice(keys) if r < 0.9 else b"nobody-home"
+                w.direct(rc, orc.direct_frame(rc, j.to_bytes(4, "little") * rng.randrange(1, 40)))
+        assert w.check() > 0
