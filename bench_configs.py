@@ -86,7 +86,7 @@ def zipf_p(n, s=0.99):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", required=True, choices=["C3", "C4", "C5dense", "C5sparse", "latency", "churn"])
+    ap.add_argument("--workload", required=True, choices=["C1", "C3", "C4", "C5dense", "C5sparse", "latency", "churn"])
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--variant", type=int, default=0)
@@ -147,6 +147,51 @@ def main():
                                      "submit_call_p50_us": tsub[len(tsub) // 2], "deliveries": int(r.n_deliveries)})
             eng.close()
         print(json.dumps(out), flush=True)
+        return
+
+    if wl == "C1":
+        # BASELINE config 1 (the reference's own bench shape, cdn-broker/benches/broadcast.rs): 128 users on
+        # one topic, user 0 sends 1 KiB broadcasts, every user incl. the sender receives them.  Raw frames
+        # in host memory → pcdn_receive_frames (host parse, R6 prune, staging) → flush → poll → release,
+        # wall clock, for batches of 1 / 16 / 256 frames per receive call.
+        import ctypes as C
+        n, K = 128, 1024
+        keys = [i.to_bytes(8, "little") for i in range(n)]                    # tests/mod.rs:111-115
+        raw = bcast_frame_n(bytes([0]), bytes(((i * 7 + 1) & 0xFF) for i in range(K)))
+        Lr = len(raw)
+        eng = pkg.Engine(device=0, stream=stream.cuda_stream, max_conns=n, max_topics=256, max_keys=256, max_key_len=32,
+                         ring_bytes_per_conn=1 << 20, max_batch_msgs=256, max_batch_bcast=256, max_batch_bytes=1 << 20,
+                         max_batch_deliveries=256 * n + 1024, batch_slots=2, pack_variant=args.variant)
+        for k in keys:
+            eng.add_user(k, [0])
+        out = {"metric": "config C1 through the engine: raw frames in host memory -> pcdn_receive_frames -> flush -> poll -> release (wall clock)",
+               "config": {"workload": "C1: 128 subscribers, 1 topic, 1 KiB broadcast from user 0 (also a subscriber)", "frame_bytes": 4 + Lr},
+               "cases": []}
+        buf = (C.c_char * Lr).from_buffer_copy(raw)
+        for M in (1, 16, 256):
+            fa = (pkg.Frame * M)()
+            for i in range(M):
+                fa[i].sender = keys[0]; fa[i].sender_len = 8; fa[i].origin = 0
+                fa[i].raw = C.cast(buf, C.c_char_p); fa[i].raw_len = Lr
+            iters = 400 if M < 256 else 200
+            ts = []
+            for it in range(iters + 20):
+                t0 = time.perf_counter()
+                rc = eng.L.pcdn_receive_frames(eng.h, fa, M, None)
+                assert rc == M, rc
+                b = eng.flush()
+                res = eng.poll(b)
+                t1 = time.perf_counter()
+                assert res.n_deliveries == M * n and res.status == 0 and res.n_overflow == 0
+                eng.release_batch(b)
+                if it >= 20:
+                    ts.append(t1 - t0)
+            ts.sort()
+            p50 = ts[len(ts) // 2]
+            out["cases"].append({"frames_per_call": M, "p50_us_per_batch": p50 * 1e6, "msgs_per_s": M / p50,
+                                 "deliveries_per_s": M * n / p50, "egress_GBps": M * n * (4 + Lr) / p50 / 1e9})
+        print(json.dumps(out), flush=True)
+        eng.close()
         return
 
     if wl == "churn":
