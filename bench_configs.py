@@ -115,7 +115,7 @@ def main():
     if wl == "latency":
         # one message at a time through the host-buffer API: submit → poll (counters + span table back)
         out = {"metric": "single-message fan-out latency, host buffers in, pcdn_submit → pcdn_poll complete (wall clock)", "unit": "us", "cases": []}
-        for n in (128, 1 << 14, 1 << 20):
+        for n, host_rings in ((128, False), (128, True), (1 << 14, False), (1 << 20, False)):
             rng = np.random.default_rng(9)
             keys = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
             keys[:, :8] = np.arange(n, dtype=np.uint64).view(np.uint8).reshape(n, 8)
@@ -123,13 +123,15 @@ def main():
             rec = (4 + len(raw) + 31) // 32 * 32
             eng = pkg.Engine(device=0, stream=stream.cuda_stream, max_conns=n, max_topics=16, max_keys=n, max_key_len=32,
                              ring_bytes_per_conn=16 * rec, max_batch_msgs=64, max_batch_bcast=16, max_batch_bytes=1 << 20,
-                             max_batch_deliveries=n + 1024, batch_slots=2, pack_variant=args.variant)
+                             max_batch_deliveries=n + 1024, batch_slots=2, pack_variant=args.variant,
+                             flags=pkg.FLAG_HOST_RINGS if host_rings else 0)
             eng.add_users_bulk(keys, 32, np.zeros(n, dtype=np.uint16), np.arange(n + 1, dtype=np.uint32))
             rcpt = keys[n // 2].tobytes()
             tmpl, roff, poff = direct_frame_template(32, 512)
             draw = bytearray(tmpl); draw[roff:roff + 32] = rcpt; draw = bytes(draw)
-            for name, msgs in (("broadcast 1 KiB to all %d subscribers" % n, [("b", [0], raw, False)]),
-                               ("direct 512 B to one of %d users" % n, [("d", rcpt, draw, False)])):
+            tag = " — rings in host memory (PCDN_FLAG_HOST_RINGS): framed bytes readable in place when poll returns" if host_rings else ""
+            for name, msgs in (("broadcast 1 KiB to all %d subscribers%s" % (n, tag), [("b", [0], raw, False)]),
+                               ("direct 512 B to one of %d users%s" % (n, tag), [("d", rcpt, draw, False)])):
                 ts, tsub = [], []
                 for it in range(220):
                     t0 = time.perf_counter()
@@ -142,6 +144,11 @@ def main():
                         ts.append((t1 - t0) * 1e6)
                         tsub.append((tm - t0) * 1e6)
                 assert r.n_deliveries == (n if msgs[0][0] == "b" else 1)
+                if host_rings:  # what the socket writers would send, read in place
+                    b = eng.submit(msgs); r = eng.poll(b)
+                    got = eng.collect_frames(r)
+                    eng.release_batch(b)
+                    assert len(got) == r.n_deliveries and all(f == [msgs[0][2]] for f in got.values())
                 ts.sort(); tsub.sort()
                 out["cases"].append({"case": name, "p50_us": ts[len(ts) // 2], "p99_us": ts[int(len(ts) * 0.99)], "min_us": ts[0],
                                      "submit_call_p50_us": tsub[len(tsub) // 2], "deliveries": int(r.n_deliveries)})

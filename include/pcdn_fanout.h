@@ -110,7 +110,14 @@ enum {
    * overflow list straight into mapped pinned host memory (no D2H copies, one event to wait for:
    * the latency path of small brokers).  This flag forces the staged path of large engines (span
    * table built in HBM, copied out while the pack is still running) regardless of size. */
-  PCDN_FLAG_STAGED_SPANS = 2
+  PCDN_FLAG_STAGED_SPANS = 2,
+  /* Egress hand-off without a device→host copy: the per-connection rings live in
+   * mapped pinned HOST memory and the pack kernel stores the framed records there over PCIe, so a
+   * span is readable by the socket writer (writev / io_uring / MSG_ZEROCOPY) the moment pcdn_poll
+   * returns: pcdn_host_rings() gives the base pointer, a span's bytes are at
+   * base + conn * ring_bytes_per_conn + ring_off.  Egress is then bounded by PCIe (≈50 GB/s, above
+   * any NIC) instead of HBM; rings in HBM (default) are for GPUDirect hand-off and measurement.   */
+  PCDN_FLAG_HOST_RINGS = 4
 };
 
 /* One routed message.  `raw` is the inbound frame body and is forwarded verbatim (R1). */
@@ -297,7 +304,8 @@ int pcdn_submit_device(pcdn_engine* e, const pcdn_device_batch* batch, uint64_t*
 int pcdn_next_batch(pcdn_engine* e, uint64_t* batch_id);
 /* Wait for (block != 0) or test a batch; fills *out (span table is in pinned host memory). */
 int pcdn_poll(pcdn_engine* e, uint64_t batch_id, pcdn_batch_result* out, int block);
-/* Copy `len` ring bytes of a connection to host memory (what a socket writer would send). */
+/* Copy `len` ring bytes of a connection to host memory (what a socket writer would send).
+ * With PCDN_FLAG_HOST_RINGS this is a plain memcpy; prefer pcdn_host_rings() and read in place.  */
 int pcdn_read(pcdn_engine* e, pcdn_conn conn, uint32_t ring_off, uint32_t len, void* dst);
 /* The host has written every span of the batch: free its ring space and its slot.  This is the
  * analogue of dropping the last `Bytes` clone (limiter/pool.rs:44-52).  In order, oldest first. */
@@ -308,6 +316,9 @@ int pcdn_get_stats(pcdn_engine* e, pcdn_stats* out);
 int pcdn_set_timing(pcdn_engine* e, int on);
 /* device pointer + geometry of the rings (zero-copy verification / GPUDirect hand-off) */
 int pcdn_ring_info(pcdn_engine* e, void** dev_base, uint64_t* ring_bytes, uint32_t* max_conns);
+/* PCDN_FLAG_HOST_RINGS: host address of the rings (valid for the life of the engine); NULL and
+ * PCDN_ENOENT when the rings live in device memory. */
+int pcdn_host_rings(pcdn_engine* e, const void** host_base);
 /* number of connected users (Connections::num_users mod.rs:127) and brokers */
 int pcdn_num_users(pcdn_engine* e, uint32_t* users, uint32_t* brokers);
 /* Connections::get_interested_by_topic mod.rs:94-124 evaluated on the HOST MIRROR of the tables

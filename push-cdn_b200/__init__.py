@@ -34,6 +34,7 @@ NVCC_FLAGS = [
 KIND_DIRECT, KIND_BROADCAST, KIND_SUBSCRIBE, KIND_UNSUBSCRIBE = 3, 4, 5, 6
 TO_USERS_ONLY = 1
 FLAG_DEVICE_PARSE = 1
+FLAG_HOST_RINGS = 4     # rings in mapped pinned host memory: spans are readable in place (egress hand-off)
 FLAG_STAGED_SPANS = 2   # force the large-engine span path (table in HBM + D2H) on a small engine
 RECORD_ALIGN = 32
 CONN_NONE = 0xFFFFFFFF
@@ -178,6 +179,7 @@ ABI = {
     "pcdn_get_stats": (_ci, [_vp, C.POINTER(Stats)]),
     "pcdn_set_timing": (_ci, [_vp, _ci]),
     "pcdn_ring_info": (_ci, [_vp, C.POINTER(_vp), C.POINTER(_u64), C.POINTER(_u32)]),
+    "pcdn_host_rings": (_ci, [_vp, C.POINTER(_vp)]),
     "pcdn_num_users": (_ci, [_vp, C.POINTER(_u32), C.POINTER(_u32)]),
     "pcdn_debug_interested": (_ci, [_vp, _u16p, _u32, _ci, C.POINTER(_u32), _u32, C.POINTER(_u32)]),
     "pcdn_debug_route": (_ci, [_vp, _u8p, _u32, C.POINTER(_ci), C.POINTER(_u32)]),
@@ -440,6 +442,8 @@ class Engine:
         per connection in ring order.  A wrapped connection has two spans: the one that does not
         start at offset 0 comes first."""
         per: Dict[int, List[Tuple[int, int, int]]] = {}
+        hbase = self.host_rings()
+        rbytes = self.ring_info()[1] if hbase else 0
         for conn, off, ln, nrec in self.spans(res):
             per.setdefault(conn, []).append((off, ln, nrec))
         out: Dict[int, List[bytes]] = {}
@@ -448,7 +452,8 @@ class Engine:
             pieces.sort(key=lambda p: (p[0] == 0 and two, p[0]))
             frames = []
             for off, ln, nrec in pieces:
-                data = self.read(conn, off, ln)
+                # host rings: the bytes are read in place, exactly what a socket writer would do
+                data = C.string_at(hbase + conn * rbytes + off, ln) if hbase else self.read(conn, off, ln)
                 p = 0
                 for _ in range(nrec):
                     L = int.from_bytes(data[p:p + 4], "big")
@@ -488,6 +493,12 @@ class Engine:
         p, rb, mc = C.c_void_p(), C.c_uint64(), C.c_uint32()
         self._chk(self.L.pcdn_ring_info(self.h, C.byref(p), C.byref(rb), C.byref(mc)))
         return (p.value or 0), rb.value, mc.value
+
+    def host_rings(self) -> int:
+        """host address of the rings (FLAG_HOST_RINGS engines), else 0"""
+        p = C.c_void_p()
+        rc = self.L.pcdn_host_rings(self.h, C.byref(p))
+        return (p.value or 0) if rc == 0 else 0
 
     def num_users(self) -> Tuple[int, int]:
         u, b = C.c_uint32(), C.c_uint32()

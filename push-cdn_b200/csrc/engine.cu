@@ -117,6 +117,7 @@ struct pcdn_engine {
   std::unique_ptr<Connections> conns;
   bool has_device = false;
   bool direct_publish = false;  // spans / overflow list written by the device into mapped host memory
+  uint8_t* h_rings = nullptr;   // PCDN_FLAG_HOST_RINGS: host address of the (mapped, pinned) rings
   int n_sms = 148;
   // main stream: uploads, table updates, direct/match/plan/offsets, release.  pack stream: k_pack, so
   // that the control kernels of batch n+1 overlap the HBM-bound pack of batch n.  copy stream: D2H.
@@ -507,7 +508,14 @@ int init_device(pcdn_engine* e) {
   DEV_ALLOC(d.keys, (size_t)g.max_keys * g.key_stride);
   DEV_ALLOC(d.ptail, g.N);
   DEV_ALLOC(d.used, g.N);
-  DEV_ALLOC(d.rings, (size_t)g.max_conns * c.ring_bytes_per_conn);
+  if (c.flags & PCDN_FLAG_HOST_RINGS) {
+    // egress hand-off: the pack stores straight into host memory the socket writers read
+    int _rc = pin_alloc_mapped(&e->h_rings, &d.rings, (size_t)g.max_conns * c.ring_bytes_per_conn);
+    if (_rc) return _rc;
+    e->pin_allocs.push_back((void*)e->h_rings);
+  } else {
+    DEV_ALLOC(d.rings, (size_t)g.max_conns * c.ring_bytes_per_conn);
+  }
   CUDA_TRY(cudaMemsetAsync(d.sub, 0, (size_t)g.T * g.W * 4, e->stream));
   CUDA_TRY(cudaMemsetAsync(d.brk, 0, (size_t)g.W * 4, e->stream));
   CUDA_TRY(cudaMemsetAsync(d.owner_conn, 0xFF, (size_t)g.max_owners * 4, e->stream));
@@ -1244,6 +1252,10 @@ int pcdn_read(pcdn_engine* e, pcdn_conn conn, uint32_t ring_off, uint32_t len, v
   if (!e->has_device) return fail(PCDN_ENODEV, "host-only engine");
   if (conn >= e->geo.max_conns || (uint64_t)ring_off + len > e->cfg.ring_bytes_per_conn)
     return fail(PCDN_EINVAL, "read outside the connection's ring");
+  if (e->h_rings) {
+    std::memcpy(dst, e->h_rings + (size_t)conn * e->cfg.ring_bytes_per_conn + ring_off, len);
+    return 0;
+  }
   CUDA_TRY(cudaMemcpyAsync(dst, e->dev.rings + (size_t)conn * e->cfg.ring_bytes_per_conn + ring_off, len,
                            cudaMemcpyDeviceToHost, e->copy_stream));
   CUDA_TRY(cudaStreamSynchronize(e->copy_stream));
@@ -1291,6 +1303,11 @@ int pcdn_ring_info(pcdn_engine* e, void** dev_base, uint64_t* ring_bytes, uint32
   if (ring_bytes) *ring_bytes = e->cfg.ring_bytes_per_conn;
   if (max_conns) *max_conns = e->geo.max_conns;
   return 0;
+}
+int pcdn_host_rings(pcdn_engine* e, const void** host_base) {
+  LOCK;
+  if (host_base) *host_base = e->h_rings;
+  return e->h_rings ? 0 : fail(PCDN_ENOENT, "rings live in device memory (PCDN_FLAG_HOST_RINGS not set)");
 }
 int pcdn_num_users(pcdn_engine* e, uint32_t* users, uint32_t* brokers) {
   LOCK;

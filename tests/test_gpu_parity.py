@@ -26,6 +26,13 @@ def test_reference_scenario_st_variant(pcdn, scenario):
     scenario(EngineBackend(pcdn, pack_variant=4))
 
 
+@pytest.mark.parametrize("scenario", scenarios.ALL, ids=lambda f: f.__name__)
+def test_reference_scenario_host_rings(pcdn, scenario):
+    """egress hand-off mode (PCDN_FLAG_HOST_RINGS): the pack stores the framed records into mapped
+    pinned host memory; the scenarios read them in place"""
+    scenario(EngineBackend(pcdn, flags=pcdn.FLAG_HOST_RINGS))
+
+
 # ------------------------------------------------------------------ differential harness
 class World:
     """drives engine and oracle with identical calls and compares delivered frames"""
@@ -113,7 +120,7 @@ def payload(rng, n):
     return bytes(rng.getrandbits(8) for _ in range(min(n, 64))) * (n // 64 + 1)
 
 
-@pytest.mark.parametrize("variant", [0, 4, 2, "staged"])
+@pytest.mark.parametrize("variant", [0, 4, 2, "staged", "host", "host-st"])
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_random_mixed_batches(pcdn, seed, variant):
     """users + peer brokers, multi-topic broadcasts (fat and thin recipient sets), directs to local,
@@ -123,6 +130,12 @@ def test_random_mixed_batches(pcdn, seed, variant):
     rng = random.Random(seed)
     if variant == "staged":
         w = World(pcdn, flags=pcdn.FLAG_STAGED_SPANS, ring_bytes_per_conn=1 << 20)
+    elif variant in ("host", "host-st"):
+        # egress hand-off mode: rings in mapped pinned host memory, frames read in place by the host
+        # (TMA bulk stores / st.global.cs over PCIe)
+        w = World(pcdn, flags=pcdn.FLAG_HOST_RINGS, pack_variant=4 if variant == "host-st" else 0,
+                  ring_bytes_per_conn=1 << 20, max_conns=2048)
+        assert w.e.host_rings() != 0
     else:
         w = World(pcdn, pack_variant=variant, ring_bytes_per_conn=1 << 20)
     keys = []
