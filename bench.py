@@ -168,6 +168,8 @@ def main():
     ap.add_argument("--ring-records", type=int, default=RING_RECORDS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--host-rings", action="store_true",
+                    help="egress hand-off mode: rings in mapped pinned host memory (PCDN_FLAG_HOST_RINGS); PCIe-bound, use with --conns <= 65536")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -203,7 +205,7 @@ def main():
     eng = pkg.Engine(device=local, stream=stream.cuda_stream, max_conns=n_conns, max_topics=256, max_keys=n_conns,
                      max_key_len=KEY_LEN, ring_bytes_per_conn=ring_bytes, max_batch_msgs=max(64, M), max_batch_bcast=max(16, M),
                      max_batch_bytes=max(1 << 20, 4 * M * (rec + 64)), max_batch_deliveries=M * n_conns + 1024, batch_slots=4,
-                     pack_variant=args.variant)
+                     pack_variant=args.variant, flags=pkg.FLAG_HOST_RINGS if args.host_rings else 0)
     # 2^20 subscribers, all on topic 0 (keys differ per rank: the shard of a larger population)
     rng = np.random.default_rng(2 + rank)
     keys = rng.integers(0, 256, size=(n_conns, KEY_LEN), dtype=np.uint8)
@@ -447,7 +449,8 @@ def main():
             "deliveries_per_s": world * deliveries_step * args.steps / (ms_max * 1e-3),
             "ingress_msgs_per_s": M * args.steps / (ms_max * 1e-3),
             "frac_of_hbm_peak": value / world / peak,
-            "config": {"workload": "C2: 2^20 subscribers/GPU, 1 topic, 1 KiB broadcast, batches of %d" % M,
+            "config": {"workload": ("C2: 2^20 subscribers/GPU, 1 topic, 1 KiB broadcast, batches of %d" % M) if n_conns == N_CONNS and not args.host_rings
+                       else "%d subscribers/GPU, 1 topic, %d B broadcast, batches of %d%s" % (n_conns, args.payload, M, ", rings in mapped pinned HOST memory (PCIe-bound egress hand-off)" if args.host_rings else ""),
                        "n_conns_per_gpu": n_conns, "payload": args.payload, "frame_bytes": F, "msgs_per_step": M,
                        "ring_bytes_per_conn": ring_bytes, "parallelism": "connection shards x%d, NCCL ingest broadcast" % world
                        if world > 1 else "single GPU", "l2": "outputs 9.1 GB/step >> L2; inputs 8.7 KB (algorithmically resident)",
