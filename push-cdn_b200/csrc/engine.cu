@@ -1272,7 +1272,7 @@ int pcdn_release_batch(pcdn_engine* e, uint64_t batch_id) {
     return fail(PCDN_EINVAL, "batches must be released oldest first");
   // ring space may be reused only after the pack that filled it has finished
   CUDA_TRY(cudaStreamWaitEvent(e->stream, s->ev_done, 0));
-  launch_release(e->dev, s->w.batch_units, e->stream);
+  launch_release(e->dev, s->w.batch_units, s->w.stats, e->stream);
   CUDA_TRY(cudaGetLastError());
   e->inflight.erase(e->inflight.begin());
   s->state = SLOT_FREE;

@@ -1173,7 +1173,10 @@ void launch_pack(const DevState& s, const Work& w, const BatchIn& b, uint32_t va
 
 // =============================================================================== release
 // four connections per thread (N is a multiple of 8192; both arrays are separate allocations)
-__global__ void __launch_bounds__(256) k_release(DevState s, const uint32_t* __restrict__ batch_units) {
+// (a batch the device rejected — BatchStats::status — reserved nothing: its batch_units are stale)
+__global__ void __launch_bounds__(256) k_release(DevState s, const uint32_t* __restrict__ batch_units,
+                                                 const BatchStats* __restrict__ stats) {
+  if (stats->status) return;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i * 4 < s.N) {
     const uint4 u = reinterpret_cast<const uint4*>(batch_units)[i];
@@ -1185,8 +1188,8 @@ __global__ void __launch_bounds__(256) k_release(DevState s, const uint32_t* __r
     }
   }
 }
-void launch_release(const DevState& s, const uint32_t* batch_units, cudaStream_t st) {
-  k_release<<<(s.N / 4 + 255) / 256, 256, 0, st>>>(s, batch_units);
+void launch_release(const DevState& s, const uint32_t* batch_units, const BatchStats* stats, cudaStream_t st) {
+  k_release<<<(s.N / 4 + 255) / 256, 256, 0, st>>>(s, batch_units, stats);
 }
 
 }  // namespace pcdn

@@ -160,7 +160,7 @@ void launch_offsets(const DevState& s, const Work& w, const BatchIn& b, bool has
 void launch_ctrl_small(const DevState& s, const Work& w, const BatchIn& b, bool has_direct, bool zero_stats,
                        BatchStats* publish, cudaStream_t st);
 void launch_pack(const DevState& s, const Work& w, const BatchIn& b, uint32_t variant, int n_sms, cudaStream_t st);
-void launch_release(const DevState& s, const uint32_t* batch_units, cudaStream_t st);
+void launch_release(const DevState& s, const uint32_t* batch_units, const BatchStats* stats, cudaStream_t st);
 size_t sort_tiles(uint32_t n);
 
 }  // namespace pcdn

@@ -281,16 +281,28 @@ def test_explicit_submit_and_counters(pcdn):
 def test_batch_capacity_rejected_not_truncated(pcdn):
     """more deliveries than max_batch_deliveries: the device rejects the whole batch (E2BIG),
     nothing is written and ring cursors are untouched"""
-    w = World(pcdn, max_batch_deliveries=1000, max_conns=4096)
+    w = World(pcdn, max_batch_deliveries=1000, max_conns=4096, batch_slots=1, ring_bytes_per_conn=4096)
     for i in range(2000):
-        w.add_user(i.to_bytes(8, "little"), [0])
+        w.add_user(i.to_bytes(8, "little"), [1] if i < 900 else [0])
+    # first a batch that fits (leaves this slot's per-connection unit counts non-zero) ...
+    for _ in range(3):
+        w.bcast([1], orc.broadcast_frame([1], b"fits" * 200))
+        assert w.check() == 900
+    w.both("subscribe_user_to", (1).to_bytes(8, "little"), [0])
+    for i in range(900):
+        w.both("subscribe_user_to", i.to_bytes(8, "little"), [0])
     raw = orc.broadcast_frame([0], b"big fan-out")
+    # ... then, in the SAME slot, one that does not: releasing it must not hand back ring space twice
     w.e.handle_broadcast_message([0], raw)
     w.e.flush()
     bid = w.e.next_batch()
     res = w.e.poll(bid)
     assert res.status == 12 and res.n_deliveries == 0 and res.n_spans == 0
     w.e.release_batch(bid)
+    for _ in range(6):  # ring accounting still exact: 4 KB rings wrap and never report overflow
+        w.bcast([1], orc.broadcast_frame([1], b"fits" * 200))
+        assert w.check() == 900
+        assert w.e.last_result.n_overflow == 0
     # the engine keeps working afterwards
     w.both("unsubscribe_user_from", (5).to_bytes(8, "little"), [0])
     for i in range(1500):
