@@ -1270,6 +1270,10 @@ int pcdn_release_batch(pcdn_engine* e, uint64_t batch_id) {
   if (!s) return fail(PCDN_ENOENT, "unknown batch id");
   if (e->inflight.empty() || e->inflight.front() != batch_id)
     return fail(PCDN_EINVAL, "batches must be released oldest first");
+  // A slot released without having been polled may still have its host→device staging copy queued:
+  // its pinned staging buffers must not be refilled before that copy ran (device-input batches have
+  // no host staging and stay fully asynchronous — the pipelined submit_device/release loop).
+  if (!s->polled && !s->device_input) CUDA_TRY(cudaEventSynchronize(s->ev_done));
   // ring space may be reused only after the pack that filled it has finished
   CUDA_TRY(cudaStreamWaitEvent(e->stream, s->ev_done, 0));
   launch_release(e->dev, s->w.batch_units, s->w.stats, e->stream);
