@@ -188,6 +188,10 @@ typedef struct pcdn_stats {
   uint64_t inflight_bytes;      /* bytes currently holding pool permits                               */
   uint64_t released_batches;
   double latency_ms_sum;        /* launch → release wall time per batch (the reference's LATENCY histogram observes the permit lifetime, limiter/pool.rs:44-52) */
+  uint64_t bytes_in;            /* raw frame bytes accepted (metrics.rs BYTES_RECV; bytes_out above is BYTES_SENT + 4 per delivery) */
+  /* the LATENCY histogram (metrics.rs:21-23) of the same launch → release time, log2 buckets in
+   * microseconds: [0] < 16 us, [i] = [8 << i, 16 << i) us for i = 1..14, [15] >= 262 ms            */
+  uint64_t latency_hist_us[16];
 } pcdn_stats;
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */

@@ -399,6 +399,7 @@ int append_msg(pcdn_engine* e, uint8_t kind, uint8_t flags, const uint16_t* topi
   s.raw_len.push_back(raw_len);
   s.ingress_bytes += raw_len;
   e->inflight_bytes += raw_len;
+  e->stats.bytes_in += raw_len;
   if (kind == PCDN_KIND_BROADCAST) {
     s.aux_off.push_back((uint32_t)s.topics.size());
     s.aux_len.push_back(n_topics);
@@ -1072,6 +1073,7 @@ int receive_frames_locked(pcdn_engine* e, const pcdn_frame* frames, uint32_t n, 
     s.n_direct += nd;
     s.ingress_bytes += ingress;
     e->inflight_bytes += ingress;
+    e->stats.bytes_in += ingress;
     if (dev && nm > m0) s.devparse = true;
     (void)b0; (void)t0;
     i = j;
@@ -1284,7 +1286,14 @@ int pcdn_release_batch(pcdn_engine* e, uint64_t batch_id) {
   e->inflight_bytes -= std::min(e->inflight_bytes, s->ingress_bytes);
   s->ingress_bytes = 0;
   e->stats.released_batches++;
-  e->stats.latency_ms_sum += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s->t_launch).count();
+  {
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s->t_launch).count();
+    e->stats.latency_ms_sum += ms;
+    const uint64_t us = (uint64_t)(ms * 1000.0);
+    int bucket = 0;
+    while (bucket < 15 && us >= (16ull << bucket)) bucket++;
+    e->stats.latency_hist_us[bucket]++;
+  }
   return 0;
   GUARD_END
 }

@@ -276,6 +276,11 @@ def test_explicit_submit_and_counters(pcdn):
     got = w.e.collect_frames(res)
     w.e.release_batch(bid)
     assert got == w.expect()
+    # metrics.rs analogues: BYTES_RECV, BYTES_SENT, LATENCY histogram (one observation per released batch)
+    st = w.e.stats()
+    assert st.bytes_in == sum(len(m[2]) for m in msgs)
+    assert st.bytes_out == res.bytes_out and st.released_batches == 1
+    assert sum(st.latency_hist_us) == 1 and st.latency_ms_sum > 0
 
 
 def test_batch_capacity_rejected_not_truncated(pcdn):
