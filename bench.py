@@ -168,6 +168,10 @@ def main():
     ap.add_argument("--ring-records", type=int, default=RING_RECORDS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--ingest", choices=["nccl", "p2p"], default="nccl",
+                    help="N>1: how the batch reaches every GPU. nccl = one NCCL broadcast per step (prefetched on a side stream); "
+                         "p2p = no collective: rank 0 exports the ingest buffer with CUDA IPC and every GPU's pack kernel stages "
+                         "the frames straight from rank 0's HBM over NVLink (TMA bulk loads from peer memory)")
     ap.add_argument("--host-rings", action="store_true",
                     help="egress hand-off mode: rings in mapped pinned host memory (PCDN_FLAG_HOST_RINGS); PCIe-bound, use with --conns <= 65536")
     args = ap.parse_args()
@@ -255,6 +259,33 @@ def main():
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
     ev_ready = [torch.cuda.Event(), torch.cuda.Event()]
     ev_free = [torch.cuda.Event(), torch.cuda.Event()]
+    p2p = world > 1 and args.ingest == "p2p"
+    if p2p:
+        # Peer-memory ingest: the ingest GPU's buffer is mapped into every other process (CUDA IPC,
+        # peer access over NVLink/NVSwitch).  A device batch is just device pointers, so the engine
+        # needs nothing new: on ranks > 0 the match/offsets kernels read the tiny descriptors and the
+        # pack kernel's TMA bulk loads pull the frames from rank 0's HBM while it fans them out.
+        from cuda.bindings import runtime as rt
+
+        def ck(res):
+            assert int(res[0]) == 0, "CUDA runtime error %r" % (res[0],)
+            return res[1] if len(res) > 1 else None
+
+        nbytes = d_arena.numel()
+        blob = [None]
+        if rank == 0:
+            p2p_ptr = int(ck(rt.cudaMalloc(nbytes)))
+            ck(rt.cudaMemcpy(p2p_ptr, d_arena.data_ptr(), nbytes, rt.cudaMemcpyKind.cudaMemcpyDeviceToDevice))
+            blob[0] = bytes(ck(rt.cudaIpcGetMemHandle(p2p_ptr)).reserved)
+        dist.broadcast_object_list(blob, src=0)
+        if rank != 0:
+            h = rt.cudaIpcMemHandle_t()
+            h.reserved = blob[0]
+            p2p_ptr = int(ck(rt.cudaIpcOpenMemHandle(h, rt.cudaIpcMemLazyEnablePeerAccess)))
+        dbs = [pkg.DeviceBatch(M, M, p2p_ptr, nbytes, d_kind.data_ptr(), d_flags.data_ptr(), d_slot.data_ptr(), d_len.data_ptr(),
+                               d_aoff.data_ptr(), d_alen.data_ptr(), d_topics.data_ptr(), M, d_bidx.data_ptr())] * 2
+        db = dbs[0]
+        dist.barrier()
 
     def prefetch(k):
         with torch.cuda.stream(comm):
@@ -262,22 +293,24 @@ def main():
             dist.broadcast(d_arenas[k], src=0)   # NCCL ingest over NVLink
             ev_ready[k].record(comm)
 
+    nccl_ingest = world > 1 and not p2p
+
     def step_device():
         k = state["i"] & 1
-        if world > 1:
+        if nccl_ingest:
             if state["i"] == 0:
                 prefetch(0)
             stream.wait_event(ev_ready[k])
         state["i"] += 1
         b = eng.submit_device(dbs[k])
         eng.release_batch(b)                     # the consumer (NIC hand-off) frees the ring space
-        if world > 1:
+        if nccl_ingest:
             ev_free[k].record(stream)            # this batch's pack is done with ingest buffer k
             prefetch(k ^ 1)                      # next step's batch, overlapping this step's pack
         return b
 
     def drain_device():
-        if world > 1:
+        if nccl_ingest:
             torch.cuda.current_stream().wait_stream(comm)
         state["i"] = 0
 
@@ -376,9 +409,14 @@ def main():
         if world == 1:
             b = eng.submit(host_msgs)            # pinned staging + H2D + kernels
         else:
-            if rank == 0:
-                d_arena.copy_(pinned, non_blocking=True)
-            dist.broadcast(d_arena, src=0)
+            if p2p:
+                if rank == 0:  # host → the exported ingest buffer; the barrier orders the peers' reads after it
+                    ck(rt.cudaMemcpyAsync(p2p_ptr, pinned.data_ptr(), nbytes, rt.cudaMemcpyKind.cudaMemcpyHostToDevice, stream.cuda_stream))
+                dist.barrier()
+            else:
+                if rank == 0:
+                    d_arena.copy_(pinned, non_blocking=True)
+                dist.broadcast(d_arena, src=0)
             b = eng.submit_device(db)
         r = eng.poll(b)                          # D2H: counters + span table
         eng.release_batch(b)
@@ -452,7 +490,8 @@ def main():
             "config": {"workload": ("C2: 2^20 subscribers/GPU, 1 topic, 1 KiB broadcast, batches of %d" % M) if n_conns == N_CONNS and not args.host_rings
                        else "%d subscribers/GPU, 1 topic, %d B broadcast, batches of %d%s" % (n_conns, args.payload, M, ", rings in mapped pinned HOST memory (PCIe-bound egress hand-off)" if args.host_rings else ""),
                        "n_conns_per_gpu": n_conns, "payload": args.payload, "frame_bytes": F, "msgs_per_step": M,
-                       "ring_bytes_per_conn": ring_bytes, "parallelism": "connection shards x%d, NCCL ingest broadcast" % world
+                       "ring_bytes_per_conn": ring_bytes, "parallelism": ("connection shards x%d, " % world + ("peer-memory ingest: frames staged from rank 0's HBM over NVLink by the pack kernel (CUDA IPC), no collective"
+                                                                               if p2p else "NCCL ingest broadcast"))
                        if world > 1 else "single GPU", "l2": "outputs 9.1 GB/step >> L2; inputs 8.7 KB (algorithmically resident)",
                        "pack_variant": args.variant, "verify": verify, "setup_s": round(setup_s, 2)},
             "roofline": {"bound": "hbm", "kernel": "k_pack (connection-major phase)" if not (args.variant & 2) else "k_pack (message-major phase)", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -93,6 +93,9 @@ def main():
     ap.add_argument("--hit", type=float, default=1.0, help="C4: fraction of recipients that exist")
     ap.add_argument("--ingest", choices=["host", "device"], default=None,
                     help="C4 only: measure end-to-end ingest of RAW FRAMES from host memory through pcdn_receive_frames with the host parser or the device parse kernel")
+    ap.add_argument("--mgpu-ingest", choices=["nccl", "p2p"], default="nccl",
+                    help="config 5 under torchrun: NCCL broadcast of the batch per step, or peer-memory ingest (rank 0's buffer "
+                         "mapped with CUDA IPC; the pack kernel stages frames from it over NVLink, no collective)")
     args = ap.parse_args()
     import torch
 
@@ -340,7 +343,34 @@ def main():
         mk = lambda a: DeviceBatch(pkg, torch, dev, a, np.full(M, 4), np.zeros(M), np.arange(M) * (slot // 16), np.full(M, L),
                                    np.arange(M), np.ones(M), topics, np.arange(M))
         db = mk(arena)
-        if world > 1:
+        p2p = world > 1 and args.mgpu_ingest == "p2p"
+        if p2p:
+            from cuda.bindings import runtime as rt
+
+            def ck(res):
+                assert int(res[0]) == 0, "CUDA runtime error %r" % (res[0],)
+                return res[1] if len(res) > 1 else None
+
+            nbytes = db.arena.numel()
+            blob = [None]
+            if rank == 0:
+                p2p_ptr = int(ck(rt.cudaMalloc(nbytes)))
+                ck(rt.cudaMemcpy(p2p_ptr, db.arena.data_ptr(), nbytes, rt.cudaMemcpyKind.cudaMemcpyDeviceToDevice))
+                blob[0] = bytes(ck(rt.cudaIpcGetMemHandle(p2p_ptr)).reserved)
+            dist.broadcast_object_list(blob, src=0)
+            if rank != 0:
+                h = rt.cudaIpcMemHandle_t()
+                h.reserved = blob[0]
+                p2p_ptr = int(ck(rt.cudaIpcOpenMemHandle(h, rt.cudaIpcMemLazyEnablePeerAccess)))
+            # same descriptors, frames read from rank 0's HBM (peer memory) by the pack kernel
+            d0 = db.db
+            db.db = pkg.DeviceBatch(d0.n_msgs, d0.n_bcast, p2p_ptr, nbytes, db.kind.data_ptr(), db.flags.data_ptr(), db.slot.data_ptr(),
+                                    db.len.data_ptr(), db.aoff.data_ptr(), db.alen.data_ptr(), db.topics.data_ptr(), len(topics),
+                                    db.bidx.data_ptr())
+            if rank != 0:
+                db.arena.zero_()   # nothing local to fall back on
+            dist.barrier()
+        elif world > 1:
             # ranks other than 0 start from zeroed ingest buffers: the frames they fan out arrive by NCCL
             dbs = [mk(arena if rank == 0 else np.zeros_like(arena)) for _ in range(2)]
         per_topic = np.bincount(subs.reshape(-1), minlength=max(T, 1))
@@ -387,7 +417,9 @@ def main():
 
     prev = 0
     it = 0
-    if world > 1:
+    p2p = world > 1 and args.mgpu_ingest == "p2p"
+    nccl_ingest = world > 1 and not p2p
+    if nccl_ingest:
         comm = torch.cuda.Stream(device=dev)
         ev_ready = [torch.cuda.Event(), torch.cuda.Event()]
         ev_free = [torch.cuda.Event(), torch.cuda.Event()]
@@ -401,7 +433,7 @@ def main():
     with torch.cuda.stream(stream):
         def step():
             nonlocal prev, it
-            if world > 1:
+            if nccl_ingest:
                 k = it & 1
                 if it == 0:
                     prefetch(0)
@@ -413,7 +445,7 @@ def main():
             if prev:
                 eng.release_batch(prev)
             prev = b
-            if world > 1:
+            if nccl_ingest:
                 ev_free[k].record(stream)
                 prefetch(k ^ 1)
 
@@ -422,7 +454,7 @@ def main():
             if prev:
                 eng.release_batch(prev)
                 prev = 0
-            if world > 1:
+            if nccl_ingest:
                 torch.cuda.current_stream().wait_stream(comm)
                 it = 0
 
@@ -448,15 +480,15 @@ def main():
             tm = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)   # max over ranks
             ms = float(tm.item())
-            # what was fanned out on this rank arrived over NCCL: must equal rank 0's frames
-            want = torch.from_numpy(arena).to(dev)
-            assert torch.equal(dbs[0].arena, want) and torch.equal(dbs[1].arena, want), "NCCL ingest differs"
+            if nccl_ingest:  # what was fanned out on this rank arrived over NCCL: must equal rank 0's frames
+                want = torch.from_numpy(arena).to(dev)
+                assert torch.equal(dbs[0].arena, want) and torch.equal(dbs[1].arena, want), "NCCL ingest differs"
         # counters of one batch + per-stage device times
         eng.set_timing(True)
         s0 = eng.stats()
         res = None
         for _ in range(max(3, args.steps // 2)):
-            b = eng.submit_device((dbs[0] if world > 1 else db).db)
+            b = eng.submit_device((dbs[0] if nccl_ingest else db).db)
             res = eng.poll(b)
             d, bo, dropped, ovf, status = res.n_deliveries, res.bytes_out, res.n_direct_dropped, res.n_overflow, res.status
             eng.release_batch(b)
@@ -476,7 +508,9 @@ def main():
         tot = torch.tensor([bo, d], dtype=torch.float64, device=dev)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)   # whole job = sum of the shards
         bo_all, d_all = float(tot[0].item()), float(tot[1].item())
-        desc = dict(desc, parallelism="connection shards x%d (2^20 per GPU), one NCCL broadcast of the batch per step, prefetched on a side stream" % world)
+        desc = dict(desc, parallelism="connection shards x%d (2^20 per GPU), " % world +
+                    ("peer-memory ingest: the pack kernel stages the frames from rank 0's HBM over NVLink (CUDA IPC), no collective" if p2p
+                     else "one NCCL broadcast of the batch per step, prefetched on a side stream"))
         if rank != 0:
             eng.close()
             dist.barrier()
