@@ -437,7 +437,6 @@ void launch_direct(const DevState& s, const Work& w, const BatchIn& b, cudaStrea
 }
 
 // =============================================================================== K1a topic match
-// grid (W/256, n_bcast): thread = one 32-connection word of one broadcast message.
 // match word `wd` (32 connections) of message m: OR of its topics' bitmap rows (a2)
 __device__ __forceinline__ uint32_t match_word(const DevState& s, const BatchIn& b, uint32_t m, uint32_t wd) {
   const uint32_t toff = b.aux_off[m], tn = b.aux_len[m];
@@ -459,15 +458,49 @@ __device__ __forceinline__ uint32_t match_word(const DevState& s, const BatchIn&
   if (fl & MSGF_USERS_ONLY) word &= ~s.brk[wd];  // to_users_only (connections/mod.rs:111)
   return word;
 }
+// Warp = one 256-word match block of one message, lane = 8 consecutive words (32-byte vector
+// loads of the bitmap rows, no block-level synchronisation: the popcount prefix of a 256-word block
+// is a lane-local prefix plus one warp scan).  grid = (ceil(nblk / 8), n_bcast).
 __global__ void __launch_bounds__(256) k_match(DevState s, BatchIn b, Work w) {
-  __shared__ uint32_t sm[9];
-  const uint32_t j = blockIdx.y;
-  const uint32_t wd = blockIdx.x * kBlockWords + threadIdx.x;  // W is a multiple of 256
-  const uint32_t word = match_word(s, b, b.bcast_index[j], wd);
-  w.B[(size_t)j * s.W + wd] = word;
-  uint32_t tot, ex = block256_excl_scan(__popc(word), &tot, sm);
-  w.wpre[(size_t)j * s.W + wd] = (uint16_t)ex;
-  if (threadIdx.x == 0) w.cnt[(size_t)j * s.nblk + blockIdx.x] = tot;
+  const uint32_t j = blockIdx.y, lane = lane_id();
+  const uint32_t blk = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (blk >= s.nblk) return;  // warp-uniform
+  const uint32_t m = b.bcast_index[j];
+  const uint32_t w0 = blk * kBlockWords + lane * 8;
+  const uint32_t toff = b.aux_off[m], tn = b.aux_len[m], fl = b.flags[m];
+  uint4 lo = make_uint4(0, 0, 0, 0), hi = make_uint4(0, 0, 0, 0);
+  auto or_row = [&](uint32_t t) {
+    if (t >= s.T) return;
+    const uint4* row = reinterpret_cast<const uint4*>(s.sub + (size_t)t * s.W + w0);
+    const uint4 a = row[0], c = row[1];
+    lo.x |= a.x; lo.y |= a.y; lo.z |= a.z; lo.w |= a.w;
+    hi.x |= c.x; hi.y |= c.y; hi.z |= c.z; hi.w |= c.w;
+  };
+  if (fl & MSGF_TOPICS_U8) {  // wire topic list read in place (device-parse mode)
+    const uint8_t* tb = b.arena + toff;
+    for (uint32_t i = 0; i < tn; i++) {
+      if ((fl & MSGF_PRUNE) && !topic_kept(tb, i, s.n_valid_topics)) continue;
+      or_row(tb[i]);
+    }
+  } else {
+    for (uint32_t i = 0; i < tn; i++) or_row(b.topics[toff + i]);
+  }
+  if (fl & MSGF_USERS_ONLY) {  // to_users_only (connections/mod.rs:111)
+    const uint4* br = reinterpret_cast<const uint4*>(s.brk + w0);
+    const uint4 a = br[0], c = br[1];
+    lo.x &= ~a.x; lo.y &= ~a.y; lo.z &= ~a.z; lo.w &= ~a.w;
+    hi.x &= ~c.x; hi.y &= ~c.y; hi.z &= ~c.z; hi.w &= ~c.w;
+  }
+  const uint32_t p0 = __popc(lo.x), p1 = p0 + __popc(lo.y), p2 = p1 + __popc(lo.z), p3 = p2 + __popc(lo.w);
+  const uint32_t p4 = p3 + __popc(hi.x), p5 = p4 + __popc(hi.y), p6 = p5 + __popc(hi.z), p7 = p6 + __popc(hi.w);
+  const uint32_t incl = warp_incl_scan(p7), ex = incl - p7;  // exclusive prefix over the lanes before this one
+  uint4* Bo = reinterpret_cast<uint4*>(w.B + (size_t)j * s.W + w0);
+  Bo[0] = lo; Bo[1] = hi;
+  uint4 pre;  // eight u16 prefixes (a 256-word block holds at most 8192 recipients)
+  pre.x = ex | ((ex + p0) << 16); pre.y = (ex + p1) | ((ex + p2) << 16);
+  pre.z = (ex + p3) | ((ex + p4) << 16); pre.w = (ex + p5) | ((ex + p6) << 16);
+  *reinterpret_cast<uint4*>(w.wpre + (size_t)j * s.W + w0) = pre;
+  if (lane == 31) w.cnt[(size_t)j * s.nblk + blk] = incl;
 }
 // one block per broadcast: exclusive prefix of the block counts, D_m
 __global__ void __launch_bounds__(256) k_match_base(DevState s, BatchIn b, Work w) {
@@ -485,7 +518,7 @@ __global__ void __launch_bounds__(256) k_match_base(DevState s, BatchIn b, Work 
 }
 void launch_match(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st) {
   if (!b.n_bcast) return;
-  dim3 grid(s.W / kBlockWords, b.n_bcast);
+  dim3 grid((s.nblk + 7) / 8, b.n_bcast);
   k_match<<<grid, 256, 0, st>>>(s, b, w);
   k_match_base<<<b.n_bcast, 256, 0, st>>>(s, b, w);
 }
