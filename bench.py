@@ -479,7 +479,7 @@ def main():
             cpu = {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
 
     if rank == 0:
-        launches_per_step = 6  # k_match, k_match_base, k_plan_a, k_offsets, k_pack, k_release
+        launches_per_step = 5  # k_match, k_plan_a, k_offsets, k_pack, k_release
         line = {
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

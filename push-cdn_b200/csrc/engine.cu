@@ -542,6 +542,8 @@ int init_device(pcdn_engine* e) {
     DEV_ALLOC(w.wpre, (size_t)MB * g.W);
     DEV_ALLOC(w.cnt, (size_t)MB * d.nblk);
     DEV_ALLOC(w.base, (size_t)MB * d.nblk);
+    DEV_ALLOC(w.done, MB);
+    CUDA_TRY(cudaMemsetAsync(w.done, 0, (size_t)MB * 4, e->stream));
     DEV_ALLOC(w.D, M);
     DEV_ALLOC(w.dconn, M);
     DEV_ALLOC(w.eb_fat, (size_t)M + 1);

@@ -500,27 +500,31 @@ __global__ void __launch_bounds__(256) k_match(DevState s, BatchIn b, Work w) {
   pre.x = ex | ((ex + p0) << 16); pre.y = (ex + p1) | ((ex + p2) << 16);
   pre.z = (ex + p3) | ((ex + p4) << 16); pre.w = (ex + p5) | ((ex + p6) << 16);
   *reinterpret_cast<uint4*>(w.wpre + (size_t)j * s.W + w0) = pre;
-  if (lane == 31) w.cnt[(size_t)j * s.nblk + blk] = incl;
-}
-// one block per broadcast: exclusive prefix of the block counts, D_m
-__global__ void __launch_bounds__(256) k_match_base(DevState s, BatchIn b, Work w) {
-  __shared__ uint32_t sm[9];
-  const uint32_t j = blockIdx.x;
-  uint32_t carry = 0;
-  for (uint32_t bb = 0; bb < s.nblk; bb += 256) {
-    const uint32_t i = bb + threadIdx.x;
-    const uint32_t v = i < s.nblk ? w.cnt[(size_t)j * s.nblk + i] : 0;
-    uint32_t tot, ex = block256_excl_scan(v, &tot, sm);
-    if (i < s.nblk) w.base[(size_t)j * s.nblk + i] = ex + carry;
-    carry += tot;
+  // The warp that finishes a message last turns its block counts into exclusive bases and D_m
+  // (no second launch).  `done[j]` counts finished blocks and is left at zero for the next batch.
+  uint32_t last = 0;
+  if (lane == 31) {
+    w.cnt[(size_t)j * s.nblk + blk] = incl;
+    __threadfence();
+    last = atomicAdd(&w.done[j], 1u) == s.nblk - 1 ? 1u : 0u;
   }
-  if (threadIdx.x == 0) { w.D[b.bcast_index[j]] = carry; w.jidx[b.bcast_index[j]] = j; }
+  if (__shfl_sync(0xffffffffu, last, 31)) {
+    __threadfence();
+    uint32_t carry = 0;
+    for (uint32_t bb = 0; bb < s.nblk; bb += 32) {
+      const uint32_t i = bb + lane;
+      const uint32_t v = i < s.nblk ? __ldcg(w.cnt + (size_t)j * s.nblk + i) : 0;
+      const uint32_t in = warp_incl_scan(v);
+      if (i < s.nblk) w.base[(size_t)j * s.nblk + i] = carry + in - v;
+      carry += __shfl_sync(0xffffffffu, in, 31);
+    }
+    if (lane == 0) { w.D[m] = carry; w.jidx[m] = j; w.done[j] = 0; }
+  }
 }
 void launch_match(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st) {
   if (!b.n_bcast) return;
   dim3 grid((s.nblk + 7) / 8, b.n_bcast);
   k_match<<<grid, 256, 0, st>>>(s, b, w);
-  k_match_base<<<b.n_bcast, 256, 0, st>>>(s, b, w);
 }
 
 // =============================================================================== K1p plan
@@ -767,7 +771,7 @@ void launch_offsets(const DevState& s, const Work& w, const BatchIn& b, bool has
 // consensus nodes, one vote or proposal at a time).  There the regular pipeline is a chain of five
 // tiny dependent launches; here match, plan and offsets run in ONE launch on one cluster of eight
 // 1024-thread CTAs — a thread per connection — with cluster barriers where the pipeline has kernel
-// boundaries.  It writes exactly the arrays k_match / k_match_base / k_plan_a / k_offsets write (the
+// boundaries.  It writes exactly the arrays k_match / k_plan_a / k_offsets write (the
 // pack kernel and the host cannot tell the difference), zeroes the batch counters itself when no
 // earlier kernel of the batch needs them, and publishes the final counters into mapped host memory.
 __device__ __forceinline__ void cluster_sync_all() {
@@ -807,7 +811,7 @@ k_ctrl_small(DevState s, BatchIn b, Work w, int zero_stats, BatchStats* publish)
     }
   }
 
-  // ---- match (= k_match + k_match_base with nblk == 1): four messages per pass, 256 words each
+  // ---- match (= k_match with nblk == 1): four messages per pass, 256 words each
   {
     const uint32_t q = tid >> 8, wd = tid & 255u;
     for (uint32_t j0 = rank * 4; j0 < b.n_bcast; j0 += 32) {  // trip count is uniform inside a CTA

@@ -110,6 +110,7 @@ struct Work {
   uint16_t* wpre;        // [max_bcast][W] exclusive popcount prefix inside the 256-word block
   uint32_t* cnt;         // [max_bcast][nblk]
   uint32_t* base;        // [max_bcast][nblk] exclusive prefix of cnt over blocks
+  uint32_t* done;        // [max_bcast] finished match blocks of a message (k_match; zero between batches)
   uint32_t* D;           // [max_msgs] recipients per message
   uint32_t* dconn;       // [max_msgs] direct: target connection or NONE
   uint32_t* eb_fat;      // [max_msgs+1] scatter-list base per message (fat list)
