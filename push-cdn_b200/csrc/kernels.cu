@@ -494,20 +494,21 @@ __global__ void __launch_bounds__(256) k_match(DevState s, BatchIn b, Work w) {
   const uint32_t p0 = __popc(lo.x), p1 = p0 + __popc(lo.y), p2 = p1 + __popc(lo.z), p3 = p2 + __popc(lo.w);
   const uint32_t p4 = p3 + __popc(hi.x), p5 = p4 + __popc(hi.y), p6 = p5 + __popc(hi.z), p7 = p6 + __popc(hi.w);
   const uint32_t incl = warp_incl_scan(p7), ex = incl - p7;  // exclusive prefix over the lanes before this one
-  uint4* Bo = reinterpret_cast<uint4*>(w.B + (size_t)j * s.W + w0);
-  Bo[0] = lo; Bo[1] = hi;
-  uint4 pre;  // eight u16 prefixes (a 256-word block holds at most 8192 recipients)
-  pre.x = ex | ((ex + p0) << 16); pre.y = (ex + p1) | ((ex + p2) << 16);
-  pre.z = (ex + p3) | ((ex + p4) << 16); pre.w = (ex + p5) | ((ex + p6) << 16);
-  *reinterpret_cast<uint4*>(w.wpre + (size_t)j * s.W + w0) = pre;
   // The warp that finishes a message last turns its block counts into exclusive bases and D_m
   // (no second launch).  `done[j]` counts finished blocks and is left at zero for the next batch.
+  // (count published BEFORE the wide stores below, so the fence only has one store to wait for)
   uint32_t last = 0;
   if (lane == 31) {
     w.cnt[(size_t)j * s.nblk + blk] = incl;
     __threadfence();
     last = atomicAdd(&w.done[j], 1u) == s.nblk - 1 ? 1u : 0u;
   }
+  uint4* Bo = reinterpret_cast<uint4*>(w.B + (size_t)j * s.W + w0);
+  Bo[0] = lo; Bo[1] = hi;
+  uint4 pre;  // eight u16 prefixes (a 256-word block holds at most 8192 recipients)
+  pre.x = ex | ((ex + p0) << 16); pre.y = (ex + p1) | ((ex + p2) << 16);
+  pre.z = (ex + p3) | ((ex + p4) << 16); pre.w = (ex + p5) | ((ex + p6) << 16);
+  *reinterpret_cast<uint4*>(w.wpre + (size_t)j * s.W + w0) = pre;
   if (__shfl_sync(0xffffffffu, last, 31)) {
     __threadfence();
     uint32_t carry = 0;
