@@ -624,8 +624,42 @@ __global__ void __launch_bounds__(256) k_plan_c(BatchIn b, Work w, uint32_t nblk
     w.cm_rank[m] = w.stats->n_cm;
   }
 }
+// Direct-only batches (no broadcast in the batch): every message is "thin" with D in {0, 1}, so the
+// plan is ONE exclusive scan (the thin scatter-list bases) instead of four; classes, fat bases, tiles
+// and the connection-major list are never read (the batch counters were zeroed at batch begin).
+__global__ void __launch_bounds__(256) k_plan_direct_a(BatchIn b, Work w) {
+  __shared__ uint32_t sm[9];
+  const uint32_t m = blockIdx.x * 256 + threadIdx.x;
+  uint32_t tot, ex = block256_excl_scan(m < b.n_msgs ? w.D[m] : 0, &tot, sm);
+  if (m < b.n_msgs) w.eb_thin[m] = ex;
+  if (threadIdx.x == 0) w.scan_tmp[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(256) k_plan_direct_b(Work w, uint32_t nblk) {
+  __shared__ uint32_t sm[9];
+  uint32_t carry = 0;
+  for (uint32_t bb = 0; bb < nblk; bb += 256) {
+    const uint32_t i = bb + threadIdx.x;
+    const uint32_t v = i < nblk ? w.scan_tmp[i] : 0;
+    uint32_t tot, ex = block256_excl_scan(v, &tot, sm);
+    if (i < nblk) w.scan_tmp[i] = ex + carry;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) { w.stats->n_thin_entries = carry; if (carry > w.cap_thin) w.stats->status = 1; }  // PCDN_E2BIG
+}
+__global__ void __launch_bounds__(256) k_plan_direct_c(BatchIn b, Work w) {
+  const uint32_t m = blockIdx.x * 256 + threadIdx.x;
+  if (m < b.n_msgs) w.eb_thin[m] += w.scan_tmp[blockIdx.x];
+  else if (m == b.n_msgs) w.eb_thin[m] = w.stats->n_thin_entries;
+}
+
 void launch_plan(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st) {
   const uint32_t nblk = (b.n_msgs + 255) / 256;
+  if (b.n_bcast == 0 && nblk > 1) {
+    k_plan_direct_a<<<nblk, 256, 0, st>>>(b, w);
+    k_plan_direct_b<<<1, 256, 0, st>>>(w, nblk);
+    k_plan_direct_c<<<(b.n_msgs + 1 + 255) / 256, 256, 0, st>>>(b, w);
+    return;
+  }
   k_plan_a<<<nblk, 256, 0, st>>>(s, b, w, nblk);
   if (nblk == 1) return;  // finished inside k_plan_a
   k_plan_b<<<4, 256, 0, st>>>(w, nblk);
