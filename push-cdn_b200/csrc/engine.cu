@@ -69,7 +69,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 enum SlotState { SLOT_FREE = 0, SLOT_OPEN = 1, SLOT_INFLIGHT = 2 };
 // engines up to this many connection slots publish spans directly into mapped host memory
-constexpr uint32_t kDirectPublishMaxConns = 8192;  // (16 K connections already measured slower than the staged D2H)
+constexpr uint32_t kDirectPublishMaxConns = 65536;  // = kSmallCtrlConns: the engines the fused control kernel serves
 
 struct Slot {
   int state = SLOT_FREE;
@@ -243,7 +243,7 @@ int launch_pipeline(pcdn_engine* e, Slot& s, uint32_t n_direct) {
   if (++s.w.stamp == 0) s.w.stamp = 1;  // validity stamp of this batch's direct buckets
   // latency path of the smallest geometry: match + plan + offsets in one cluster launch that also
   // zeroes / publishes the counters (kernels.cu: k_ctrl_small)
-  const bool fused = dp && e->geo.N == kSmallCtrlConns && s.in.n_msgs <= kSmallCtrlMsgs;
+  const bool fused = dp && e->geo.N <= kSmallCtrlConns && s.in.n_msgs <= kSmallCtrlMsgs;
   const bool zero_in_kernel = fused && !s.devparse;  // (k_parse counts into the batch counters before the fused kernel)
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[0], st));
   if (!zero_in_kernel) launch_batch_begin(e->dev, s.w, s.in, has_direct, st);

@@ -801,11 +801,11 @@ void launch_offsets(const DevState& s, const Work& w, const BatchIn& b, bool has
 }
 
 // =============================================================================== fused control (small engines)
-// The smallest geometry (N = 8192 connections, W = 256 words, one 256-word block per message) with a
-// batch of at most kSmallCtrlMsgs messages is the latency regime of a real broker (a few hundred
-// consensus nodes, one vote or proposal at a time).  There the regular pipeline is a chain of five
+// Small geometries (N <= kSmallCtrlConns connection slots, i.e. at most 8 match blocks per message)
+// with a batch of at most kSmallCtrlMsgs messages are the latency regime of a real broker (a few
+// hundred to a few thousand consensus nodes, one vote or proposal at a time).  There the regular pipeline is a chain of five
 // tiny dependent launches; here match, plan and offsets run in ONE launch on one cluster of eight
-// 1024-thread CTAs — a thread per connection — with cluster barriers where the pipeline has kernel
+// 1024-thread CTAs — a thread per connection and 8192-connection pass — with cluster barriers where the pipeline has kernel
 // boundaries.  It writes exactly the arrays k_match / k_plan_a / k_offsets write (the
 // pack kernel and the host cannot tell the difference), zeroes the batch counters itself when no
 // earlier kernel of the batch needs them, and publishes the final counters into mapped host memory.
@@ -846,31 +846,43 @@ k_ctrl_small(DevState s, BatchIn b, Work w, int zero_stats, BatchStats* publish)
     }
   }
 
-  // ---- match (= k_match with nblk == 1): four messages per pass, 256 words each
+  // ---- match (= k_match): four (message, 256-word block) items per pass and CTA
   {
-    const uint32_t q = tid >> 8, wd = tid & 255u;
-    for (uint32_t j0 = rank * 4; j0 < b.n_bcast; j0 += 32) {  // trip count is uniform inside a CTA
-      const uint32_t j = j0 + q;
-      const bool live = j < b.n_bcast;
-      const uint32_t m = live ? b.bcast_index[j] : 0;
-      const uint32_t word = live ? match_word(s, b, m, wd) : 0;
+    const uint32_t q = tid >> 8, wl = tid & 255u, nitems = b.n_bcast * s.nblk;
+    for (uint32_t i0 = rank * 4; i0 < nitems; i0 += 32) {  // trip count is uniform inside a CTA
+      const uint32_t it = i0 + q;
+      const bool live = it < nitems;
+      const uint32_t j = live ? it / s.nblk : 0, blk = live ? it % s.nblk : 0;
+      const uint32_t wd = blk * kBlockWords + wl;
+      const uint32_t word = live ? match_word(s, b, b.bcast_index[j], wd) : 0;
       uint32_t tot, ex = cta_excl_scan<32>(__popc(word), &tot, sm);
-      if (wd == 0) gbase[q] = ex;
+      if (wl == 0) gbase[q] = ex;
       if (tid == 0) gbase[4] = tot;
       __syncthreads();
       if (live) {
         w.B[(size_t)j * s.W + wd] = word;
         w.wpre[(size_t)j * s.W + wd] = (uint16_t)(ex - gbase[q]);
-        if (wd == 0) {
-          const uint32_t d = gbase[q + 1] - gbase[q];
-          w.cnt[j] = d; w.base[j] = 0;  // nblk == 1
-          w.D[m] = d; w.jidx[m] = j;
-        }
+        if (wl == 0) w.cnt[(size_t)j * s.nblk + blk] = gbase[q + 1] - gbase[q];
       }
       __syncthreads();
     }
   }
   cluster_sync_all();
+
+  // ---- block bases and D_m of every broadcast (thread = message; at most 8 blocks each) on CTA 0
+  if (rank == 0) {
+    if (tid < b.n_bcast) {
+      uint32_t carry = 0;
+      for (uint32_t blk = 0; blk < s.nblk; blk++) {
+        const uint32_t v = w.cnt[(size_t)tid * s.nblk + blk];
+        w.base[(size_t)tid * s.nblk + blk] = carry;
+        carry += v;
+      }
+      const uint32_t m = b.bcast_index[tid];
+      w.D[m] = carry; w.jidx[m] = tid;
+    }
+    __syncthreads();
+  }
 
   // ---- plan (= the single-block case of k_plan_a) on CTA 0
   if (rank == 0) {
@@ -898,8 +910,8 @@ k_ctrl_small(DevState s, BatchIn b, Work w, int zero_stats, BatchStats* publish)
   }
   cluster_sync_all();
 
-  // ---- offsets: thread = connection
-  offsets_body<HAS_DIRECT, 1024>(s, b, w, s.N, rank * 1024 + tid);
+  // ---- offsets: thread = connection (one pass per 8192 connections)
+  for (uint32_t c0 = 0; c0 < s.N; c0 += 8192) offsets_body<HAS_DIRECT, 1024>(s, b, w, s.N, c0 + rank * 1024 + tid);
 
   // ---- final counters straight into the host's (mapped, pinned) result block
   if (publish) {

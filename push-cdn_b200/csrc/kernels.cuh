@@ -14,7 +14,7 @@
 //                       records), message-major (16 KiB chunks staged once per CTA, replicated to
 //                       ~128 KB worth of recipients per tile), thin (warp per delivery; its own
 //                       full-occupancy launch k_pack_thin for batches of >= 2048 direct messages)
-//   K1s k_ctrl_small    latency path (N = 8192 connection slots, <= 256 messages): K3 + sort + K1a +
+//   K1s k_ctrl_small    latency path (N <= 65536 connection slots, <= 256 messages): K3 + sort + K1a +
 //                       K1p + K1b in ONE cluster launch, counters/spans published to mapped host memory
 //   K4  k_apply_*       scatter of changed table words/slots (subscribe, add/remove, direct map)
 //       k_release       ring space of a consumed batch goes back to the connections
@@ -37,7 +37,7 @@ constexpr uint32_t kBlockWords = 256;        // bitmap words per match block (81
 // connection by connection, so that one connection's records form ONE contiguous run in its ring
 constexpr uint32_t kCmGroup = 8;             // messages staged together in shared memory
 constexpr uint32_t kCmMaxBytes = 4096;       // largest padded record that takes the cm path
-constexpr uint32_t kSmallCtrlConns = 8192;    // geometry served by the fused control kernel (one thread per connection)
+constexpr uint32_t kSmallCtrlConns = 65536;   // largest geometry served by the fused control kernel (<= 8 match blocks per message)
 constexpr uint32_t kSmallCtrlMsgs = 256;      // largest batch it takes
 constexpr uint32_t kThinSeparateMin = 2048;  // direct messages in a batch from which the thin pack gets its own launch
 constexpr uint32_t kCmTileWords = 16;        // bitmap words (512 connections) per cm tile
@@ -157,7 +157,7 @@ void launch_direct(const DevState& s, const Work& w, const BatchIn& b, cudaStrea
 void launch_match(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st);
 void launch_plan(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st);
 void launch_offsets(const DevState& s, const Work& w, const BatchIn& b, bool has_direct, cudaStream_t st);
-// fused match + plan + offsets for N == kSmallCtrlConns and n_msgs <= kSmallCtrlMsgs (one cluster launch)
+// fused match + plan + offsets for N <= kSmallCtrlConns and n_msgs <= kSmallCtrlMsgs (one cluster launch)
 void launch_ctrl_small(const DevState& s, const Work& w, const BatchIn& b, bool has_direct, bool zero_stats,
                        BatchStats* publish, cudaStream_t st);
 void launch_pack(const DevState& s, const Work& w, const BatchIn& b, uint32_t variant, int n_sms, cudaStream_t st);

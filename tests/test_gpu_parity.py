@@ -4,6 +4,8 @@ order (integer/byte work — no tolerance).  Run with `pytest -m gpu` on a B200.
 """
 import random
 
+import numpy as np
+
 import pytest
 
 import scenarios
@@ -465,15 +467,28 @@ def test_connection_id_quarantined_until_batches_released(pcdn):
     e.close()
 
 
-@pytest.mark.parametrize("staged", [False, True])
-def test_small_engine_batch_sizes_across_the_fused_limit(pcdn, staged):
-    """an 8192-slot engine routes batches of <= 256 messages through the fused control kernel
-    (k_ctrl_small) and larger ones through the regular pipeline; both must agree with the oracle at
-    and around the limit (1, 2, 255, 256, 257, 700 messages; broadcasts, directs incl. a hot
-    recipient and unknown keys)"""
+@pytest.mark.parametrize("staged,max_conns", [(False, 8192), (True, 8192), (False, 20000), (False, 65536), (False, 65537)])
+def test_small_engine_batch_sizes_across_the_fused_limit(pcdn, staged, max_conns):
+    """engines with <= 65536 connection slots route batches of <= 256 messages through the fused
+    control kernel (k_ctrl_small: 1, 3 and 8 passes of 8192 connections here) and larger ones through
+    the regular pipeline; all must agree with the oracle at and around the limit (1, 2, 255, 256, 257,
+    700 messages; broadcasts, directs incl. a hot recipient and unknown keys).  65537 slots is the
+    first geometry that always takes the regular pipeline with the staged span table."""
     rng = random.Random(11)
-    w = World(pcdn, ring_bytes_per_conn=1 << 20, max_batch_msgs=1024, max_batch_bcast=1024,
-              flags=pcdn.FLAG_STAGED_SPANS if staged else 0)
+    w = World(pcdn, ring_bytes_per_conn=1 << 18, max_batch_msgs=1024, max_batch_bcast=1024, max_conns=max_conns,
+              max_keys=max(16384, max_conns + 2048), flags=pcdn.FLAG_STAGED_SPANS if staged else 0)
+    # connection ids are handed out densely: with the bulk loader the later 8192-connection blocks of a
+    # large engine get users too (topic 9 only, so they stay out of the checked traffic)
+    if max_conns > 8192:
+        n_fill = max_conns - 2000
+        fill = np.zeros((n_fill, 8), dtype=np.uint8)
+        fill[:, :4] = np.arange(n_fill, dtype=np.uint32).view(np.uint8).reshape(n_fill, 4)
+        fill[:, 7] = 0xEE
+        conns = w.e.add_users_bulk(fill, 8, np.full(n_fill, 9, dtype=np.uint16), np.arange(n_fill + 1, dtype=np.uint32))
+        for i in range(0, n_fill, max(1, n_fill // 40)):   # ... except a sample, known to the oracle, that also takes topic 8
+            k = fill[i].tobytes()
+            w.e.subscribe_user_to(k, [8])
+            w.map[int(conns[i])] = w.o.add_user(k, [9, 8])
     keys = [rng.getrandbits(64).to_bytes(8, "little") * 4 for _ in range(700)]
     for k in keys:
         w.add_user(k, [t for t in range(8) if rng.random() < (0.5 if t == 0 else 0.05)])
@@ -483,7 +498,7 @@ def test_small_engine_batch_sizes_across_the_fused_limit(pcdn, staged):
         for j in range(n):
             r = rng.random()
             if r < 0.4:
-                t = [rng.randrange(8)] + ([0] if rng.random() < 0.3 else [])
+                t = [rng.randrange(9)] + ([0] if rng.random() < 0.3 else [])
                 w.bcast(t, orc.broadcast_frame(t, payload(rng, rng.choice([0, 5, 300, 1500]))), rng.random() < 0.2)
             else:
                 rc = hot if r < 0.6 else rng.choice(keys) if r < 0.9 else b"nobody-home"
