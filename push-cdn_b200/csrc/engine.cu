@@ -96,6 +96,11 @@ struct Slot {
   // results
   BatchStats* h_stats = nullptr;  // pinned: final counters (after the pack)
   BatchStats* d_stats_pub = nullptr;  // direct publish: device alias of h_stats (mapped)
+  // span table / overflow list of this batch: written by the device straight into mapped host memory
+  // (few spans expected) or staged in HBM and copied out while the pack runs (up to 2 per connection)
+  bool spans_mapped = false;
+  Span* d_spans_map = nullptr; Span* d_spans_dev = nullptr;
+  uint32_t* d_ovf_map = nullptr; uint32_t* d_ovf_dev = nullptr;
   BatchStats* h_early = nullptr;  // pinned: counters as of k_offsets (n_spans, n_overflow are final there)
   Span* h_spans = nullptr;        // pinned
   uint32_t* h_overflow = nullptr; // pinned
@@ -244,6 +249,13 @@ int launch_pipeline(pcdn_engine* e, Slot& s, uint32_t n_direct) {
   // latency path of the smallest geometry: match + plan + offsets in one cluster launch that also
   // zeroes / publishes the counters (kernels.cu: k_ctrl_small)
   const bool fused = dp && e->geo.N <= kSmallCtrlConns && s.in.n_msgs <= kSmallCtrlMsgs;
+  // Spans go straight into mapped host memory when few are expected (16-byte PCIe writes: a table
+  // of 16 K spans measured 20 us slower than the staged copy): the smallest geometry, or a batch
+  // without broadcasts and with few messages (at most one span per message).  Otherwise they are staged in HBM and copied
+  // out with one DMA of the exact size while the pack runs.
+  s.spans_mapped = dp && (e->geo.N <= 8192 || (s.in.n_bcast == 0 && s.in.n_msgs <= 4096));
+  s.w.spans = s.spans_mapped ? s.d_spans_map : s.d_spans_dev;
+  s.w.overflow = s.spans_mapped ? s.d_ovf_map : s.d_ovf_dev;
   const bool zero_in_kernel = fused && !s.devparse;  // (k_parse counts into the batch counters before the fused kernel)
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[0], st));
   if (!zero_in_kernel) launch_batch_begin(e->dev, s.w, s.in, has_direct, st);
@@ -260,7 +272,7 @@ int launch_pipeline(pcdn_engine* e, Slot& s, uint32_t n_direct) {
     launch_offsets(e->dev, s.w, s.in, has_direct, st);
     if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[3], st));
   }
-  if (!dp) {
+  if (!s.spans_mapped) {
     CUDA_TRY(cudaEventRecord(s.ev_ctrl, st));
     // the span table is final once k_offsets is done: its counters go home while the pack runs
     CUDA_TRY(cudaStreamWaitEvent(cs, s.ev_ctrl, 0));
@@ -269,8 +281,8 @@ int launch_pipeline(pcdn_engine* e, Slot& s, uint32_t n_direct) {
     // pack on its own stream (packs of successive batches stay ordered among themselves)
     if (ps != st) CUDA_TRY(cudaStreamWaitEvent(ps, s.ev_ctrl, 0));
   }
-  // (direct publish: k_offsets wrote spans / overflow into mapped host memory; everything stays
-  //  on one stream and the host waits for ev_done only)
+  // (mapped spans: k_offsets wrote spans / overflow into host memory; everything stays on one
+  //  stream and the host waits for ev_done only)
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[4], ps));
   launch_pack(e->dev, s.w, s.in, e->cfg.pack_variant, e->n_sms, ps);
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[5], ps));
@@ -568,18 +580,19 @@ int init_device(pcdn_engine* e) {
     CUDA_TRY(cudaMemsetAsync(w.dstamp, 0, ((size_t)g.N + 1) * 4, e->stream));
     w.stamp = 0;
     DEV_ALLOC(w.batch_units, g.N);
+    DEV_ALLOC(s.d_spans_dev, (size_t)2 * g.N);
+    DEV_ALLOC(s.d_ovf_dev, g.N);
     if (e->direct_publish) {
-      int _rc = pin_alloc_mapped(&s.h_spans, &w.spans, (size_t)2 * g.N);
+      int _rc = pin_alloc_mapped(&s.h_spans, &s.d_spans_map, (size_t)2 * g.N);
       if (_rc) return _rc;
       e->pin_allocs.push_back((void*)s.h_spans);
-      if ((_rc = pin_alloc_mapped(&s.h_overflow, &w.overflow, (size_t)g.N))) return _rc;
+      if ((_rc = pin_alloc_mapped(&s.h_overflow, &s.d_ovf_map, (size_t)g.N))) return _rc;
       e->pin_allocs.push_back((void*)s.h_overflow);
     } else {
-      DEV_ALLOC(w.spans, (size_t)2 * g.N);
-      DEV_ALLOC(w.overflow, g.N);
       PIN_ALLOC(s.h_spans, (size_t)2 * g.max_conns);
       PIN_ALLOC(s.h_overflow, g.max_conns);
     }
+    w.spans = s.d_spans_dev; w.overflow = s.d_ovf_dev;
     DEV_ALLOC(w.msg_status, M);
     PIN_ALLOC(s.h_msg_status, M);
     DEV_ALLOC(w.stats, 1);
@@ -1169,7 +1182,7 @@ int pcdn_poll(pcdn_engine* e, uint64_t batch_id, pcdn_batch_result* out, int blo
   // The blocking waits happen OUTSIDE the engine lock, so ingest threads keep appending to the next
   // batch while an egress thread waits for this one (one poller per batch).
   cudaEvent_t ev_early = nullptr, ev_done = nullptr;
-  bool wait = false;
+  bool wait = false, mapped = false;
   {
     std::lock_guard<std::mutex> g(e->mu);
     Slot* s = find_slot(e, batch_id);
@@ -1180,15 +1193,15 @@ int pcdn_poll(pcdn_engine* e, uint64_t batch_id, pcdn_batch_result* out, int blo
         if (q == cudaErrorNotReady) return 1;
         CUDA_TRY(q);
       }
-      ev_early = s->ev_early; ev_done = s->ev_done; wait = true;
+      ev_early = s->ev_early; ev_done = s->ev_done; wait = true; mapped = s->spans_mapped;
     }
   }
   uint32_t nsp = 0, nov = 0;
   bool devparse = false;
   if (wait) {
     // 1. counters as of k_offsets → exact size of the span table; its D2H overlaps the pack
-    //    (direct publish: the table is already in host memory when ev_done fires)
-    if (!e->direct_publish) {
+    //    (mapped spans: the table is already in host memory when ev_done fires)
+    if (!mapped) {
       CUDA_TRY(cudaEventSynchronize(ev_early));
       std::lock_guard<std::mutex> g(e->mu);
       Slot* s = find_slot(e, batch_id);
