@@ -106,9 +106,10 @@ enum {
    * path.  Deviation: a malformed / all-topics-invalid frame is reported after the batch instead of
    * synchronously, so later frames of that sender inside the same batch are still routed. */
   PCDN_FLAG_DEVICE_PARSE = 1,
-  /* Engines with <= 65536 connection slots let the offsets kernel write the span table and the
-   * overflow list straight into mapped pinned host memory (no D2H copies, one event to wait for:
-   * the latency path of small brokers).  This flag forces the staged path of large engines (span
+  /* Engines with <= 65536 connection slots take the latency path for small batches: one fused
+   * control launch, counters published into mapped pinned host memory, and the span table /
+   * overflow list written there directly by the offsets kernel when few spans are expected
+   * (no D2H copies, one event to wait for).  This flag forces the path of large engines (span
    * table built in HBM, copied out while the pack is still running) regardless of size. */
   PCDN_FLAG_STAGED_SPANS = 2,
   /* Egress hand-off without a device→host copy: the per-connection rings live in
