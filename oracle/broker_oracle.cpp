@@ -4,7 +4,7 @@
 //
 // Each function cites the reference file:line it restates (paths relative to the reference repo).
 // The reference cannot be built here (Rust; no cargo/rustc), so this restatement is pinned by
-// replaying the reference's own tests against it (tests/test_oracle_reference_scenarios.py):
+// replaying the reference's own tests against it (tests/test_oracle_reference.py, tests/scenarios.py):
 //   cdn-broker/src/tests/broadcast.rs:26-167, cdn-broker/src/tests/direct.rs:27-173,
 //   cdn-broker/src/connections/broadcast/relational_map.rs:132-346,
 //   cdn-broker/src/connections/versioned_map.rs:277-376, cdn-broker/src/connections/mod.rs:410-526,
