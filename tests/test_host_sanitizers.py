@@ -46,3 +46,23 @@ def test_host_code_under_asan_ubsan(tmp_path):
     r = subprocess.run([str(exe), str(corpus), "120000", "7"], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, (r.stdout + r.stderr)[-6000:]
     assert "host_fuzz ok" in r.stdout
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc not available")
+def test_state_calls_under_tsan(tmp_path):
+    """SURVEY 8b threading contract: state calls and lookups from many host threads.  The library is
+    rebuilt with ThreadSanitizer (host code of engine.cu / kernels.cu included) and a C driver runs
+    8 threads x 20 000 calls against a host-only engine; any data race report fails the test."""
+    exe = tmp_path / "tsan_state_calls"
+    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "kernels.cu", "host_state.cpp", "frame_parse.cpp")]
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-g", "-std=c++17",
+           "-Xcompiler", "-fPIC,-pthread,-fsanitize=thread", "-I", os.path.join(ROOT, "include"), *srcs,
+           os.path.join(ROOT, "tests", "cpp", "tsan_state_calls.c"), "-o", str(exe), "-lpthread", "-ltsan"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0 and "tsan" in r.stderr.lower():
+        pytest.skip("libtsan not available: " + r.stderr[-300:])
+    assert r.returncode == 0, r.stderr[-4000:]
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0:exitcode=66")
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=900, env=env)
+    assert "ThreadSanitizer" not in r.stderr, r.stderr[-6000:]
+    assert r.returncode == 0 and "tsan driver ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
