@@ -986,7 +986,8 @@ int receive_frames_locked(pcdn_engine* e, const pcdn_frame* frames, uint32_t n, 
       const pcdn_frame& f = frames[i];
       FramePlan& p = plan[i];
       p.kind = -1; p.rc = 0; p.f0_off = p.f0_len = p.ntopics = 0;
-      if (f.raw_len > 0x1FFFFFFFu || align_up(4 + (size_t)f.raw_len, 16) + 64 > c.max_batch_bytes) continue;  // sequential path reports it
+      if (f.raw_len > 0x1FFFFFFFu || align_up(4 + (size_t)f.raw_len, 16) + 64 > c.max_batch_bytes ||
+          (c.global_memory_pool_size && f.raw_len > c.global_memory_pool_size)) continue;  // sequential path reports it (PCDN_EINVAL / PCDN_ENOSPC for that frame)
       if (dev) {
         const int k = peek_kind_core(f.raw, f.raw_len);
         if (k == PCDN_KIND_DIRECT || k == PCDN_KIND_BROADCAST) p.kind = (int8_t)k;
@@ -1116,19 +1117,67 @@ int pcdn_flush(pcdn_engine* e, uint64_t* batch_id) {
   GUARD_END
 }
 
+// All-or-nothing check of an explicit batch against every per-batch capacity, BEFORE anything is
+// staged: a refused pcdn_submit leaves no message behind that a later flush would deliver (and a
+// retry would deliver twice).
+static int validate_explicit_batch(pcdn_engine* e, const pcdn_msg* msgs, uint32_t n) {
+  const pcdn_config& c = e->cfg;
+  if (!e->has_device) return fail(PCDN_ENODEV, "host-only engine cannot route messages");
+  if (n > c.max_batch_msgs) return fail(PCDN_ENOSPC, "batch larger than max_batch_msgs");
+  if (n && !msgs) return fail(PCDN_EINVAL, "null message array");
+  uint64_t bytes = 0, topics = 0, ingress = 0, nb = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const pcdn_msg& m = msgs[i];
+    if (m.kind != PCDN_KIND_BROADCAST && m.kind != PCDN_KIND_DIRECT)
+      return fail(PCDN_EINVAL, "message " + std::to_string(i) + ": kind must be broadcast or direct");
+    if (m.flags & ~(uint8_t)PCDN_TO_USERS_ONLY)
+      return fail(PCDN_EINVAL, "message " + std::to_string(i) + ": unknown bits in pcdn_msg.flags");
+    if (m.raw_len > 0x1FFFFFFFu) return fail(PCDN_EINVAL, "message larger than MAX_MESSAGE_SIZE (cdn-proto/src/lib.rs:25)");
+    if ((m.raw_len && !m.raw) || (m.kind == PCDN_KIND_BROADCAST && m.n_topics && !m.topics) ||
+        (m.kind == PCDN_KIND_DIRECT && m.recipient_len && !m.recipient))
+      return fail(PCDN_EINVAL, "message " + std::to_string(i) + ": null pointer with non-zero length");
+    if (c.global_memory_pool_size && m.raw_len > c.global_memory_pool_size)
+      return fail(PCDN_EINVAL, "message larger than the global memory pool");
+    bytes += align_up(4 + (size_t)m.raw_len, 16);
+    if (m.kind == PCDN_KIND_DIRECT) bytes += align_up(std::min<uint32_t>(m.recipient_len, c.max_key_len), 16);  // worst case: key staged beside the frame
+    else { nb++; topics += m.n_topics; }
+    ingress += m.raw_len;
+  }
+  if (bytes + 64 > c.max_batch_bytes) return fail(PCDN_ENOSPC, "batch does not fit max_batch_bytes");
+  if (nb > c.max_batch_bcast) return fail(PCDN_ENOSPC, "batch has more broadcasts than max_batch_bcast");
+  if (topics > e->topics_cap) return fail(PCDN_ENOSPC, "batch has more topic entries than the descriptor block holds");
+  if (c.global_memory_pool_size && e->inflight_bytes + ingress > c.global_memory_pool_size)
+    return fail(PCDN_EAGAIN, "global memory pool exhausted: release a batch first");
+  return 0;
+}
+
+// drop the open batch (nothing of it has been launched) and give its permits back
+static void abandon_open(pcdn_engine* e) {
+  if (e->open_slot < 0) return;
+  Slot& s = e->slots[e->open_slot];
+  e->inflight_bytes -= std::min(e->inflight_bytes, s.ingress_bytes);
+  e->stats.bytes_in -= std::min(e->stats.bytes_in, s.ingress_bytes);
+  slot_reset_open(s);
+  s.state = SLOT_FREE;
+  e->open_slot = -1;
+}
+
 int pcdn_submit(pcdn_engine* e, const pcdn_msg* msgs, uint32_t n, uint64_t* batch_id) {
   GUARD_BEGIN
   LOCK;
   if (batch_id) *batch_id = 0;
-  int rc = flush_open(e, nullptr);  // keep explicit batches separate from the implicit open one
+  int rc = validate_explicit_batch(e, msgs, n);  // before anything is staged or launched
   if (rc) return rc;
-  if (n > e->cfg.max_batch_msgs) return fail(PCDN_ENOSPC, "batch larger than max_batch_msgs");
+  rc = flush_open(e, nullptr);  // keep explicit batches separate from the implicit open one
+  if (rc) return rc;
+  if (n == 0) return 0;
+  if ((rc = acquire_open_slot(e))) return rc;  // PCDN_EAGAIN: nothing staged
   for (uint32_t i = 0; i < n; i++) {
     const pcdn_msg& m = msgs[i];
     uint64_t before = e->next_batch_id;
     rc = append_msg(e, m.kind, m.flags, m.topics, m.n_topics, m.recipient, m.recipient_len, m.raw, m.raw_len);
-    if (rc) return rc;
-    if (e->next_batch_id != before) return fail(PCDN_ENOSPC, "batch exceeded a per-batch capacity and was split");
+    if (rc == 0 && e->next_batch_id != before) rc = fail(PCDN_ENOSPC, "batch exceeded a per-batch capacity and was split");
+    if (rc) { abandon_open(e); return rc; }  // unreachable after validation; never leave a half batch open
   }
   return flush_open(e, batch_id);
   GUARD_END

@@ -82,7 +82,10 @@ bool HostTables::route_find(const uint8_t* key, uint32_t len, uint32_t* route) c
 }
 
 int HostTables::place(CuckooEntry e, uint32_t bucket) {
-  // random-walk cuckoo insertion; the alternate bucket depends on (bucket, tag) only
+  // random-walk cuckoo insertion; the alternate bucket depends on (bucket, tag) only.  Every eviction
+  // is logged so that a walk that ends without a free slot can be undone: a failed insert must not
+  // leave some OTHER key (the last victim) without a slot.
+  std::vector<std::pair<uint32_t, CuckooEntry>> undo;
   for (int kick = 0; kick < 512; kick++) {
     uint32_t alt = alt_bucket(bucket, e.tag, g.bucket_mask);
     for (uint32_t b : {bucket, alt})
@@ -92,12 +95,14 @@ int HostTables::place(CuckooEntry e, uint32_t bucket) {
     kick_rng_ = kick_rng_ * 1664525u + 1013904223u;
     uint32_t victim = alt * 4 + ((kick_rng_ >> 16) & 3);
     CuckooEntry v = cuckoo[victim];
+    undo.emplace_back(victim, v);
     write_slot(victim, e);
     e = v;
     bucket = alt;  // the victim lived in `alt`; its other choice is alt_bucket(alt, v.tag)
   }
-  // Could not place `e` (an entry, possibly not the inserted one, is homeless).  Callers size the
-  // table at <= 50 % load where this is not reached in practice; report it loudly.
+  // Could not place `e`.  Callers size the table at <= 50 % load where this is not reached in
+  // practice; put every evicted entry back where it was (newest first) and report it loudly.
+  for (size_t i = undo.size(); i-- > 0;) write_slot(undo[i].first, undo[i].second);
   return PCDN_ENOSPC;
 }
 
@@ -120,6 +125,7 @@ int HostTables::route_upsert(const uint8_t* key, uint32_t len, uint32_t route) {
   CuckooEntry e{key_tag(h), ks, route, len};
   int rc = place(e, key_bucket(h, g.bucket_mask));
   if (rc == 0) n_keys_++;
+  else free_key_slots_.push_back(ks);  // the key slot goes back (its bytes are never referenced)
   return rc;
 }
 
@@ -209,6 +215,9 @@ void Connections::dm_modify_local(const std::string& key, bool has, uint32_t own
 int Connections::update_route(const std::string& key) {
   const uint8_t* k = (const uint8_t*)key.data();
   uint32_t len = (uint32_t)key.size();
+  // keys longer than max_key_len cannot be connected users (add_user refuses them) and have no slot
+  // in the key arena: they live in the CRDT map only (sync parity) and never get a device route
+  if (len > t_.g.max_key_len) return 0;
   auto it = direct_map_.find(key);
   if (it == direct_map_.end() || !it->second.has) { t_.route_erase(k, len); return 0; }
   if (it->second.owner == 0) {
@@ -339,6 +348,14 @@ int Connections::add_broker(const char* ident, uint32_t* conn) {
   int rc = owner_id(bi, &owner);
   if (rc) return rc;
   if (owner == 0) return PCDN_EINVAL;  // a broker never connects to itself (heartbeat.rs:66-70)
+  {  // refuse BEFORE dropping the existing connection when no id could be handed out afterwards (as add_user)
+    const bool quarantining = oldest_unreleased <= fence_now;
+    const bool reconnect = brokers_.count(id) != 0;
+    const bool have = !free_conns_.empty() || next_conn_ < t_.g.max_conns ||
+                      (!quarantine_.empty() && quarantine_.front().second < oldest_unreleased) ||
+                      (reconnect && !quarantining);
+    if (!have) return (quarantine_.empty() && !reconnect) ? PCDN_ENOSPC : PCDN_EAGAIN;
+  }
   remove_broker(ident);
   uint32_t c;
   if ((rc = alloc_conn(CONN_BROKER, &c))) return rc;
@@ -387,14 +404,26 @@ int Connections::unsubscribe_broker_from(const char* ident, const uint16_t* topi
 int Connections::apply_user_sync(const char* remote_identity, const std::vector<UserSyncEntry>& es) {
   BrokerIdent remote = BrokerIdent::parse(remote_identity);
   bool remote_wins_ties = remote > identity_;
-  std::vector<std::string> changed;
-  for (const UserSyncEntry& e : es) {
-    if (e.key.size() > t_.g.max_key_len) return PCDN_EKEYLEN;
-    uint32_t owner = 0;
-    if (e.has_owner) {
-      int rc = owner_id(BrokerIdent::parse(e.owner.c_str()), &owner);
-      if (rc) return rc;
+  // Resolve every owner BEFORE touching the map: the only failure that can refuse the merge as a
+  // whole (owner table full) must happen while nothing has changed.  The reference's merge cannot
+  // fail at all (versioned_map.rs:202-269), so from here on every entry is merged and every changed
+  // key gets its remove_user (mod.rs:157-161), whatever happens to an individual device route.
+  std::vector<uint32_t> owners(es.size(), 0);
+  {
+    const size_t owners_before = owners_.size();
+    for (size_t i = 0; i < es.size(); i++) {
+      if (!es[i].has_owner) continue;
+      int rc = owner_id(BrokerIdent::parse(es[i].owner.c_str()), &owners[i]);
+      if (rc) {  // undo the owner ids handed out by this call
+        while (owners_.size() > owners_before) { owner_ids_.erase(owners_.back().str()); owners_.pop_back(); }
+        return rc;
+      }
     }
+  }
+  std::vector<std::string> changed;
+  for (size_t i = 0; i < es.size(); i++) {
+    const UserSyncEntry& e = es[i];
+    const uint32_t owner = owners[i];
     auto it = direct_map_.find(e.key);
     if (it != direct_map_.end()) {
       bool take = e.version > it->second.version ||
@@ -412,7 +441,7 @@ int Connections::apply_user_sync(const char* remote_identity, const std::vector<
   int rc = 0;
   for (const std::string& k : changed) {
     int r = remove_user(k);  // ends with update_route(k)
-    if (r && !rc) rc = r;
+    if (r && !rc) rc = r;    // (route table full: the CRDT state is still complete and consistent)
   }
   return rc;
 }

@@ -252,3 +252,38 @@ def test_state_calls_from_many_threads(pcdn):
         for i in (1, 2, 4, 1498):
             assert e.debug_route(bytes([t]) + i.to_bytes(4, "little"))[0] == 1
         assert e.debug_route(bytes([t]) + (3).to_bytes(4, "little")) == (0, -1)
+
+
+def test_apply_user_sync_overlong_key_does_not_tear_the_merge(pcdn):
+    """a peer's sync holding one key longer than max_key_len must not stop the merge half
+    way.  VersionedMap::merge (versioned_map.rs:202-269) cannot fail and apply_user_sync always
+    finishes with remove_user for every changed key (connections/mod.rs:157-161)."""
+    e = pcdn.Engine(device=-1, max_conns=64, max_keys=256, max_key_len=16, identity="a/a")
+    o = orc.Oracle("a/a")
+    ec, oc = e.add_user(b"alice", [1, 2]), o.add_user(b"alice", [1, 2])
+    long_key = b"L" * 40
+    sync = [(b"alice", 5, "b/b"), (long_key, 3, "b/b"), (b"carol", 2, "b/b")]
+    e.apply_user_sync("b/b", sync)   # no error: the over-long key simply has no device route
+    o.apply_user_sync("b/b", sync)
+    # alice moved to b/b: kicked locally (route REMOTE, no subscriptions, not a user any more)
+    assert e.debug_route(b"alice")[0] == 2 and o.route(b"alice")[0] == 2
+    assert e.debug_interested([1, 2]) == [] and o.interested([1, 2], False) == []
+    assert e.num_users()[0] == 0 == o.num_users()
+    assert e.debug_route(b"carol")[0] == 2
+    # the CRDT map holds all three entries, exactly like the reference's
+    got = sorted(e.get_user_sync(full=True))
+    assert got == sorted([(b"alice", 5, "b/b"), (b"carol", 2, "b/b"), (long_key, 3, "b/b")])
+    assert e.debug_route(long_key)[0] == 0   # never routable on the device (documented deviation 2)
+
+
+def test_add_broker_reconnect_refused_before_anything_changes(pcdn):
+    """add_broker with a full id space must refuse BEFORE dropping the existing broker."""
+    e = pcdn.Engine(device=-1, max_conns=2, max_keys=64, identity="a/a")
+    e.add_user(b"u0", [0])
+    c = e.add_broker("b/b")
+    e.subscribe_broker_to("b/b", [3])
+    with pytest.raises(pcdn.PcdnError) as ei:
+        e.add_broker("c/c")          # id space full: refused
+    assert ei.value.code == -5
+    assert e.debug_interested([3]) == [c] and e.num_users() == (1, 1)
+    assert e.add_broker("b/b") == c  # a reconnect reuses its own id (no batch in flight)
