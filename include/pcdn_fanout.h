@@ -18,6 +18,14 @@
  *
  * There is NO CPU data path behind this ABI: with `device < 0` the engine is a host-only state
  * mirror (used by CPU unit tests of the table logic) and every data call fails with PCDN_ENODEV.
+ *
+ * Several GPUs: ONE engine can spread its connections over the GPUs of a box
+ * (pcdn_config.n_devices / devices).  Every state and data-in call below is unchanged — the engine
+ * is still one logical broker with one connection-id space — and the library itself replicates
+ * each batch to all GPUs (one ncclBroadcast over NVLink per batch, issued by the library on a side
+ * stream) and lets every GPU fan out to its own connection shard.  The reference analogue is the
+ * broker -> peer-broker forward with to_users_only (cdn-broker/src/tasks/broker/handler.rs:156-160,
+ * 262-271): a message crosses once, each shard delivers to its own users.
  */
 #ifndef PCDN_FANOUT_H
 #define PCDN_FANOUT_H
@@ -29,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PCDN_ABI_VERSION 1u
+#define PCDN_ABI_VERSION 2u
 
 /* ---- status codes ------------------------------------------------------------------------- */
 enum {
@@ -90,12 +98,41 @@ typedef struct pcdn_config {
   const char* identity;         /* this broker's BrokerIdentifier string "public/private"       */
   uint32_t pack_variant;        /* 0 = default; see DESIGN.md (kernel selection for profiling)  */
   uint32_t flags;               /* PCDN_FLAG_*                                                  */
+  /* ---- connection shards over several GPUs ---------------------------------------
+   * n_devices > 1 (or world_shards > 1): `max_conns`, `ring_bytes_per_conn` and the batch capacities
+   * are PER SHARD; `max_keys`, `max_topics` describe the whole broker (the direct map is replicated
+   * on every GPU: a direct message resolves identically everywhere and is packed by the GPU that
+   * owns the target connection).  Connection ids are global: id = shard * shard_stride + local, a
+   * new connection goes to the least-loaded shard (the marshal's policy for brokers,
+   * cdn-proto/src/connection/auth/marshal.rs:108-118); pcdn_shard_info() gives shard_stride.
+   * With n_devices >= 1 `device` is ignored and `stream` (optional) is the main stream of devices[0]. */
+  uint32_t n_devices;           /* 0 = single device `device`; else number of entries of `devices`          */
+  uint32_t ingest;              /* PCDN_INGEST_*: how a batch reaches every shard                           */
+  const int32_t* devices;       /* CUDA ordinals; an ordinal may repeat (shards sharing one GPU: PCDN_INGEST_HOST only) */
+  /* Multi-process groups (one process per GPU, e.g. torchrun): every process creates its engine with
+   * the SAME config except devices/first_shard and then issues the SAME sequence of state and
+   * data-in calls with the same arguments (SPMD, like the ranks of an NCCL job).  Each process keeps
+   * the whole routing state, applies table updates to its own GPUs only, and polls / reads its own
+   * shards.  The process that owns global shard 0 is the ingest root: only ITS copy of a batch's
+   * bytes is used — it goes to every GPU of the group with the ncclBroadcast.                      */
+  uint32_t world_shards;        /* total shards of the broker over all processes (0 = n_devices)            */
+  uint32_t first_shard;         /* global index of devices[0]                                               */
+  const void* nccl_unique_id;   /* world_shards > n_devices: the 128-byte id from pcdn_nccl_unique_id(), identical in every process */
   uint64_t global_memory_pool_size; /* Limiter analogue (cdn-proto/src/connection/limiter/mod.rs:56-68,
                                  * cdn-broker/src/binaries/broker.rs:71-72 default 1 GiB): bytes of inbound frames
                                  * that may be in flight (accepted, their batch not yet released); 0 = unlimited.
                                  * The reference awaits the semaphore; here a frame that does not fit is refused
                                  * with PCDN_EAGAIN and the caller retries after releasing a batch. */
 } pcdn_config;
+
+/* pcdn_config.ingest — sharded engines: how the staged batch gets from the host into every GPU */
+enum {
+  PCDN_INGEST_NCCL = 0, /* host -> GPU of shard 0 (one H2D), then ONE ncclBroadcast over NVLink to all shards,
+                         * issued by the library on a side stream so it overlaps the previous batch's pack
+                         * (default; libnccl.so.2 is bound at run time and its absence is PCDN_ENODEV)  */
+  PCDN_INGEST_HOST = 1  /* every shard copies the batch from pinned host memory itself (no NCCL needed;
+                         * also the only mode for shards that share a GPU)                              */
+};
 
 /* pcdn_config.flags */
 enum {
@@ -315,6 +352,31 @@ int pcdn_read(pcdn_engine* e, pcdn_conn conn, uint32_t ring_off, uint32_t len, v
 /* The host has written every span of the batch: free its ring space and its slot.  This is the
  * analogue of dropping the last `Bytes` clone (limiter/pool.rs:44-52).  In order, oldest first. */
 int pcdn_release_batch(pcdn_engine* e, uint64_t batch_id);
+
+/* ---- connection shards (n_devices > 1) ------------------------------------------------------ */
+/* A fresh ncclUniqueId (128 bytes) for pcdn_config.nccl_unique_id: one process generates it and
+ * hands it to the others by whatever channel the host has (torch.distributed store, a file, MPI). */
+#define PCDN_NCCL_UNIQUE_ID_BYTES 128
+int pcdn_nccl_unique_id(void* out128);
+typedef struct pcdn_shard_desc {
+  uint32_t global_index;  /* shard number inside the broker (0 .. world_shards-1)                     */
+  int32_t device;         /* CUDA ordinal                                                            */
+  pcdn_conn conn_base;    /* ids [conn_base, conn_base + shard_stride) belong to this shard           */
+  uint32_t shard_stride;  /* id range per shard (max_conns rounded up to a multiple of 8192)         */
+  void* rings_dev;        /* device address of this shard's rings [max_conns][ring_bytes_per_conn]    */
+  const void* rings_host; /* PCDN_FLAG_HOST_RINGS: host address of the same rings, else NULL          */
+  uint64_t ring_bytes;
+  uint32_t n_conns;       /* connections currently living on this shard                               */
+  uint32_t nccl_ranks;    /* size of the ingest communicator this shard belongs to (0 = none)        */
+} pcdn_shard_desc;
+/* number of shards THIS process drives (1 for a single-GPU engine) */
+int pcdn_num_shards(pcdn_engine* e, uint32_t* n_local, uint32_t* n_world);
+int pcdn_shard_info(pcdn_engine* e, uint32_t local_shard, pcdn_shard_desc* out);
+/* pcdn_poll for ONE local shard: spans (global connection ids, this shard's connections only) are
+ * read in place from that shard's pinned result buffer — what the shard's egress writer uses.
+ * pcdn_poll itself waits for all local shards and returns the summed counters with the shards'
+ * span tables concatenated into one engine-owned array (a host copy: convenience, not the fast path). */
+int pcdn_poll_shard(pcdn_engine* e, uint64_t batch_id, uint32_t local_shard, pcdn_batch_result* out, int block);
 
 /* ---- introspection (tests, metrics: cdn-proto/src/connection/metrics.rs:12-28) ------------- */
 int pcdn_get_stats(pcdn_engine* e, pcdn_stats* out);

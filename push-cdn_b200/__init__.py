@@ -24,8 +24,8 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpcdn_fanout.so")
 INCLUDE = os.path.join(_ROOT, "include")
 
-SOURCES = ["engine.cu", "kernels.cu", "host_state.cpp", "frame_parse.cpp"]
-HEADERS = ["kernels.cuh", "host_state.h", "frame_parse.h", "frame_parse_core.h", "hash.h"]
+SOURCES = ["engine.cu", "kernels.cu", "host_state.cpp", "frame_parse.cpp", "nccl_dl.cpp"]
+HEADERS = ["kernels.cuh", "host_state.h", "frame_parse.h", "frame_parse_core.h", "hash.h", "nccl_dl.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-pthread", "-shared",
@@ -36,6 +36,7 @@ TO_USERS_ONLY = 1
 FLAG_DEVICE_PARSE = 1
 FLAG_HOST_RINGS = 4     # rings in mapped pinned host memory: spans are readable in place (egress hand-off)
 FLAG_STAGED_SPANS = 2   # force the large-engine span path (table in HBM + D2H) on a small engine
+INGEST_NCCL, INGEST_HOST = 0, 1   # sharded engines: NCCL broadcast over NVLink | every shard copies from host
 RECORD_ALIGN = 32
 CONN_NONE = 0xFFFFFFFF
 
@@ -68,7 +69,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not os.path.exists(nvcc):
         nvcc = "nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd, cwd=CSRC)
@@ -82,7 +83,10 @@ class Config(C.Structure):
         ("max_batch_msgs", C.c_uint32), ("max_batch_bcast", C.c_uint32), ("max_batch_bytes", C.c_uint64),
         ("max_batch_deliveries", C.c_uint64), ("batch_slots", C.c_uint32), ("n_valid_topics", C.c_uint32),
         ("hash_seed", C.c_uint64), ("stream", C.c_void_p), ("identity", C.c_char_p), ("pack_variant", C.c_uint32),
-        ("flags", C.c_uint32), ("global_memory_pool_size", C.c_uint64),
+        ("flags", C.c_uint32),
+        ("n_devices", C.c_uint32), ("ingest", C.c_uint32), ("devices", C.POINTER(C.c_int32)),
+        ("world_shards", C.c_uint32), ("first_shard", C.c_uint32), ("nccl_unique_id", C.c_void_p),
+        ("global_memory_pool_size", C.c_uint64),
     ]
 
 
@@ -113,6 +117,12 @@ class DeviceBatch(C.Structure):
         ("aux_off", C.c_void_p), ("aux_len", C.c_void_p), ("topics", C.c_void_p), ("n_topics_total", C.c_uint32),
         ("bcast_index", C.c_void_p),
     ]
+
+
+class ShardDesc(C.Structure):
+    _fields_ = [("global_index", C.c_uint32), ("device", C.c_int32), ("conn_base", C.c_uint32), ("shard_stride", C.c_uint32),
+                ("rings_dev", C.c_void_p), ("rings_host", C.c_void_p), ("ring_bytes", C.c_uint64), ("n_conns", C.c_uint32),
+                ("nccl_ranks", C.c_uint32)]
 
 
 class Stats(C.Structure):
@@ -177,6 +187,10 @@ ABI = {
     "pcdn_poll": (_ci, [_vp, _u64, C.POINTER(BatchResult), _ci]),
     "pcdn_read": (_ci, [_vp, _u32, _u32, _u32, _vp]),
     "pcdn_release_batch": (_ci, [_vp, _u64]),
+    "pcdn_nccl_unique_id": (_ci, [_vp]),
+    "pcdn_num_shards": (_ci, [_vp, C.POINTER(_u32), C.POINTER(_u32)]),
+    "pcdn_shard_info": (_ci, [_vp, _u32, C.POINTER(ShardDesc)]),
+    "pcdn_poll_shard": (_ci, [_vp, _u64, _u32, C.POINTER(BatchResult), _ci]),
     "pcdn_get_stats": (_ci, [_vp, C.POINTER(Stats)]),
     "pcdn_set_timing": (_ci, [_vp, _ci]),
     "pcdn_ring_info": (_ci, [_vp, C.POINTER(_vp), C.POINTER(_u64), C.POINTER(_u32)]),
@@ -203,9 +217,18 @@ def lib() -> C.CDLL:
             f = getattr(L, name)
             f.restype = res
             f.argtypes = args
-        assert L.pcdn_abi_version() == 1
+        assert L.pcdn_abi_version() == 2
         _lib = L
     return _lib
+
+
+def nccl_unique_id() -> bytes:
+    """a fresh 128-byte ncclUniqueId for multi-process sharded engines (one process makes it, all use it)"""
+    buf = C.create_string_buffer(128)
+    rc = lib().pcdn_nccl_unique_id(C.cast(buf, C.c_void_p))
+    if rc < 0:
+        raise PcdnError(rc, lib().pcdn_last_error().decode())
+    return buf.raw
 
 
 def _t16(topics: Iterable[int]):
@@ -227,7 +250,10 @@ def parse_frame(raw: bytes):
 class Engine:
     """One fan-out engine on one CUDA device (or a host-only state mirror with ``device=-1``)."""
 
-    def __init__(self, device: int = 0, stream: Optional[int] = None, identity: str = "/", **kw):
+    def __init__(self, device: int = 0, stream: Optional[int] = None, identity: str = "/",
+                 devices: Optional[Sequence[int]] = None, nccl_unique_id: Optional[bytes] = None, **kw):
+        """devices=[0, 1, ...]: one connection shard per listed GPU (the engine stays one logical
+        broker); world_shards / first_shard / nccl_unique_id: multi-process groups (see the header)."""
         self.L = lib()
         cfg = Config()
         self.L.pcdn_config_default(C.byref(cfg))
@@ -236,6 +262,14 @@ class Engine:
         cfg.identity = self._identity
         if stream is not None:
             cfg.stream = stream
+        if devices is not None:
+            self._devices = (C.c_int32 * len(devices))(*devices)
+            cfg.n_devices = len(devices)
+            cfg.devices = self._devices
+        if nccl_unique_id is not None:
+            assert len(nccl_unique_id) == 128
+            self._uid = C.create_string_buffer(nccl_unique_id, 128)
+            cfg.nccl_unique_id = C.cast(self._uid, C.c_void_p)
         for k, v in kw.items():
             if not hasattr(cfg, k):
                 raise TypeError(f"unknown config field {k}")
@@ -244,6 +278,28 @@ class Engine:
         h = C.c_void_p()
         self._chk(self.L.pcdn_create(C.byref(cfg), C.byref(h)))
         self.h = h
+        self._shards = None
+
+    # ---- connection shards --------------------------------------------------------------------
+    def num_shards(self) -> Tuple[int, int]:
+        a, b = C.c_uint32(), C.c_uint32()
+        self._chk(self.L.pcdn_num_shards(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def shard_info(self, local_shard: int) -> ShardDesc:
+        d = ShardDesc()
+        self._chk(self.L.pcdn_shard_info(self.h, local_shard, C.byref(d)))
+        return d
+
+    def shards(self) -> List[ShardDesc]:
+        if self._shards is None:
+            self._shards = [self.shard_info(i) for i in range(max(1, self.num_shards()[0]))]
+        return self._shards
+
+    def poll_shard(self, batch_id: int, local_shard: int, block: bool = True) -> Optional[BatchResult]:
+        r = BatchResult()
+        rc = self._chk(self.L.pcdn_poll_shard(self.h, batch_id, local_shard, C.byref(r), int(block)))
+        return None if rc == 1 else r
 
     def close(self):
         if getattr(self, "h", None):
@@ -443,8 +499,9 @@ class Engine:
         per connection in ring order.  A wrapped connection has two spans: the one that does not
         start at offset 0 comes first."""
         per: Dict[int, List[Tuple[int, int, int]]] = {}
-        hbase = self.host_rings()
-        rbytes = self.ring_info()[1] if hbase else 0
+        sh = self.shards()
+        stride, rbytes = sh[0].shard_stride, sh[0].ring_bytes
+        hosts = {d.global_index: d.rings_host for d in sh if d.rings_host}
         for conn, off, ln, nrec in self.spans(res):
             per.setdefault(conn, []).append((off, ln, nrec))
         out: Dict[int, List[bytes]] = {}
@@ -454,7 +511,8 @@ class Engine:
             frames = []
             for off, ln, nrec in pieces:
                 # host rings: the bytes are read in place, exactly what a socket writer would do
-                data = C.string_at(hbase + conn * rbytes + off, ln) if hbase else self.read(conn, off, ln)
+                hb = hosts.get(conn // stride)
+                data = C.string_at(hb + (conn % stride) * rbytes + off, ln) if hb else self.read(conn, off, ln)
                 p = 0
                 for _ in range(nrec):
                     L = int.from_bytes(data[p:p + 4], "big")
@@ -508,7 +566,7 @@ class Engine:
 
     def debug_interested(self, topics: Iterable[int], to_users_only: bool = False) -> List[int]:
         t, n = _t16(topics)
-        cap = self.cfg.max_conns
+        cap = self.shard_info(0).shard_stride * max(1, self.num_shards()[1])  # the whole id space (all shards)
         out = (C.c_uint32 * cap)()
         k = C.c_uint32()
         self._chk(self.L.pcdn_debug_interested(self.h, t, n, int(to_users_only), out, cap, C.byref(k)))

@@ -1,158 +1,26 @@
 // engine.cu — host runtime of the fan-out engine and the C ABI (include/pcdn_fanout.h).
 //
-// One engine = one CUDA device, one stream, the routing tables (host mirror in host_state.*, device
-// copy in DevState), the per-connection output rings and a small pool of batch slots.  A batch is
-// staged in pinned memory while it is open, copied to the device on flush and routed by the kernel
-// pipeline of kernels.cuh; results (span table, counters) come back through pinned memory.
+// One engine = one logical broker: ONE host mirror of the routing tables (host_state.*) and ONE
+// connection-id space, spread over one or more connection SHARDS.  A shard = one CUDA device with
+// its streams, its slice of the subscription bitmap, a replica of the direct map, the output rings
+// of its connections and its share of every batch slot.  A batch is staged in pinned memory while it
+// is open, brought to every shard on flush (one H2D for a single shard; H2D to shard 0 + ONE
+// ncclBroadcast over NVLink for several), routed there by the kernel pipeline of kernels.cuh, and
+// its results (span table, counters) come back through pinned memory per shard.
 // There is no CPU data path: without a device every routing call fails with PCDN_ENODEV.
-#include <cuda_runtime.h>
+#include "engine_internal.h"
 
-#include <algorithm>
-#include <chrono>
-#include <cstdio>
-#include <cstring>
-#include <memory>
-#include <mutex>
-#include <new>
-#include <string>
-#include <thread>
-#include <vector>
-
-#include "frame_parse.h"
-#include "host_state.h"
-#include "kernels.cuh"
-#include "pcdn_fanout.h"
-
-using namespace pcdn;
-
-namespace {
-
+namespace pcdn_detail {
 thread_local std::string g_err;
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
-
-#define CUDA_TRY(expr)                                                                         \
-  do {                                                                                         \
-    cudaError_t _e = (expr);                                                                   \
-    if (_e != cudaSuccess)                                                                     \
-      return fail(PCDN_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));             \
-  } while (0)
-
-template <class T>
-int dev_alloc(T** p, size_t n) {
-  *p = nullptr;
-  if (!n) n = 1;
-  cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
-  if (e != cudaSuccess) return fail(PCDN_ENOMEM, std::string("cudaMalloc ") + std::to_string(n * sizeof(T)) + " B: " + cudaGetErrorString(e));
-  return 0;
-}
-template <class T>
-int pin_alloc(T** p, size_t n) {
-  *p = nullptr;
-  if (!n) n = 1;
-  cudaError_t e = cudaMallocHost((void**)p, n * sizeof(T));
-  if (e != cudaSuccess) return fail(PCDN_ENOMEM, std::string("cudaMallocHost ") + std::to_string(n * sizeof(T)) + " B: " + cudaGetErrorString(e));
-  return 0;
-}
-
-// pinned + mapped: the device writes through *dev_alias (same bytes the host reads through *p)
-template <typename T>
-int pin_alloc_mapped(T** p, T** dev_alias, size_t n) {
-  *p = nullptr;
-  if (!n) n = 1;
-  cudaError_t e = cudaHostAlloc((void**)p, n * sizeof(T), cudaHostAllocMapped);
-  if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)dev_alias, (void*)*p, 0);
-  if (e != cudaSuccess) return fail(PCDN_ENOMEM, std::string("cudaHostAlloc(mapped) ") + std::to_string(n * sizeof(T)) + " B: " + cudaGetErrorString(e));
-  return 0;
-}
-
-inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-enum SlotState { SLOT_FREE = 0, SLOT_OPEN = 1, SLOT_INFLIGHT = 2 };
-// engines up to this many connection slots publish spans directly into mapped host memory
-constexpr uint32_t kDirectPublishMaxConns = 65536;  // = kSmallCtrlConns: the engines the fused control kernel serves
-
-struct Slot {
-  int state = SLOT_FREE;
-  uint64_t batch_id = 0;
-  bool polled = false, device_input = false;
-  // host staging while open
-  uint8_t* h_arena = nullptr;   // pinned
-  size_t arena_used = 0;
-  std::vector<uint8_t> kind, flags;
-  std::vector<uint32_t> slot_off16, raw_len, aux_off, aux_len, bcast_index;
-  std::vector<uint16_t> topics;
-  uint32_t n_direct = 0;
-  uint64_t ingress_bytes = 0;   // pool permits held by this batch
-  std::chrono::steady_clock::time_point t_launch;
-  bool devparse = false;        // some messages carry MSGF_DEVPARSE (k_parse runs first)
-  int8_t* h_msg_status = nullptr;  // pinned
-  uint32_t n_msg_errors = 0;
-  uint8_t* h_desc = nullptr;    // pinned descriptor block
-  // device
-  uint8_t* d_arena = nullptr;
-  uint8_t* d_desc = nullptr;
-  Work w{};
-  BatchIn in{};
-  // results
-  BatchStats* h_stats = nullptr;  // pinned: final counters (after the pack)
-  BatchStats* d_stats_pub = nullptr;  // direct publish: device alias of h_stats (mapped)
-  // span table / overflow list of this batch: written by the device straight into mapped host memory
-  // (few spans expected) or staged in HBM and copied out while the pack runs (up to 2 per connection)
-  bool spans_mapped = false;
-  Span* d_spans_map = nullptr; Span* d_spans_dev = nullptr;
-  uint32_t* d_ovf_map = nullptr; uint32_t* d_ovf_dev = nullptr;
-  BatchStats* h_early = nullptr;  // pinned: counters as of k_offsets (n_spans, n_overflow are final there)
-  Span* h_spans = nullptr;        // pinned
-  uint32_t* h_overflow = nullptr; // pinned
-  cudaEvent_t ev_done = nullptr;   // pack + final counters complete (pack stream)
-  cudaEvent_t ev_ctrl = nullptr;   // match/plan/offsets complete (main stream)
-  cudaEvent_t ev_early = nullptr;  // early counters are in h_early (copy stream)
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  bool timed = false;
-};
-
-}  // namespace
-
-struct pcdn_engine {
-  std::mutex mu;
-  pcdn_config cfg{};
-  std::string identity;
-  Geometry geo{};
-  std::unique_ptr<HostTables> tables;
-  std::unique_ptr<Connections> conns;
-  bool has_device = false;
-  bool direct_publish = false;  // spans / overflow list written by the device into mapped host memory
-  uint8_t* h_rings = nullptr;   // PCDN_FLAG_HOST_RINGS: host address of the (mapped, pinned) rings
-  int n_sms = 148;
-  // main stream: uploads, table updates, direct/match/plan/offsets, release.  pack stream: k_pack, so
-  // that the control kernels of batch n+1 overlap the HBM-bound pack of batch n.  copy stream: D2H.
-  cudaStream_t stream = nullptr, pack_stream = nullptr, copy_stream = nullptr;
-  bool own_stream = false;
-  DevState dev{};
-  std::vector<Slot> slots;
-  int open_slot = -1;
-  uint64_t next_batch_id = 1;
-  std::vector<uint64_t> inflight;  // submit order
-  size_t desc_cap = 0, topics_cap = 0;
-  // journal staging (pinned + device), reuse guarded by an event
-  uint8_t* jstage_h = nullptr; uint8_t* jstage_d = nullptr; size_t jstage_cap = 0;
-  cudaEvent_t ev_journal = nullptr; bool ev_journal_pending = false;
-  std::vector<Upd32> h_u32; std::vector<UpdSlot> h_slot; std::vector<uint32_t> h_kslot; std::vector<uint8_t> h_kbytes;
-  bool timing = false;
-  uint64_t inflight_bytes = 0;  // Limiter analogue: accepted frame bytes whose batch is not released yet
-  pcdn_stats stats{};
-  std::vector<void*> dev_allocs, pin_allocs;
-  // buffers behind pcdn_get_*_sync
-  std::vector<UserSyncEntry> sync_users;
-  std::vector<pcdn_user_sync_entry> sync_users_c;
-  std::vector<TopicSyncEntry> sync_topics;
-  std::vector<pcdn_topic_sync_entry> sync_topics_c;
-};
+}  // namespace pcdn_detail
 
 namespace {
 
-// Upload changed table words/slots/keys and apply them on the engine stream (K4).  Stream order
-// gives R12: every earlier batch sees the old tables, every later batch the new ones.
+// Upload changed table words/slots/keys and apply them on every local shard's stream (K4).  Stream
+// order gives R12: every earlier batch sees the old tables, every later batch the new ones.  A
+// shard's bitmap / broker mask are its word slice of the global arrays; owner_conn, the cuckoo
+// slots and the key arena are replicated.
 int flush_journal(pcdn_engine* e) {
   HostTables& t = *e->tables;
   if (!e->has_device) { t.clear_dirty(); return 0; }
@@ -160,68 +28,83 @@ int flush_journal(pcdn_engine* e) {
   bool any = !t.dirty_sub.empty() || !t.dirty_brk.empty() || !t.dirty_owner.empty() || !t.dirty_slots.empty() ||
              !t.dirty_keys.empty();
   if (!any) return 0;
-  cudaStream_t st = e->stream;
-  // keys first (slots reference them)
+  const uint32_t Ws = e->shard_W(), W = g.W;
   const bool full_keys = t.dirty_keys.size() > (size_t)g.max_keys / 16 + 64;
-  if (full_keys) CUDA_TRY(cudaMemcpyAsync(e->dev.keys, t.keys.data(), t.keys.size(), cudaMemcpyHostToDevice, st));
-  e->h_u32.clear(); e->h_slot.clear(); e->h_kslot.clear(); e->h_kbytes.clear();
-  bool full_sub = t.dirty_sub.size() > t.sub.size() / 16 + 64;
-  if (full_sub) CUDA_TRY(cudaMemcpyAsync(e->dev.sub, t.sub.data(), t.sub.size() * 4, cudaMemcpyHostToDevice, st));
-  else for (uint32_t i : t.dirty_sub) e->h_u32.push_back(Upd32{0, i, t.sub[i]});
-  for (uint32_t i : t.dirty_brk) e->h_u32.push_back(Upd32{1, i, t.brk[i]});
-  for (uint32_t i : t.dirty_owner) e->h_u32.push_back(Upd32{2, i, t.owner_conn[i]});
-  bool full_slots = t.dirty_slots.size() > t.cuckoo.size() / 16 + 64;
-  if (full_slots) CUDA_TRY(cudaMemcpyAsync(e->dev.cuckoo, t.cuckoo.data(), t.cuckoo.size() * sizeof(CuckooEntry), cudaMemcpyHostToDevice, st));
-  else for (uint32_t i : t.dirty_slots) e->h_slot.push_back(UpdSlot{i, t.cuckoo[i]});
+  const bool full_sub = t.dirty_sub.size() > t.sub.size() / 16 + 64;
+  const bool full_slots = t.dirty_slots.size() > t.cuckoo.size() / 16 + 64;
+  // parts common to all shards
+  e->h_slot.clear(); e->h_kslot.clear(); e->h_kbytes.clear();
+  if (!full_slots) for (uint32_t i : t.dirty_slots) e->h_slot.push_back(UpdSlot{i, t.cuckoo[i]});
   if (!full_keys) for (uint32_t k : t.dirty_keys) {
     e->h_kslot.push_back(k);
     size_t at = e->h_kbytes.size();
     e->h_kbytes.resize(at + g.key_stride);
     std::memcpy(&e->h_kbytes[at], &t.keys[(size_t)k * g.key_stride], g.key_stride);
   }
-  // One pinned staging block [Upd32 | UpdSlot | key slots | key bytes] → one H2D copy → apply kernels.
-  // The staging block is reused by the next flush; an event (not a stream sync) guards it, so table
-  // churn at control-plane rate never stalls the batches already queued on the stream.
-  const size_t b_u32 = align_up(e->h_u32.size() * sizeof(Upd32), 16), b_slot = align_up(e->h_slot.size() * sizeof(UpdSlot), 16);
-  const size_t b_ks = align_up(e->h_kslot.size() * 4, 16), b_kb = align_up(e->h_kbytes.size(), 16);
-  const size_t total = b_u32 + b_slot + b_ks + b_kb;
-  if (total) {
-    if (e->ev_journal_pending) { CUDA_TRY(cudaEventSynchronize(e->ev_journal)); e->ev_journal_pending = false; }
-    if (total > e->jstage_cap) {
-      const size_t ncap = std::max(total, e->jstage_cap * 2 + (1 << 16));
-      CUDA_TRY(cudaStreamSynchronize(st));
-      if (e->jstage_h) cudaFreeHost(e->jstage_h);
-      if (e->jstage_d) cudaFree(e->jstage_d);
-      e->jstage_h = nullptr; e->jstage_d = nullptr; e->jstage_cap = 0;
-      CUDA_TRY(cudaMallocHost((void**)&e->jstage_h, ncap));
-      CUDA_TRY(cudaMalloc((void**)&e->jstage_d, ncap));
-      e->jstage_cap = ncap;
+  for (Shard& sh : e->shards) {
+    DeviceGuard dg(sh.device);
+    cudaStream_t st = sh.stream;
+    const uint32_t w0 = sh.gindex * Ws;
+    // keys first (slots reference them)
+    if (full_keys) CUDA_TRY(cudaMemcpyAsync(sh.dev.keys, t.keys.data(), t.keys.size(), cudaMemcpyHostToDevice, st));
+    sh.h_u32.clear();
+    if (full_sub) {
+      if (Ws == W) CUDA_TRY(cudaMemcpyAsync(sh.dev.sub, t.sub.data(), t.sub.size() * 4, cudaMemcpyHostToDevice, st));
+      else CUDA_TRY(cudaMemcpy2DAsync(sh.dev.sub, (size_t)Ws * 4, t.sub.data() + w0, (size_t)W * 4, (size_t)Ws * 4, g.T, cudaMemcpyHostToDevice, st));
+    } else {
+      for (uint32_t i : t.dirty_sub) {
+        const uint32_t row = i / W, wd = i % W;
+        if (wd >= w0 && wd < w0 + Ws) sh.h_u32.push_back(Upd32{0, row * Ws + (wd - w0), t.sub[i]});
+      }
     }
-    uint8_t* h = e->jstage_h;
-    if (b_u32) std::memcpy(h, e->h_u32.data(), e->h_u32.size() * sizeof(Upd32));
-    if (b_slot) std::memcpy(h + b_u32, e->h_slot.data(), e->h_slot.size() * sizeof(UpdSlot));
-    if (b_ks) std::memcpy(h + b_u32 + b_slot, e->h_kslot.data(), e->h_kslot.size() * 4);
-    if (b_kb) std::memcpy(h + b_u32 + b_slot + b_ks, e->h_kbytes.data(), e->h_kbytes.size());
-    CUDA_TRY(cudaMemcpyAsync(e->jstage_d, h, total, cudaMemcpyHostToDevice, st));
-    uint8_t* d = e->jstage_d;
-    launch_apply_updates(e->dev, (const Upd32*)d, (uint32_t)e->h_u32.size(), (const UpdSlot*)(d + b_u32), (uint32_t)e->h_slot.size(),
-                         (const uint32_t*)(d + b_u32 + b_slot), d + b_u32 + b_slot + b_ks, (uint32_t)e->h_kslot.size(), st);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(e->ev_journal, st));
-    e->ev_journal_pending = true;
+    for (uint32_t i : t.dirty_brk)
+      if (i >= w0 && i < w0 + Ws) sh.h_u32.push_back(Upd32{1, i - w0, t.brk[i]});
+    for (uint32_t i : t.dirty_owner) sh.h_u32.push_back(Upd32{2, i, t.owner_conn[i]});
+    if (full_slots) CUDA_TRY(cudaMemcpyAsync(sh.dev.cuckoo, t.cuckoo.data(), t.cuckoo.size() * sizeof(CuckooEntry), cudaMemcpyHostToDevice, st));
+    // One pinned staging block [Upd32 | UpdSlot | key slots | key bytes] → one H2D copy → apply kernels.
+    // The staging block is reused by the next flush; an event (not a stream sync) guards it, so table
+    // churn at control-plane rate never stalls the batches already queued on the stream.
+    const size_t b_u32 = align_up(sh.h_u32.size() * sizeof(Upd32), 16), b_slot = align_up(e->h_slot.size() * sizeof(UpdSlot), 16);
+    const size_t b_ks = align_up(e->h_kslot.size() * 4, 16), b_kb = align_up(e->h_kbytes.size(), 16);
+    const size_t total = b_u32 + b_slot + b_ks + b_kb;
+    if (total) {
+      if (sh.ev_journal_pending) { CUDA_TRY(cudaEventSynchronize(sh.ev_journal)); sh.ev_journal_pending = false; }
+      if (total > sh.jstage_cap) {
+        const size_t ncap = std::max(total, sh.jstage_cap * 2 + (1 << 16));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (sh.jstage_h) cudaFreeHost(sh.jstage_h);
+        if (sh.jstage_d) cudaFree(sh.jstage_d);
+        sh.jstage_h = nullptr; sh.jstage_d = nullptr; sh.jstage_cap = 0;
+        CUDA_TRY(cudaMallocHost((void**)&sh.jstage_h, ncap));
+        CUDA_TRY(cudaMalloc((void**)&sh.jstage_d, ncap));
+        sh.jstage_cap = ncap;
+      }
+      uint8_t* h = sh.jstage_h;
+      if (b_u32) std::memcpy(h, sh.h_u32.data(), sh.h_u32.size() * sizeof(Upd32));
+      if (b_slot) std::memcpy(h + b_u32, e->h_slot.data(), e->h_slot.size() * sizeof(UpdSlot));
+      if (b_ks) std::memcpy(h + b_u32 + b_slot, e->h_kslot.data(), e->h_kslot.size() * 4);
+      if (b_kb) std::memcpy(h + b_u32 + b_slot + b_ks, e->h_kbytes.data(), e->h_kbytes.size());
+      CUDA_TRY(cudaMemcpyAsync(sh.jstage_d, h, total, cudaMemcpyHostToDevice, st));
+      uint8_t* d = sh.jstage_d;
+      launch_apply_updates(sh.dev, (const Upd32*)d, (uint32_t)sh.h_u32.size(), (const UpdSlot*)(d + b_u32), (uint32_t)e->h_slot.size(),
+                           (const uint32_t*)(d + b_u32 + b_slot), d + b_u32 + b_slot + b_ks, (uint32_t)e->h_kslot.size(), st);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaEventRecord(sh.ev_journal, st));
+      sh.ev_journal_pending = true;
+    }
+    // whole-table uploads come from pageable vectors (staged by the runtime before the call returns);
+    // they only happen on bulk loads, where one synchronisation is irrelevant
+    if (full_keys || full_sub || full_slots) CUDA_TRY(cudaStreamSynchronize(st));
   }
-  // whole-table uploads come from pageable vectors (staged by the runtime before the call returns);
-  // they only happen on bulk loads, where one synchronisation is irrelevant
-  if (full_keys || full_sub || full_slots) CUDA_TRY(cudaStreamSynchronize(st));
   t.clear_dirty();
   return 0;
 }
 
 void slot_reset_open(Slot& s) {
-  s.arena_used = 0; s.n_direct = 0; s.devparse = false; s.n_msg_errors = 0; s.ingress_bytes = 0;
+  s.arena_used = 0; s.n_direct = 0; s.devparse = false; s.ingress_bytes = 0; s.n_msgs = 0;
   s.kind.clear(); s.flags.clear(); s.slot_off16.clear(); s.raw_len.clear(); s.aux_off.clear(); s.aux_len.clear();
   s.bcast_index.clear(); s.topics.clear();
-  s.polled = false; s.device_input = false; s.timed = false;
+  s.device_input = false; s.counted = false;
 }
 
 int acquire_open_slot(pcdn_engine* e) {
@@ -236,40 +119,46 @@ int acquire_open_slot(pcdn_engine* e) {
   return fail(PCDN_EAGAIN, "all batch slots are in flight: poll and release a batch first");
 }
 
-// run the kernel pipeline for slot `s` whose BatchIn is ready on the device
-int launch_pipeline(pcdn_engine* e, Slot& s, uint32_t n_direct) {
+// run the kernel pipeline of one shard for slot `si`, whose BatchIn is ready (or will be, once
+// ev_ingest fires) in that shard's memory
+int launch_shard_pipeline(pcdn_engine* e, Shard& sh, uint32_t si, uint32_t n_direct, bool devparse, bool wait_ingest) {
+  DeviceGuard dg(sh.device);
+  ShardSlot& s = sh.slots[si];
   // Default: the pack runs on the main stream.  A/B switch (pack_variant bit 3): run it on the
   // high-priority pack stream so the next batch's control kernels overlap it — measured SLOWER for
   // the bulk-store pack (profiles/r1_sweep_overlap.txt), so it stays opt-in.
-  const bool dp = e->direct_publish;
-  cudaStream_t st = e->stream, ps = (!dp && (e->cfg.pack_variant & 8)) ? e->pack_stream : e->stream, cs = e->copy_stream;
+  const bool dp = sh.direct_publish;
+  cudaStream_t st = sh.stream, ps = (!dp && (e->cfg.pack_variant & 8)) ? sh.pack_stream : sh.stream, cs = sh.copy_stream;
   const bool has_direct = n_direct > 0;
+  if (wait_ingest) CUDA_TRY(cudaStreamWaitEvent(st, s.ev_ingest, 0));
   s.timed = e->timing;
+  s.polled = false;
+  s.n_msg_errors = 0;
   if (++s.w.stamp == 0) s.w.stamp = 1;  // validity stamp of this batch's direct buckets
   // latency path of the smallest geometry: match + plan + offsets in one cluster launch that also
   // zeroes / publishes the counters (kernels.cu: k_ctrl_small)
-  const bool fused = dp && e->geo.N <= kSmallCtrlConns && s.in.n_msgs <= kSmallCtrlMsgs;
+  const bool fused = dp && sh.dev.N <= kSmallCtrlConns && s.in.n_msgs <= kSmallCtrlMsgs;
   // Spans go straight into mapped host memory when few are expected (16-byte PCIe writes: a table
   // of 16 K spans measured 20 us slower than the staged copy): the smallest geometry, or a batch
   // without broadcasts and with few messages (at most one span per message).  Otherwise they are staged in HBM and copied
   // out with one DMA of the exact size while the pack runs.
-  s.spans_mapped = dp && (e->geo.N <= 8192 || (s.in.n_bcast == 0 && s.in.n_msgs <= 4096));
+  s.spans_mapped = dp && (sh.dev.N <= 8192 || (s.in.n_bcast == 0 && s.in.n_msgs <= 4096));
   s.w.spans = s.spans_mapped ? s.d_spans_map : s.d_spans_dev;
   s.w.overflow = s.spans_mapped ? s.d_ovf_map : s.d_ovf_dev;
-  const bool zero_in_kernel = fused && !s.devparse;  // (k_parse counts into the batch counters before the fused kernel)
+  const bool zero_in_kernel = fused && !devparse;  // (k_parse counts into the batch counters before the fused kernel)
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[0], st));
-  if (!zero_in_kernel) launch_batch_begin(e->dev, s.w, s.in, has_direct, st);
-  if (s.devparse) launch_parse(e->dev, s.w, s.in, st);
-  if (has_direct && !fused) launch_direct(e->dev, s.w, s.in, st);  // fused: lookup + sort inside k_ctrl_small
+  if (!zero_in_kernel) launch_batch_begin(sh.dev, s.w, s.in, has_direct, st);
+  if (devparse) launch_parse(sh.dev, s.w, s.in, st);
+  if (has_direct && !fused) launch_direct(sh.dev, s.w, s.in, st);  // fused: lookup + sort inside k_ctrl_small
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[1], st));
   if (fused) {
-    launch_ctrl_small(e->dev, s.w, s.in, has_direct, zero_in_kernel, s.d_stats_pub, st);
+    launch_ctrl_small(sh.dev, s.w, s.in, has_direct, zero_in_kernel, s.d_stats_pub, st);
     if (s.timed) { CUDA_TRY(cudaEventRecord(s.ev[2], st)); CUDA_TRY(cudaEventRecord(s.ev[3], st)); }
   } else {
-    launch_match(e->dev, s.w, s.in, st);
+    launch_match(sh.dev, s.w, s.in, st);
     if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[2], st));
-    launch_plan(e->dev, s.w, s.in, st);
-    launch_offsets(e->dev, s.w, s.in, has_direct, st);
+    launch_plan(sh.dev, s.w, s.in, st);
+    launch_offsets(sh.dev, s.w, s.in, has_direct, st);
     if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[3], st));
   }
   if (!s.spans_mapped) {
@@ -284,16 +173,90 @@ int launch_pipeline(pcdn_engine* e, Slot& s, uint32_t n_direct) {
   // (mapped spans: k_offsets wrote spans / overflow into host memory; everything stays on one
   //  stream and the host waits for ev_done only)
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[4], ps));
-  launch_pack(e->dev, s.w, s.in, e->cfg.pack_variant, e->n_sms, ps);
+  launch_pack(sh.dev, s.w, s.in, e->cfg.pack_variant, sh.n_sms, ps);
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[5], ps));
   CUDA_TRY(cudaGetLastError());
   if (!fused) CUDA_TRY(cudaMemcpyAsync(s.h_stats, s.w.stats, sizeof(BatchStats), cudaMemcpyDeviceToHost, ps));
   CUDA_TRY(cudaEventRecord(s.ev_done, ps));
+  return 0;
+}
+
+// every local shard runs the pipeline; the slot becomes the newest in-flight batch
+int launch_pipeline(pcdn_engine* e, uint32_t si, uint32_t n_direct, bool wait_ingest) {
+  Slot& s = e->slots[si];
+  for (Shard& sh : e->shards) {
+    int rc = launch_shard_pipeline(e, sh, si, n_direct, s.devparse, wait_ingest);
+    if (rc) return rc;
+  }
   s.state = SLOT_INFLIGHT;
   s.t_launch = std::chrono::steady_clock::now();
   s.batch_id = e->next_batch_id++;
-  s.polled = false;
+  s.counted = false;
   e->inflight.push_back(s.batch_id);
+  return 0;
+}
+
+// Sharded engines: bring `bytes` of slot si's pinned staging (or, for device input, `src_root` on the
+// root GPU) into every shard's d_arena.  NCCL mode: H2D on the root's ingest stream, then ONE
+// ncclBroadcast per region over all shards of the broker (grouped over the local shards), all on the
+// ingest streams — ahead of the main streams, so it overlaps the pack of the previous batch.  The
+// region may only be overwritten once the pack that last read this slot's arena is done (ev_done).
+struct IngestRegion { const void* root_src; size_t dst_off; size_t bytes; };  // root_src: device pointer on the root, or nullptr = staged bytes
+int ingest_regions(pcdn_engine* e, uint32_t si, const uint8_t* h_src, const IngestRegion* regs, int nregs, bool device_input) {
+  Slot& s = e->slots[si];
+  (void)s;
+  if (e->ingest == PCDN_INGEST_HOST) {
+    // every shard copies from the pinned staging itself (device input: peer copy from the root
+    // shard's buffers, which the root reads in place)
+    for (Shard& sh : e->shards) {
+      DeviceGuard dg(sh.device);
+      ShardSlot& ss = sh.slots[si];
+      CUDA_TRY(cudaStreamWaitEvent(sh.ingest_stream, ss.ev_done, 0));
+      if (device_input) CUDA_TRY(cudaStreamWaitEvent(sh.ingest_stream, e->shards[0].ev_submit, 0));
+      for (int r = 0; r < nregs && !(device_input && sh.gindex == 0); r++) {
+        if (!regs[r].bytes) continue;
+        if (device_input)
+          CUDA_TRY(cudaMemcpyPeerAsync(ss.d_arena + regs[r].dst_off, sh.device, regs[r].root_src, e->shards[0].device, regs[r].bytes, sh.ingest_stream));
+        else
+          CUDA_TRY(cudaMemcpyAsync(ss.d_arena + regs[r].dst_off, h_src + regs[r].dst_off, regs[r].bytes, cudaMemcpyHostToDevice, sh.ingest_stream));
+      }
+      CUDA_TRY(cudaEventRecord(ss.ev_ingest, sh.ingest_stream));
+    }
+    return 0;
+  }
+  const NcclApi* nc = e->nccl;
+  for (Shard& sh : e->shards) {
+    DeviceGuard dg(sh.device);
+    ShardSlot& ss = sh.slots[si];
+    CUDA_TRY(cudaStreamWaitEvent(sh.ingest_stream, ss.ev_done, 0));
+    if (sh.gindex == 0) {
+      if (device_input) CUDA_TRY(cudaStreamWaitEvent(sh.ingest_stream, sh.ev_submit, 0));
+      else
+        for (int r = 0; r < nregs; r++)
+          if (regs[r].bytes)
+            CUDA_TRY(cudaMemcpyAsync(ss.d_arena + regs[r].dst_off, h_src + regs[r].dst_off, regs[r].bytes, cudaMemcpyHostToDevice, sh.ingest_stream));
+    }
+  }
+  NCCL_TRY(nc, nc->GroupStart());
+  for (Shard& sh : e->shards) {
+    DeviceGuard dg(sh.device);
+    ShardSlot& ss = sh.slots[si];
+    for (int r = 0; r < nregs; r++) {
+      if (!regs[r].bytes) continue;
+      // the root sends from where the bytes are (its staged copy, or the caller's device buffers in
+      // place) and every other shard receives into its own arena
+      void* dst = ss.d_arena + regs[r].dst_off;
+      const void* src = (sh.gindex == 0 && device_input) ? regs[r].root_src : dst;
+      if (sh.gindex == 0 && device_input) dst = const_cast<void*>(src);
+      int rc = nc->Broadcast(src, dst, regs[r].bytes, kNcclUint8, 0, sh.comm, sh.ingest_stream);
+      if (rc) { nc->GroupEnd(); return fail(PCDN_ECUDA, std::string("ncclBroadcast: ") + nc->GetErrorString(rc)); }
+    }
+  }
+  NCCL_TRY(nc, nc->GroupEnd());
+  for (Shard& sh : e->shards) {
+    DeviceGuard dg(sh.device);
+    CUDA_TRY(cudaEventRecord(sh.slots[si].ev_ingest, sh.ingest_stream));
+  }
   return 0;
 }
 
@@ -301,13 +264,13 @@ int launch_pipeline(pcdn_engine* e, Slot& s, uint32_t n_direct) {
 int flush_open(pcdn_engine* e, uint64_t* batch_id) {
   if (batch_id) *batch_id = 0;
   if (e->open_slot < 0) return 0;
-  Slot& s = e->slots[e->open_slot];
+  const uint32_t si = (uint32_t)e->open_slot;
+  Slot& s = e->slots[si];
   const uint32_t n = (uint32_t)s.kind.size();
   if (n == 0) { s.state = SLOT_FREE; e->open_slot = -1; return 0; }
   if (!e->has_device) return fail(PCDN_ENODEV, "host-only engine cannot route messages");
   int rc = flush_journal(e);
   if (rc) return rc;
-  cudaStream_t st = e->stream;
   // descriptor block layout (offsets 16-byte aligned)
   size_t o_kind = 0, o_flags = align_up(o_kind + n, 16), o_slot = align_up(o_flags + n, 16);
   size_t o_len = o_slot + (size_t)n * 4, o_aoff = o_len + (size_t)n * 4, o_alen = o_aoff + (size_t)n * 4;
@@ -316,10 +279,10 @@ int flush_open(pcdn_engine* e, uint64_t* batch_id) {
   if (total > e->desc_cap) return fail(PCDN_ENOSPC, "descriptor block overflow");
   // Small batches ride in ONE host→device copy: the descriptor block is appended to the frame arena
   // when it fits there (one DMA + one API call less on the latency path); otherwise two copies.
+  // Sharded engines always use the appended layout: the batch is one ingest region.
   const size_t doff = align_up(s.arena_used, 256);
-  const bool one_copy = doff + total <= (size_t)e->cfg.max_batch_bytes + 64 && doff + total <= (64u << 10);
+  const bool one_copy = e->sharded || (doff + total <= (size_t)e->cfg.max_batch_bytes + 64 && doff + total <= (64u << 10));
   uint8_t* hd = one_copy ? s.h_arena + doff : s.h_desc;
-  uint8_t* dd = one_copy ? s.d_arena + doff : s.d_desc;
   std::memcpy(hd + o_kind, s.kind.data(), n);
   std::memcpy(hd + o_flags, s.flags.data(), n);
   std::memcpy(hd + o_slot, s.slot_off16.data(), (size_t)n * 4);
@@ -328,25 +291,39 @@ int flush_open(pcdn_engine* e, uint64_t* batch_id) {
   std::memcpy(hd + o_alen, s.aux_len.data(), (size_t)n * 4);
   if (!s.bcast_index.empty()) std::memcpy(hd + o_bidx, s.bcast_index.data(), s.bcast_index.size() * 4);
   if (!s.topics.empty()) std::memcpy(hd + o_top, s.topics.data(), s.topics.size() * 2);
-  if (one_copy) {
-    CUDA_TRY(cudaMemcpyAsync(s.d_arena, s.h_arena, doff + total, cudaMemcpyHostToDevice, st));
+  if (e->sharded) {
+    std::memset(s.h_arena + s.arena_used, 0, doff - s.arena_used);
+    IngestRegion reg{nullptr, 0, doff + total};
+    if ((rc = ingest_regions(e, si, s.h_arena, &reg, 1, false))) return rc;
   } else {
-    CUDA_TRY(cudaMemcpyAsync(s.d_arena, s.h_arena, align_up(s.arena_used, 16), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(s.d_desc, s.h_desc, total, cudaMemcpyHostToDevice, st));
+    Shard& sh = e->shards[0];
+    DeviceGuard dg(sh.device);
+    ShardSlot& ss = sh.slots[si];
+    if (one_copy) {
+      CUDA_TRY(cudaMemcpyAsync(ss.d_arena, s.h_arena, doff + total, cudaMemcpyHostToDevice, sh.stream));
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(ss.d_arena, s.h_arena, align_up(s.arena_used, 16), cudaMemcpyHostToDevice, sh.stream));
+      CUDA_TRY(cudaMemcpyAsync(ss.d_desc, s.h_desc, total, cudaMemcpyHostToDevice, sh.stream));
+    }
   }
-  s.in.n_msgs = n;
-  s.in.n_bcast = (uint32_t)s.bcast_index.size();
-  s.in.arena = s.d_arena;
-  s.in.kind = dd + o_kind;
-  s.in.flags = dd + o_flags;
-  s.in.slot_off16 = (const uint32_t*)(dd + o_slot);
-  s.in.raw_len = (const uint32_t*)(dd + o_len);
-  s.in.aux_off = (const uint32_t*)(dd + o_aoff);
-  s.in.aux_len = (const uint32_t*)(dd + o_alen);
-  s.in.bcast_index = (const uint32_t*)(dd + o_bidx);
-  s.in.topics = (const uint16_t*)(dd + o_top);
+  for (Shard& sh : e->shards) {
+    ShardSlot& ss = sh.slots[si];
+    uint8_t* dd = one_copy ? ss.d_arena + doff : ss.d_desc;
+    ss.in.n_msgs = n;
+    ss.in.n_bcast = (uint32_t)s.bcast_index.size();
+    ss.in.arena = ss.d_arena;
+    ss.in.kind = dd + o_kind;
+    ss.in.flags = dd + o_flags;
+    ss.in.slot_off16 = (const uint32_t*)(dd + o_slot);
+    ss.in.raw_len = (const uint32_t*)(dd + o_len);
+    ss.in.aux_off = (const uint32_t*)(dd + o_aoff);
+    ss.in.aux_len = (const uint32_t*)(dd + o_alen);
+    ss.in.bcast_index = (const uint32_t*)(dd + o_bidx);
+    ss.in.topics = (const uint16_t*)(dd + o_top);
+  }
   s.device_input = false;
-  rc = launch_pipeline(e, s, s.n_direct);
+  s.n_msgs = n;
+  rc = launch_pipeline(e, si, s.n_direct, e->sharded);
   if (rc) return rc;
   if (batch_id) *batch_id = s.batch_id;
   e->open_slot = -1;
@@ -419,9 +396,11 @@ int append_msg(pcdn_engine* e, uint8_t kind, uint8_t flags, const uint16_t* topi
     s.bcast_index.push_back(m);
   } else {
     // recipient key: read it in place when it lies inside the frame at a 4-byte aligned offset
+    // (multi-process groups always stage it beside the frame: the layout must not depend on how a
+    // process happens to hold the bytes)
     size_t koff;
     if (recipient_len && recipient >= raw && recipient + recipient_len <= raw + raw_len &&
-        ((off + 4 + (size_t)(recipient - raw)) & 3) == 0) {
+        ((off + 4 + (size_t)(recipient - raw)) & 3) == 0 && e->world_shards == e->shards.size()) {
       koff = off + 4 + (size_t)(recipient - raw);
     } else {
       koff = s.arena_used;
@@ -437,32 +416,50 @@ int append_msg(pcdn_engine* e, uint8_t kind, uint8_t flags, const uint16_t* topi
   return 0;
 }
 
-Slot* find_slot(pcdn_engine* e, uint64_t id) {
-  for (auto& s : e->slots)
-    if (s.state == SLOT_INFLIGHT && s.batch_id == id) return &s;
-  return nullptr;
+}  // namespace
+int pcdn_detail::find_slot_index(pcdn_engine* e, uint64_t id) {
+  for (size_t i = 0; i < e->slots.size(); i++)
+    if (e->slots[i].state == SLOT_INFLIGHT && e->slots[i].batch_id == id) return (int)i;
+  return -1;
+}
+namespace {
+
+void destroy_shard(pcdn_engine* e, Shard& sh) {
+  cudaSetDevice(sh.device);
+  if (sh.stream) cudaStreamSynchronize(sh.stream);
+  if (sh.pack_stream) cudaStreamSynchronize(sh.pack_stream);
+  if (sh.copy_stream) cudaStreamSynchronize(sh.copy_stream);
+  if (sh.ingest_stream) cudaStreamSynchronize(sh.ingest_stream);
+  if (sh.comm && e->nccl) { e->nccl->CommDestroy(sh.comm); sh.comm = nullptr; }
+  for (auto& s : sh.slots) {
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+    if (s.ev_ctrl) cudaEventDestroy(s.ev_ctrl);
+    if (s.ev_early) cudaEventDestroy(s.ev_early);
+    if (s.ev_ingest) cudaEventDestroy(s.ev_ingest);
+    for (auto& ev : s.ev) if (ev) cudaEventDestroy(ev);
+  }
+  for (void* p : sh.dev_allocs) cudaFree(p);
+  for (void* p : sh.pin_allocs) cudaFreeHost(p);
+  if (sh.jstage_h) cudaFreeHost(sh.jstage_h);
+  if (sh.jstage_d) cudaFree(sh.jstage_d);
+  if (sh.ev_journal) cudaEventDestroy(sh.ev_journal);
+  if (sh.ev_submit) cudaEventDestroy(sh.ev_submit);
+  if (sh.copy_stream) cudaStreamDestroy(sh.copy_stream);
+  if (sh.pack_stream) cudaStreamDestroy(sh.pack_stream);
+  if (sh.ingest_stream) cudaStreamDestroy(sh.ingest_stream);
+  if (sh.own_stream && sh.stream) cudaStreamDestroy(sh.stream);
 }
 
 void destroy_engine(pcdn_engine* e) {
   if (e->has_device) {
-    cudaSetDevice(e->cfg.device);
-    cudaStreamSynchronize(e->stream);
-    if (e->pack_stream) cudaStreamSynchronize(e->pack_stream);
-    if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
-    for (auto& s : e->slots) {
-      if (s.ev_done) cudaEventDestroy(s.ev_done);
-      if (s.ev_ctrl) cudaEventDestroy(s.ev_ctrl);
-      if (s.ev_early) cudaEventDestroy(s.ev_early);
-      for (auto& ev : s.ev) if (ev) cudaEventDestroy(ev);
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (Shard& sh : e->shards) destroy_shard(e, sh);
+    for (Slot& s : e->slots) {
+      if (s.h_arena) cudaFreeHost(s.h_arena);
+      if (s.h_desc) cudaFreeHost(s.h_desc);
     }
-    for (void* p : e->dev_allocs) cudaFree(p);
-    for (void* p : e->pin_allocs) cudaFreeHost(p);
-    if (e->jstage_h) cudaFreeHost(e->jstage_h);
-    if (e->jstage_d) cudaFree(e->jstage_d);
-    if (e->ev_journal) cudaEventDestroy(e->ev_journal);
-    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
-    if (e->pack_stream) cudaStreamDestroy(e->pack_stream);
-    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    if (prev >= 0) cudaSetDevice(prev);
   }
   delete e;
 }
@@ -471,91 +468,92 @@ void destroy_engine(pcdn_engine* e) {
   do {                                                    \
     int _rc = dev_alloc(&(ptr), (n));                     \
     if (_rc) return _rc;                                  \
-    e->dev_allocs.push_back((void*)(ptr));                \
+    sh.dev_allocs.push_back((void*)(ptr));                \
   } while (0)
 #define PIN_ALLOC(ptr, n)                                 \
   do {                                                    \
     int _rc = pin_alloc(&(ptr), (n));                     \
     if (_rc) return _rc;                                  \
-    e->pin_allocs.push_back((void*)(ptr));                \
+    sh.pin_allocs.push_back((void*)(ptr));                \
+  } while (0)
+#define PIN_ALLOC_MAPPED(ptr, alias, n)                   \
+  do {                                                    \
+    int _rc = pin_alloc_mapped(&(ptr), &(alias), (n));    \
+    if (_rc) return _rc;                                  \
+    sh.pin_allocs.push_back((void*)(ptr));                \
   } while (0)
 
-int init_device(pcdn_engine* e) {
+// device side of one shard: streams, its table slices / replicas, rings, per-slot scratch + results
+int init_shard(pcdn_engine* e, Shard& sh, int ndev, void* user_stream) {
   const pcdn_config& c = e->cfg;
   const Geometry& g = e->geo;
-  int ndev = 0;
-  cudaError_t err = cudaGetDeviceCount(&ndev);
-  if (err != cudaSuccess || ndev == 0)
-    return fail(PCDN_ENODEV, std::string("no CUDA device: ") + cudaGetErrorString(err));
-  if (c.device >= ndev) return fail(PCDN_ENODEV, "device ordinal out of range");
-  CUDA_TRY(cudaSetDevice(c.device));
+  if (sh.device < 0 || sh.device >= ndev) return fail(PCDN_ENODEV, "device ordinal out of range");
+  CUDA_TRY(cudaSetDevice(sh.device));
   cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, c.device));
-  e->n_sms = prop.multiProcessorCount;
-  if (c.stream) { e->stream = (cudaStream_t)c.stream; e->own_stream = false; }
-  else { CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true; }
-  CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaEventCreateWithFlags(&e->ev_journal, cudaEventDisableTiming));
+  CUDA_TRY(cudaGetDeviceProperties(&prop, sh.device));
+  sh.n_sms = prop.multiProcessorCount;
+  if (user_stream) { sh.stream = (cudaStream_t)user_stream; sh.own_stream = false; }
+  else { CUDA_TRY(cudaStreamCreateWithFlags(&sh.stream, cudaStreamNonBlocking)); sh.own_stream = true; }
+  CUDA_TRY(cudaStreamCreateWithFlags(&sh.copy_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&sh.ev_journal, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&sh.ev_submit, cudaEventDisableTiming));
   {
     // highest priority: when a pack and the (small) control kernels of the next batch become
     // runnable together, the pack's persistent CTAs must be placed first and evenly over the SMs
     int lo = 0, hi = 0;
     CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    CUDA_TRY(cudaStreamCreateWithPriority(&e->pack_stream, cudaStreamNonBlocking, hi));
+    CUDA_TRY(cudaStreamCreateWithPriority(&sh.pack_stream, cudaStreamNonBlocking, hi));
+    if (e->sharded) CUDA_TRY(cudaStreamCreateWithPriority(&sh.ingest_stream, cudaStreamNonBlocking, hi));
   }
-  e->has_device = true;
-  e->direct_publish = g.N <= kDirectPublishMaxConns && !(c.flags & PCDN_FLAG_STAGED_SPANS);
+  const uint32_t Ns = g.shard_N, Ws = Ns / 32;
+  sh.direct_publish = Ns <= kDirectPublishMaxConns && !(c.flags & PCDN_FLAG_STAGED_SPANS);
 
-  DevState& d = e->dev;
-  d.N = g.N; d.W = g.W; d.T = g.T; d.nblk = g.W / kBlockWords;
+  DevState& d = sh.dev;
+  d.N = Ns; d.W = Ws; d.T = g.T; d.nblk = Ws / kBlockWords;
   d.bucket_mask = g.bucket_mask; d.key_stride = g.key_stride; d.seed = g.seed;
   d.ring_bytes = c.ring_bytes_per_conn; d.ring_units = (uint32_t)(c.ring_bytes_per_conn / kUnit);
   d.cm_enable = (c.pack_variant & 2) ? 0 : 1;
   d.fat_tile_bytes = (128u << 10) << ((c.pack_variant >> 4) & 15u);  // A/B: bits 4-7 double the tile
   d.n_valid_topics = c.n_valid_topics;
   d.max_key_len = c.max_key_len;
-  DEV_ALLOC(d.sub, (size_t)g.T * g.W);
-  DEV_ALLOC(d.brk, g.W);
+  d.conn_base = sh.gindex * Ns;
+  d.count_drops = sh.gindex == 0 ? 1u : 0u;
+  DEV_ALLOC(d.sub, (size_t)g.T * Ws);
+  DEV_ALLOC(d.brk, Ws);
   DEV_ALLOC(d.owner_conn, g.max_owners);
   DEV_ALLOC(d.cuckoo, (size_t)g.nbuckets * 4);
   DEV_ALLOC(d.keys, (size_t)g.max_keys * g.key_stride);
-  DEV_ALLOC(d.ptail, g.N);
-  DEV_ALLOC(d.used, g.N);
+  DEV_ALLOC(d.ptail, Ns);
+  DEV_ALLOC(d.used, Ns);
   if (c.flags & PCDN_FLAG_HOST_RINGS) {
     // egress hand-off: the pack stores straight into host memory the socket writers read
-    int _rc = pin_alloc_mapped(&e->h_rings, &d.rings, (size_t)g.max_conns * c.ring_bytes_per_conn);
-    if (_rc) return _rc;
-    e->pin_allocs.push_back((void*)e->h_rings);
+    PIN_ALLOC_MAPPED(sh.h_rings, d.rings, (size_t)g.shard_max_conns * c.ring_bytes_per_conn);
   } else {
-    DEV_ALLOC(d.rings, (size_t)g.max_conns * c.ring_bytes_per_conn);
+    DEV_ALLOC(d.rings, (size_t)g.shard_max_conns * c.ring_bytes_per_conn);
   }
-  CUDA_TRY(cudaMemsetAsync(d.sub, 0, (size_t)g.T * g.W * 4, e->stream));
-  CUDA_TRY(cudaMemsetAsync(d.brk, 0, (size_t)g.W * 4, e->stream));
-  CUDA_TRY(cudaMemsetAsync(d.owner_conn, 0xFF, (size_t)g.max_owners * 4, e->stream));
-  CUDA_TRY(cudaMemsetAsync(d.cuckoo, 0, (size_t)g.nbuckets * 4 * sizeof(CuckooEntry), e->stream));
-  CUDA_TRY(cudaMemsetAsync(d.keys, 0, (size_t)g.max_keys * g.key_stride, e->stream));
-  CUDA_TRY(cudaMemsetAsync(d.ptail, 0, (size_t)g.N * 4, e->stream));
-  CUDA_TRY(cudaMemsetAsync(d.used, 0, (size_t)g.N * 4, e->stream));
+  CUDA_TRY(cudaMemsetAsync(d.sub, 0, (size_t)g.T * Ws * 4, sh.stream));
+  CUDA_TRY(cudaMemsetAsync(d.brk, 0, (size_t)Ws * 4, sh.stream));
+  CUDA_TRY(cudaMemsetAsync(d.owner_conn, 0xFF, (size_t)g.max_owners * 4, sh.stream));
+  CUDA_TRY(cudaMemsetAsync(d.cuckoo, 0, (size_t)g.nbuckets * 4 * sizeof(CuckooEntry), sh.stream));
+  CUDA_TRY(cudaMemsetAsync(d.keys, 0, (size_t)g.max_keys * g.key_stride, sh.stream));
+  CUDA_TRY(cudaMemsetAsync(d.ptail, 0, (size_t)Ns * 4, sh.stream));
+  CUDA_TRY(cudaMemsetAsync(d.used, 0, (size_t)Ns * 4, sh.stream));
 
   const uint32_t M = c.max_batch_msgs, MB = c.max_batch_bcast;
-  e->topics_cap = (size_t)M * 4 + 4096;
-  e->desc_cap = align_up((size_t)M * 2 + 64, 16) + (size_t)M * 20 + 64 + e->topics_cap * 2 + 64;
   const size_t cap_fat = (size_t)c.max_batch_deliveries;
   const size_t cap_thin = std::min<size_t>(c.max_batch_deliveries, (size_t)M * (kFatMin - 1));
   const size_t ntiles = sort_tiles(M);
-  e->slots.resize(c.batch_slots);
-  for (Slot& s : e->slots) {
-    PIN_ALLOC(s.h_arena, c.max_batch_bytes + 64);
-    PIN_ALLOC(s.h_desc, e->desc_cap);
-    DEV_ALLOC(s.d_arena, c.max_batch_bytes + 64);
-    DEV_ALLOC(s.d_desc, e->desc_cap);
+  sh.slots.resize(c.batch_slots);
+  for (ShardSlot& s : sh.slots) {
+    DEV_ALLOC(s.d_arena, e->arena_cap);
+    if (!e->sharded) DEV_ALLOC(s.d_desc, e->desc_cap);
     Work& w = s.w;
-    DEV_ALLOC(w.B, (size_t)MB * g.W);
-    DEV_ALLOC(w.wpre, (size_t)MB * g.W);
+    DEV_ALLOC(w.B, (size_t)MB * Ws);
+    DEV_ALLOC(w.wpre, (size_t)MB * Ws);
     DEV_ALLOC(w.cnt, (size_t)MB * d.nblk);
     DEV_ALLOC(w.base, (size_t)MB * d.nblk);
     DEV_ALLOC(w.done, MB);
-    CUDA_TRY(cudaMemsetAsync(w.done, 0, (size_t)MB * 4, e->stream));
+    CUDA_TRY(cudaMemsetAsync(w.done, 0, (size_t)MB * 4, sh.stream));
     DEV_ALLOC(w.D, M);
     DEV_ALLOC(w.dconn, M);
     DEV_ALLOC(w.eb_fat, (size_t)M + 1);
@@ -574,47 +572,94 @@ int init_device(pcdn_engine* e) {
     for (int k = 0; k < 2; k++) { DEV_ALLOC(w.skey[k], M); DEV_ALLOC(w.sval[k], M); }
     DEV_ALLOC(w.hist, 256 * ntiles);
     DEV_ALLOC(w.hist_tmp, 256 * ntiles / 1024 + 2);
-    DEV_ALLOC(w.dstart, (size_t)g.N + 1);
-    DEV_ALLOC(w.dend, (size_t)g.N + 1);
-    DEV_ALLOC(w.dstamp, (size_t)g.N + 1);
-    CUDA_TRY(cudaMemsetAsync(w.dstamp, 0, ((size_t)g.N + 1) * 4, e->stream));
+    DEV_ALLOC(w.dstart, (size_t)Ns + 1);
+    DEV_ALLOC(w.dend, (size_t)Ns + 1);
+    DEV_ALLOC(w.dstamp, (size_t)Ns + 1);
+    CUDA_TRY(cudaMemsetAsync(w.dstamp, 0, ((size_t)Ns + 1) * 4, sh.stream));
     w.stamp = 0;
-    DEV_ALLOC(w.batch_units, g.N);
-    DEV_ALLOC(s.d_spans_dev, (size_t)2 * g.N);
-    DEV_ALLOC(s.d_ovf_dev, g.N);
-    if (e->direct_publish) {
-      int _rc = pin_alloc_mapped(&s.h_spans, &s.d_spans_map, (size_t)2 * g.N);
-      if (_rc) return _rc;
-      e->pin_allocs.push_back((void*)s.h_spans);
-      if ((_rc = pin_alloc_mapped(&s.h_overflow, &s.d_ovf_map, (size_t)g.N))) return _rc;
-      e->pin_allocs.push_back((void*)s.h_overflow);
+    DEV_ALLOC(w.batch_units, Ns);
+    DEV_ALLOC(s.d_spans_dev, (size_t)2 * Ns);
+    DEV_ALLOC(s.d_ovf_dev, Ns);
+    if (sh.direct_publish) {
+      PIN_ALLOC_MAPPED(s.h_spans, s.d_spans_map, (size_t)2 * Ns);
+      PIN_ALLOC_MAPPED(s.h_overflow, s.d_ovf_map, (size_t)Ns);
     } else {
-      PIN_ALLOC(s.h_spans, (size_t)2 * g.max_conns);
-      PIN_ALLOC(s.h_overflow, g.max_conns);
+      PIN_ALLOC(s.h_spans, (size_t)2 * g.shard_max_conns);
+      PIN_ALLOC(s.h_overflow, g.shard_max_conns);
     }
     w.spans = s.d_spans_dev; w.overflow = s.d_ovf_dev;
     DEV_ALLOC(w.msg_status, M);
     PIN_ALLOC(s.h_msg_status, M);
     DEV_ALLOC(w.stats, 1);
-    if (e->direct_publish) {
-      int _rc = pin_alloc_mapped(&s.h_stats, &s.d_stats_pub, 1);
-      if (_rc) return _rc;
-      e->pin_allocs.push_back((void*)s.h_stats);
-    } else {
-      PIN_ALLOC(s.h_stats, 1);
-    }
+    if (sh.direct_publish) PIN_ALLOC_MAPPED(s.h_stats, s.d_stats_pub, 1);
+    else PIN_ALLOC(s.h_stats, 1);
     PIN_ALLOC(s.h_early, 1);
     CUDA_TRY(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&s.ev_ctrl, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&s.ev_early, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&s.ev_ingest, cudaEventDisableTiming));
     for (auto& ev : s.ev) CUDA_TRY(cudaEventCreate(&ev));
   }
-  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  CUDA_TRY(cudaStreamSynchronize(sh.stream));
+  return 0;
+}
+
+// the ingest communicator: one NCCL rank per shard of the broker, ranks of this process = its shards
+int init_nccl(pcdn_engine* e) {
+  const char* why = "";
+  e->nccl = nccl_api(&why);
+  if (!e->nccl) return fail(PCDN_ENODEV, std::string("PCDN_INGEST_NCCL needs libnccl.so.2: ") + why);
+  NcclUniqueId id;
+  if (e->cfg.nccl_unique_id) std::memcpy(&id, e->cfg.nccl_unique_id, sizeof(id));
+  else NCCL_TRY(e->nccl, e->nccl->GetUniqueId(&id));
+  NCCL_TRY(e->nccl, e->nccl->GroupStart());
+  for (Shard& sh : e->shards) {
+    cudaSetDevice(sh.device);
+    int rc = e->nccl->CommInitRank(&sh.comm, (int)e->world_shards, id, (int)sh.gindex);
+    if (rc) { e->nccl->GroupEnd(); return fail(PCDN_ECUDA, std::string("ncclCommInitRank: ") + e->nccl->GetErrorString(rc)); }
+  }
+  NCCL_TRY(e->nccl, e->nccl->GroupEnd());
+  for (Shard& sh : e->shards) {
+    int n = 0;
+    if (e->nccl->CommCount && e->nccl->CommCount(sh.comm, &n) == 0) sh.nccl_ranks = n;
+  }
+  return 0;
+}
+
+int init_device(pcdn_engine* e) {
+  const pcdn_config& c = e->cfg;
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if (err != cudaSuccess || ndev == 0)
+    return fail(PCDN_ENODEV, std::string("no CUDA device: ") + cudaGetErrorString(err));
+  int prev = -1;
+  cudaGetDevice(&prev);
+  const uint32_t M = c.max_batch_msgs;
+  e->topics_cap = (size_t)M * 4 + 4096;
+  e->desc_cap = align_up((size_t)M * 2 + 64, 16) + (size_t)M * 20 + 64 + e->topics_cap * 2 + 64;
+  // sharded engines keep frames + descriptor block in one ingest region (and device-input batches
+  // need room for the descriptor arrays behind the frames)
+  e->arena_cap = c.max_batch_bytes + 64 + (e->sharded ? 256 + e->desc_cap : 0);
+  e->has_device = true;
+  for (size_t i = 0; i < e->shards.size(); i++) {
+    int rc = init_shard(e, e->shards[i], ndev, i == 0 ? c.stream : nullptr);
+    if (rc) return rc;
+  }
+  e->slots.resize(c.batch_slots);
+  for (Slot& s : e->slots) {
+    int rc = pin_alloc(&s.h_arena, e->arena_cap);
+    if (rc) return rc;
+    if (!e->sharded && (rc = pin_alloc(&s.h_desc, e->desc_cap))) return rc;
+  }
+  if (e->sharded && e->ingest == PCDN_INGEST_NCCL) {
+    int rc = init_nccl(e);
+    if (rc) return rc;
+  }
+  if (prev >= 0) cudaSetDevice(prev);
   return 0;
 }
 
 }  // namespace
-
 // ================================================================================== C ABI
 #define LOCK std::lock_guard<std::mutex> _g(e->mu)
 #define GUARD_BEGIN try {
@@ -657,13 +702,41 @@ int pcdn_create(const pcdn_config* cfg, pcdn_engine** out) {
   if (cfg->ring_bytes_per_conn % PCDN_RECORD_ALIGN || cfg->ring_bytes_per_conn == 0 || cfg->ring_bytes_per_conn > (1ull << 31))
     return fail(PCDN_EINVAL, "ring_bytes_per_conn must be a multiple of 32, at most 2 GiB");
   if (cfg->max_key_len > 4096) return fail(PCDN_EINVAL, "max_key_len > 4096");
+  // ---- connection shards
+  const uint32_t n_local = cfg->n_devices ? cfg->n_devices : 1;
+  const uint32_t world = cfg->world_shards ? cfg->world_shards : n_local;
+  if (cfg->n_devices && !cfg->devices) return fail(PCDN_EINVAL, "n_devices > 0 but devices == NULL");
+  if (n_local > 64 || world > 1024 || cfg->first_shard + n_local > world)
+    return fail(PCDN_EINVAL, "shard layout: first_shard + n_devices must be <= world_shards");
+  if (cfg->ingest != PCDN_INGEST_NCCL && cfg->ingest != PCDN_INGEST_HOST) return fail(PCDN_EINVAL, "unknown pcdn_config.ingest");
+  const bool host_only = cfg->n_devices ? false : cfg->device < 0;
+  if (world > n_local && cfg->ingest == PCDN_INGEST_NCCL && !cfg->nccl_unique_id && !host_only)
+    return fail(PCDN_EINVAL, "a multi-process group needs pcdn_config.nccl_unique_id (pcdn_nccl_unique_id)");
+  const uint64_t shard_N = align_up(cfg->max_conns, 32 * kBlockWords);
+  if (shard_N * world > 0xFFFF0000ull) return fail(PCDN_EINVAL, "connection id space (max_conns x shards) exceeds 32 bits");
+  if (cfg->n_devices && cfg->ingest == PCDN_INGEST_NCCL && world > 1)
+    for (uint32_t i = 0; i < n_local; i++)
+      for (uint32_t j = 0; j < i; j++)
+        if (cfg->devices[i] == cfg->devices[j])
+          return fail(PCDN_EINVAL, "PCDN_INGEST_NCCL needs one GPU per shard (use PCDN_INGEST_HOST for shards that share a device)");
   pcdn_engine* e = new pcdn_engine();
   e->cfg = *cfg;
   e->identity = cfg->identity ? cfg->identity : "/";
   e->cfg.identity = e->identity.c_str();
+  e->world_shards = world;
+  e->first_shard = cfg->first_shard;
+  e->sharded = world > 1;
+  e->ingest = cfg->ingest;
+  if (cfg->n_devices) e->devices.assign(cfg->devices, cfg->devices + cfg->n_devices);
+  else e->devices.assign(1, cfg->device);
+  e->cfg.devices = e->devices.data();
+  e->cfg.nccl_unique_id = nullptr;  // consumed below; never dereferenced after pcdn_create returns
   Geometry& g = e->geo;
-  g.max_conns = cfg->max_conns;
-  g.N = (uint32_t)align_up(cfg->max_conns, 32 * kBlockWords);
+  g.n_shards = world;
+  g.shard_N = (uint32_t)shard_N;
+  g.shard_max_conns = cfg->max_conns;
+  g.max_conns = (world - 1) * g.shard_N + cfg->max_conns;
+  g.N = world * g.shard_N;
   g.W = g.N / 32;
   g.T = cfg->max_topics;
   g.max_keys = cfg->max_keys;
@@ -677,8 +750,12 @@ int pcdn_create(const pcdn_config* cfg, pcdn_engine** out) {
   g.seed = cfg->hash_seed ? cfg->hash_seed : 0x243F6A8885A308D3ULL;
   e->tables.reset(new HostTables(g));
   e->conns.reset(new Connections(*e->tables, e->identity.c_str()));
-  if (cfg->device >= 0) {
+  if (!host_only) {
+    e->shards.resize(n_local);
+    for (uint32_t i = 0; i < n_local; i++) { e->shards[i].device = e->devices[i]; e->shards[i].gindex = cfg->first_shard + i; }
+    e->cfg.nccl_unique_id = cfg->nccl_unique_id;
     int rc = init_device(e);
+    e->cfg.nccl_unique_id = nullptr;
     if (rc) { destroy_engine(e); return rc; }
   }
   *out = e;
@@ -1191,30 +1268,64 @@ int pcdn_submit_device(pcdn_engine* e, const pcdn_device_batch* b, uint64_t* bat
   if (!b || b->n_msgs == 0 || b->n_msgs > e->cfg.max_batch_msgs || b->n_bcast > e->cfg.max_batch_bcast ||
       b->n_bcast > b->n_msgs)
     return fail(PCDN_EINVAL, "device batch exceeds configured capacities");
+  const uint32_t n = b->n_msgs, nb = b->n_bcast;
+  // region layout of the batch inside a receiving shard's arena (sharded engines)
+  const size_t o_arena = 0, o_kind = align_up(b->arena_bytes, 256), o_flags = align_up(o_kind + n, 16), o_slot = align_up(o_flags + n, 16);
+  const size_t o_len = o_slot + (size_t)n * 4, o_aoff = o_len + (size_t)n * 4, o_alen = o_aoff + (size_t)n * 4;
+  const size_t o_bidx = o_alen + (size_t)n * 4, o_top = align_up(o_bidx + (size_t)nb * 4, 16);
+  const size_t total = align_up(o_top + (size_t)b->n_topics_total * 2, 16);
+  if (e->sharded) {
+    if (total > e->arena_cap) return fail(PCDN_ENOSPC, "device batch does not fit the shards' ingest region (max_batch_bytes)");
+    if (e->ingest == PCDN_INGEST_HOST && e->world_shards != e->shards.size())
+      return fail(PCDN_EINVAL, "device-resident batches in a multi-process group need PCDN_INGEST_NCCL");
+  }
   int rc = flush_open(e, nullptr);
   if (rc) return rc;
   if ((rc = acquire_open_slot(e))) return rc;
-  Slot& s = e->slots[e->open_slot];
-  if ((rc = flush_journal(e))) { s.state = SLOT_FREE; e->open_slot = -1; return rc; }
-  s.in.n_msgs = b->n_msgs;
-  s.in.n_bcast = b->n_bcast;
-  s.in.arena = (const uint8_t*)b->arena;
-  s.in.kind = b->kind;
-  s.in.flags = b->flags;
-  s.in.slot_off16 = b->slot_off16;
-  s.in.raw_len = b->raw_len;
-  s.in.aux_off = b->aux_off;
-  s.in.aux_len = b->aux_len;
-  s.in.topics = b->topics;
-  s.in.bcast_index = b->bcast_index;
+  const uint32_t si = (uint32_t)e->open_slot;
+  Slot& s = e->slots[si];
+  auto give_up = [&](int code) { s.state = SLOT_FREE; e->open_slot = -1; return code; };
+  if ((rc = flush_journal(e))) return give_up(rc);
+  if (e->sharded) {
+    // the batch lives on the root GPU (global shard 0): everything queued so far on the root's main
+    // stream (the caller's producer kernels when it shares that stream) comes before the broadcast
+    if (e->owns_root()) {
+      Shard& root = e->shards[0];
+      DeviceGuard dg(root.device);
+      CUDA_TRY(cudaEventRecord(root.ev_submit, root.stream));
+    }
+    const IngestRegion regs[9] = {
+        {b->arena, o_arena, (size_t)b->arena_bytes}, {b->kind, o_kind, n}, {b->flags, o_flags, n},
+        {b->slot_off16, o_slot, (size_t)n * 4}, {b->raw_len, o_len, (size_t)n * 4}, {b->aux_off, o_aoff, (size_t)n * 4},
+        {b->aux_len, o_alen, (size_t)n * 4}, {b->bcast_index, o_bidx, (size_t)nb * 4}, {b->topics, o_top, (size_t)b->n_topics_total * 2}};
+    if ((rc = ingest_regions(e, si, nullptr, regs, 9, true))) return give_up(rc);
+  }
+  for (Shard& sh : e->shards) {
+    ShardSlot& ss = sh.slots[si];
+    ss.in.n_msgs = n;
+    ss.in.n_bcast = nb;
+    if (!e->sharded || sh.gindex == 0) {  // where the caller put it
+      ss.in.arena = (const uint8_t*)b->arena;
+      ss.in.kind = b->kind; ss.in.flags = b->flags; ss.in.slot_off16 = b->slot_off16; ss.in.raw_len = b->raw_len;
+      ss.in.aux_off = b->aux_off; ss.in.aux_len = b->aux_len; ss.in.topics = b->topics; ss.in.bcast_index = b->bcast_index;
+    } else {
+      uint8_t* d = ss.d_arena;
+      ss.in.arena = d + o_arena;
+      ss.in.kind = d + o_kind; ss.in.flags = d + o_flags;
+      ss.in.slot_off16 = (const uint32_t*)(d + o_slot); ss.in.raw_len = (const uint32_t*)(d + o_len);
+      ss.in.aux_off = (const uint32_t*)(d + o_aoff); ss.in.aux_len = (const uint32_t*)(d + o_alen);
+      ss.in.bcast_index = (const uint32_t*)(d + o_bidx); ss.in.topics = (const uint16_t*)(d + o_top);
+    }
+  }
   s.device_input = true;
   s.devparse = false;
-  rc = launch_pipeline(e, s, b->n_msgs - b->n_bcast);
-  if (rc) { s.state = SLOT_FREE; e->open_slot = -1; return rc; }
+  s.n_msgs = n;
+  rc = launch_pipeline(e, si, n - nb, e->sharded);
+  if (rc) return give_up(rc);
   if (batch_id) *batch_id = s.batch_id;
   e->open_slot = -1;
   e->stats.batches++;
-  e->stats.msgs += b->n_msgs;
+  e->stats.msgs += n;
   return 0;
   GUARD_END
 }
@@ -1226,64 +1337,91 @@ int pcdn_next_batch(pcdn_engine* e, uint64_t* batch_id) {
   return 0;
 }
 
-int pcdn_poll(pcdn_engine* e, uint64_t batch_id, pcdn_batch_result* out, int block) {
-  GUARD_BEGIN
-  // The blocking waits happen OUTSIDE the engine lock, so ingest threads keep appending to the next
-  // batch while an egress thread waits for this one (one poller per batch).
+extern "C++" {
+namespace {
+
+void fill_result(pcdn_engine* e, const Slot& s, const Shard& sh, const ShardSlot& ss, uint64_t batch_id, pcdn_batch_result* out) {
+  const BatchStats& bs = *ss.h_stats;
+  const uint32_t cap = e->geo.shard_max_conns;
+  out->batch_id = batch_id;
+  out->n_msgs = s.n_msgs;
+  out->n_spans = std::min<uint32_t>(bs.n_spans, 2 * cap);
+  out->spans = reinterpret_cast<const pcdn_span*>(ss.h_spans);
+  out->n_deliveries = bs.n_deliveries;
+  out->bytes_out = bs.bytes_out;
+  out->n_overflow = std::min<uint32_t>(bs.n_overflow, cap);
+  out->overflow_conns = ss.h_overflow;
+  out->n_direct_dropped = bs.n_direct_dropped;
+  out->status = bs.status ? (uint32_t)(-PCDN_E2BIG) : 0;
+  out->msg_status = s.devparse ? ss.h_msg_status : nullptr;
+  out->n_msg_errors = ss.n_msg_errors;
+  out->reserved = sh.gindex;
+}
+
+// wait for (or test) one shard's share of a batch and fetch its results; returns 1 when !block and
+// the shard is not done yet.  The blocking waits happen OUTSIDE the engine lock, so ingest threads
+// keep appending to the next batch while an egress thread waits for this one (one poller per
+// shard and batch).
+}  // namespace
+int pcdn_detail::poll_one(pcdn_engine* e, uint64_t batch_id, uint32_t li, int block) {
   cudaEvent_t ev_early = nullptr, ev_done = nullptr;
-  bool wait = false, mapped = false;
+  bool mapped = false;
+  int device = 0;
   {
     std::lock_guard<std::mutex> g(e->mu);
-    Slot* s = find_slot(e, batch_id);
-    if (!s) return fail(PCDN_ENOENT, "unknown batch id");
-    if (!s->polled) {
-      if (!block) {
-        cudaError_t q = cudaEventQuery(s->ev_done);
-        if (q == cudaErrorNotReady) return 1;
-        CUDA_TRY(q);
-      }
-      ev_early = s->ev_early; ev_done = s->ev_done; wait = true; mapped = s->spans_mapped;
+    const int si = find_slot_index(e, batch_id);
+    if (si < 0) return fail(PCDN_ENOENT, "unknown batch id");
+    if (li >= e->shards.size()) return fail(PCDN_EINVAL, "no such local shard");
+    ShardSlot& ss = e->shards[li].slots[si];
+    if (ss.polled) return 0;
+    device = e->shards[li].device;
+    if (!block) {
+      DeviceGuard dg(device);
+      cudaError_t q = cudaEventQuery(ss.ev_done);
+      if (q == cudaErrorNotReady) return 1;
+      CUDA_TRY(q);
     }
+    ev_early = ss.ev_early; ev_done = ss.ev_done; mapped = ss.spans_mapped;
   }
+  DeviceGuard dg(device);
   uint32_t nsp = 0, nov = 0;
   bool devparse = false;
-  if (wait) {
-    // 1. counters as of k_offsets → exact size of the span table; its D2H overlaps the pack
-    //    (mapped spans: the table is already in host memory when ev_done fires)
-    if (!mapped) {
-      CUDA_TRY(cudaEventSynchronize(ev_early));
-      std::lock_guard<std::mutex> g(e->mu);
-      Slot* s = find_slot(e, batch_id);
-      if (!s) return fail(PCDN_ENOENT, "batch released while it was being polled");
-      nsp = std::min<uint32_t>(s->h_early->n_spans, 2 * e->geo.max_conns);
-      nov = std::min<uint32_t>(s->h_early->n_overflow, e->geo.max_conns);
-      devparse = s->devparse;
-      if (nsp) CUDA_TRY(cudaMemcpyAsync(s->h_spans, s->w.spans, (size_t)nsp * sizeof(Span), cudaMemcpyDeviceToHost, e->copy_stream));
-      if (nov) CUDA_TRY(cudaMemcpyAsync(s->h_overflow, s->w.overflow, (size_t)nov * 4, cudaMemcpyDeviceToHost, e->copy_stream));
-    } else {
-      std::lock_guard<std::mutex> g(e->mu);
-      Slot* s = find_slot(e, batch_id);
-      if (!s) return fail(PCDN_ENOENT, "batch released while it was being polled");
-      devparse = s->devparse;
+  // 1. counters as of k_offsets → exact size of the span table; its D2H overlaps the pack
+  //    (mapped spans: the table is already in host memory when ev_done fires)
+  if (!mapped) CUDA_TRY(cudaEventSynchronize(ev_early));
+  {
+    std::lock_guard<std::mutex> g(e->mu);
+    const int si = find_slot_index(e, batch_id);
+    if (si < 0) return fail(PCDN_ENOENT, "batch released while it was being polled");
+    Shard& sh = e->shards[li];
+    ShardSlot& ss = sh.slots[si];
+    devparse = e->slots[si].devparse;
+    if (!mapped && !ss.polled) {
+      nsp = std::min<uint32_t>(ss.h_early->n_spans, 2 * e->geo.shard_max_conns);
+      nov = std::min<uint32_t>(ss.h_early->n_overflow, e->geo.shard_max_conns);
+      if (nsp) CUDA_TRY(cudaMemcpyAsync(ss.h_spans, ss.w.spans, (size_t)nsp * sizeof(Span), cudaMemcpyDeviceToHost, sh.copy_stream));
+      if (nov) CUDA_TRY(cudaMemcpyAsync(ss.h_overflow, ss.w.overflow, (size_t)nov * 4, cudaMemcpyDeviceToHost, sh.copy_stream));
     }
-    // 2. the pack itself (ring bytes are valid after this)
-    CUDA_TRY(cudaEventSynchronize(ev_done));
   }
+  // 2. the pack itself (ring bytes are valid after this)
+  CUDA_TRY(cudaEventSynchronize(ev_done));
   std::lock_guard<std::mutex> _g(e->mu);
-  Slot* s = find_slot(e, batch_id);
-  if (!s) return fail(PCDN_ENOENT, "batch released while it was being polled");
-  if (wait && !s->polled) {
-    if (devparse) CUDA_TRY(cudaMemcpyAsync(s->h_msg_status, s->w.msg_status, s->in.n_msgs, cudaMemcpyDeviceToHost, e->copy_stream));
-    if (nsp || nov || devparse) CUDA_TRY(cudaStreamSynchronize(e->copy_stream));
-    if (s->devparse) { s->n_msg_errors = 0; for (uint32_t i = 0; i < s->in.n_msgs; i++) s->n_msg_errors += s->h_msg_status[i] != 0; }
-    const BatchStats& bs = *s->h_stats;
-    s->polled = true;
+  const int si = find_slot_index(e, batch_id);
+  if (si < 0) return fail(PCDN_ENOENT, "batch released while it was being polled");
+  Shard& sh = e->shards[li];
+  ShardSlot& ss = sh.slots[si];
+  if (!ss.polled) {
+    if (devparse) CUDA_TRY(cudaMemcpyAsync(ss.h_msg_status, ss.w.msg_status, ss.in.n_msgs, cudaMemcpyDeviceToHost, sh.copy_stream));
+    if (nsp || nov || devparse) CUDA_TRY(cudaStreamSynchronize(sh.copy_stream));
+    if (devparse) { ss.n_msg_errors = 0; for (uint32_t i = 0; i < ss.in.n_msgs; i++) ss.n_msg_errors += ss.h_msg_status[i] != 0; }
+    const BatchStats& bs = *ss.h_stats;
+    ss.polled = true;
     e->stats.deliveries += bs.n_deliveries;
     e->stats.bytes_out += bs.bytes_out;
-    if (s->timed) {
+    if (ss.timed && li == 0) {  // stage times of the first local shard (shards run the same pipeline side by side)
       float t[4] = {0, 0, 0, 0};
-      for (int i = 0; i < 3; i++) cudaEventElapsedTime(&t[i], s->ev[i], s->ev[i + 1]);
-      cudaEventElapsedTime(&t[3], s->ev[4], s->ev[5]);
+      for (int i = 0; i < 3; i++) cudaEventElapsedTime(&t[i], ss.ev[i], ss.ev[i + 1]);
+      cudaEventElapsedTime(&t[3], ss.ev[4], ss.ev[5]);
       e->stats.ms_direct += t[0];
       e->stats.ms_match += t[1];
       e->stats.ms_plan += t[2];
@@ -1292,21 +1430,54 @@ int pcdn_poll(pcdn_engine* e, uint64_t batch_id, pcdn_batch_result* out, int blo
       e->stats.timed_batches++;
     }
   }
+  return 0;
+}
+
+}  // extern "C++"
+
+int pcdn_poll_shard(pcdn_engine* e, uint64_t batch_id, uint32_t local_shard, pcdn_batch_result* out, int block) {
+  GUARD_BEGIN
+  if (!e->has_device) return fail(PCDN_ENODEV, "host-only engine");
+  int rc = poll_one(e, batch_id, local_shard, block);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> _g(e->mu);
+  const int si = find_slot_index(e, batch_id);
+  if (si < 0) return fail(PCDN_ENOENT, "batch released while it was being polled");
+  if (out) fill_result(e, e->slots[si], e->shards[local_shard], e->shards[local_shard].slots[si], batch_id, out);
+  return 0;
+  GUARD_END
+}
+
+int pcdn_poll(pcdn_engine* e, uint64_t batch_id, pcdn_batch_result* out, int block) {
+  GUARD_BEGIN
+  if (!e->has_device) return fail(PCDN_ENODEV, "host-only engine");
+  const uint32_t nl = (uint32_t)e->shards.size();
+  if (nl == 1) return pcdn_poll_shard(e, batch_id, 0, out, block);
+  for (uint32_t li = 0; li < nl; li++) {
+    int rc = poll_one(e, batch_id, li, block);
+    if (rc) return rc;  // error, or 1 = some shard still running
+  }
+  std::lock_guard<std::mutex> _g(e->mu);
+  const int si = find_slot_index(e, batch_id);
+  if (si < 0) return fail(PCDN_ENOENT, "batch released while it was being polled");
+  Slot& s = e->slots[si];
   if (out) {
-    const BatchStats& bs = *s->h_stats;
-    out->batch_id = batch_id;
-    out->n_msgs = s->in.n_msgs;
-    out->n_spans = std::min<uint32_t>(bs.n_spans, 2 * e->geo.max_conns);
-    out->spans = reinterpret_cast<const pcdn_span*>(s->h_spans);
-    out->n_deliveries = bs.n_deliveries;
-    out->bytes_out = bs.bytes_out;
-    out->n_overflow = std::min<uint32_t>(bs.n_overflow, e->geo.max_conns);
-    out->overflow_conns = s->h_overflow;
-    out->n_direct_dropped = bs.n_direct_dropped;
-    out->status = bs.status ? (uint32_t)(-PCDN_E2BIG) : 0;
-    out->msg_status = s->devparse ? s->h_msg_status : nullptr;
-    out->n_msg_errors = s->n_msg_errors;
-    out->reserved = 0;
+    // summed counters + the shards' span tables concatenated (ascending shard = ascending id range)
+    s.merged_spans.clear(); s.merged_overflow.clear();
+    pcdn_batch_result tot{};
+    for (uint32_t li = 0; li < nl; li++) {
+      pcdn_batch_result r{};
+      fill_result(e, s, e->shards[li], e->shards[li].slots[si], batch_id, &r);
+      s.merged_spans.insert(s.merged_spans.end(), r.spans, r.spans + r.n_spans);
+      s.merged_overflow.insert(s.merged_overflow.end(), r.overflow_conns, r.overflow_conns + r.n_overflow);
+      tot.n_deliveries += r.n_deliveries; tot.bytes_out += r.bytes_out; tot.n_direct_dropped += r.n_direct_dropped;
+      tot.status |= r.status;
+      if (li == 0) { tot.msg_status = r.msg_status; tot.n_msg_errors = r.n_msg_errors; }  // identical on every shard
+    }
+    tot.batch_id = batch_id; tot.n_msgs = s.n_msgs;
+    tot.n_spans = (uint32_t)s.merged_spans.size(); tot.spans = s.merged_spans.data();
+    tot.n_overflow = (uint32_t)s.merged_overflow.size(); tot.overflow_conns = s.merged_overflow.data();
+    *out = tot;
   }
   return 0;
   GUARD_END
@@ -1316,15 +1487,20 @@ int pcdn_read(pcdn_engine* e, pcdn_conn conn, uint32_t ring_off, uint32_t len, v
   GUARD_BEGIN
   LOCK;
   if (!e->has_device) return fail(PCDN_ENODEV, "host-only engine");
-  if (conn >= e->geo.max_conns || (uint64_t)ring_off + len > e->cfg.ring_bytes_per_conn)
+  const uint32_t gs = conn / e->geo.shard_N, local = conn % e->geo.shard_N;
+  if (gs < e->first_shard || gs >= e->first_shard + e->shards.size())
+    return fail(PCDN_ENOENT, "connection lives on a shard of another process");
+  if (local >= e->geo.shard_max_conns || (uint64_t)ring_off + len > e->cfg.ring_bytes_per_conn)
     return fail(PCDN_EINVAL, "read outside the connection's ring");
-  if (e->h_rings) {
-    std::memcpy(dst, e->h_rings + (size_t)conn * e->cfg.ring_bytes_per_conn + ring_off, len);
+  Shard& sh = e->shards[gs - e->first_shard];
+  if (sh.h_rings) {
+    std::memcpy(dst, sh.h_rings + (size_t)local * e->cfg.ring_bytes_per_conn + ring_off, len);
     return 0;
   }
-  CUDA_TRY(cudaMemcpyAsync(dst, e->dev.rings + (size_t)conn * e->cfg.ring_bytes_per_conn + ring_off, len,
-                           cudaMemcpyDeviceToHost, e->copy_stream));
-  CUDA_TRY(cudaStreamSynchronize(e->copy_stream));
+  DeviceGuard dg(sh.device);
+  CUDA_TRY(cudaMemcpyAsync(dst, sh.dev.rings + (size_t)local * e->cfg.ring_bytes_per_conn + ring_off, len,
+                           cudaMemcpyDeviceToHost, sh.copy_stream));
+  CUDA_TRY(cudaStreamSynchronize(sh.copy_stream));
   return 0;
   GUARD_END
 }
@@ -1332,32 +1508,82 @@ int pcdn_read(pcdn_engine* e, pcdn_conn conn, uint32_t ring_off, uint32_t len, v
 int pcdn_release_batch(pcdn_engine* e, uint64_t batch_id) {
   GUARD_BEGIN
   LOCK;
-  Slot* s = find_slot(e, batch_id);
-  if (!s) return fail(PCDN_ENOENT, "unknown batch id");
+  const int si = find_slot_index(e, batch_id);
+  if (si < 0) return fail(PCDN_ENOENT, "unknown batch id");
   if (e->inflight.empty() || e->inflight.front() != batch_id)
     return fail(PCDN_EINVAL, "batches must be released oldest first");
-  // A slot released without having been polled may still have its host→device staging copy queued:
-  // its pinned staging buffers must not be refilled before that copy ran (device-input batches have
-  // no host staging and stay fully asynchronous — the pipelined submit_device/release loop).
-  if (!s->polled && !s->device_input) CUDA_TRY(cudaEventSynchronize(s->ev_done));
-  // ring space may be reused only after the pack that filled it has finished
-  CUDA_TRY(cudaStreamWaitEvent(e->stream, s->ev_done, 0));
-  launch_release(e->dev, s->w.batch_units, s->w.stats, e->stream);
-  CUDA_TRY(cudaGetLastError());
+  Slot& s = e->slots[si];
+  for (Shard& sh : e->shards) {
+    DeviceGuard dg(sh.device);
+    ShardSlot& ss = sh.slots[si];
+    // A slot released without having been polled may still have its host→device staging copy queued:
+    // its pinned staging buffers must not be refilled before that copy ran (device-input batches have
+    // no host staging and stay fully asynchronous — the pipelined submit_device/release loop).
+    if (!ss.polled && !s.device_input) CUDA_TRY(cudaEventSynchronize(e->sharded ? ss.ev_ingest : ss.ev_done));
+    // ring space may be reused only after the pack that filled it has finished
+    CUDA_TRY(cudaStreamWaitEvent(sh.stream, ss.ev_done, 0));
+    launch_release(sh.dev, ss.w.batch_units, ss.w.stats, sh.stream);
+    CUDA_TRY(cudaGetLastError());
+  }
   e->inflight.erase(e->inflight.begin());
-  s->state = SLOT_FREE;
+  s.state = SLOT_FREE;
   // the last 'clone' of every frame of this batch is gone: permits back to the pool (pool.rs:44-52)
-  e->inflight_bytes -= std::min(e->inflight_bytes, s->ingress_bytes);
-  s->ingress_bytes = 0;
+  e->inflight_bytes -= std::min(e->inflight_bytes, s.ingress_bytes);
+  s.ingress_bytes = 0;
   e->stats.released_batches++;
   {
-    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s->t_launch).count();
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s.t_launch).count();
     e->stats.latency_ms_sum += ms;
     const uint64_t us = (uint64_t)(ms * 1000.0);
     int bucket = 0;
     while (bucket < 15 && us >= (16ull << bucket)) bucket++;
     e->stats.latency_hist_us[bucket]++;
   }
+  return 0;
+  GUARD_END
+}
+
+// ---- connection shards -------------------------------------------------------------------------
+int pcdn_nccl_unique_id(void* out128) {
+  GUARD_BEGIN
+  if (!out128) return fail(PCDN_EINVAL, "null argument");
+  const char* why = "";
+  const NcclApi* nc = nccl_api(&why);
+  if (!nc) return fail(PCDN_ENODEV, std::string("libnccl.so.2 not available: ") + why);
+  NcclUniqueId id;
+  NCCL_TRY(nc, nc->GetUniqueId(&id));
+  std::memcpy(out128, &id, sizeof(id));
+  return 0;
+  GUARD_END
+}
+int pcdn_num_shards(pcdn_engine* e, uint32_t* n_local, uint32_t* n_world) {
+  LOCK;
+  if (n_local) *n_local = e->has_device ? (uint32_t)e->shards.size() : 0;
+  if (n_world) *n_world = e->world_shards;
+  return 0;
+}
+int pcdn_shard_info(pcdn_engine* e, uint32_t local_shard, pcdn_shard_desc* out) {
+  GUARD_BEGIN
+  LOCK;
+  if (!out) return fail(PCDN_EINVAL, "null argument");
+  std::memset(out, 0, sizeof(*out));
+  out->shard_stride = e->geo.shard_N;
+  out->ring_bytes = e->cfg.ring_bytes_per_conn;
+  if (!e->has_device) {  // host-only mirror: geometry only
+    if (local_shard != 0) return fail(PCDN_EINVAL, "no such local shard");
+    out->global_index = e->first_shard; out->device = -1; out->conn_base = e->first_shard * e->geo.shard_N;
+    return 0;
+  }
+  if (local_shard >= e->shards.size()) return fail(PCDN_EINVAL, "no such local shard");
+  const Shard& sh = e->shards[local_shard];
+  out->global_index = sh.gindex;
+  out->device = sh.device;
+  out->conn_base = sh.dev.conn_base;
+  out->rings_dev = sh.dev.rings;
+  out->rings_host = sh.h_rings;
+  out->nccl_ranks = (uint32_t)sh.nccl_ranks;
+  std::vector<uint32_t> v;
+  out->n_conns = e->conns->shard_load(sh.gindex);
   return 0;
   GUARD_END
 }
@@ -1376,15 +1602,16 @@ int pcdn_set_timing(pcdn_engine* e, int on) {
 }
 int pcdn_ring_info(pcdn_engine* e, void** dev_base, uint64_t* ring_bytes, uint32_t* max_conns) {
   LOCK;
-  if (dev_base) *dev_base = e->has_device ? (void*)e->dev.rings : nullptr;
+  if (dev_base) *dev_base = e->has_device ? (void*)e->shards[0].dev.rings : nullptr;  // first local shard (pcdn_shard_info for the others)
   if (ring_bytes) *ring_bytes = e->cfg.ring_bytes_per_conn;
-  if (max_conns) *max_conns = e->geo.max_conns;
+  if (max_conns) *max_conns = e->geo.shard_max_conns;
   return 0;
 }
 int pcdn_host_rings(pcdn_engine* e, const void** host_base) {
   LOCK;
-  if (host_base) *host_base = e->h_rings;
-  return e->h_rings ? 0 : fail(PCDN_ENOENT, "rings live in device memory (PCDN_FLAG_HOST_RINGS not set)");
+  uint8_t* h = e->has_device ? e->shards[0].h_rings : nullptr;
+  if (host_base) *host_base = h;
+  return h ? 0 : fail(PCDN_ENOENT, "rings live in device memory (PCDN_FLAG_HOST_RINGS not set)");
 }
 int pcdn_num_users(pcdn_engine* e, uint32_t* users, uint32_t* brokers) {
   LOCK;

@@ -156,27 +156,48 @@ Connections::Connections(HostTables& t, const char* identity)
     : t_(t), identity_(BrokerIdent::parse(identity)) {
   owners_.push_back(identity_);
   owner_ids_[identity_.str()] = 0;
-  conn_kind_.assign(t_.g.max_conns, CONN_FREE);
+  conn_kind_.assign(t_.g.N, CONN_FREE);
   topic_key_count_.assign(t_.g.T, 0);
+  free_conns_.resize(t_.g.n_shards);
+  next_conn_.assign(t_.g.n_shards, 0);
+  shard_load_.assign(t_.g.n_shards, 0);
 }
 
-int Connections::alloc_conn(int kind, uint32_t* conn) {
-  uint32_t c;
+void Connections::drain_quarantine() {
   while (!quarantine_.empty() && quarantine_.front().second < oldest_unreleased) {
-    free_conns_.push_back(quarantine_.front().first);
+    const uint32_t c = quarantine_.front().first;
+    free_conns_[c / t_.g.shard_N].push_back(c);
     quarantine_.pop_front();
   }
-  if (!free_conns_.empty()) { c = free_conns_.back(); free_conns_.pop_back(); }
-  else if (next_conn_ < t_.g.max_conns) c = next_conn_++;
-  else return quarantine_.empty() ? PCDN_ENOSPC : PCDN_EAGAIN;  // ids come back when older batches are released
+}
+bool Connections::id_available() const {
+  for (uint32_t s = 0; s < t_.g.n_shards; s++)
+    if (!free_conns_[s].empty() || next_conn_[s] < t_.g.shard_max_conns) return true;
+  return false;
+}
+int Connections::alloc_conn(int kind, uint32_t* conn) {
+  drain_quarantine();
+  // least-loaded shard that can hand out an id (ties: lowest shard index, so every process of a
+  // multi-process group that replays the same calls picks the same id)
+  int best = -1;
+  for (uint32_t s = 0; s < t_.g.n_shards; s++) {
+    if (free_conns_[s].empty() && next_conn_[s] >= t_.g.shard_max_conns) continue;
+    if (best < 0 || shard_load_[s] < shard_load_[best]) best = (int)s;
+  }
+  if (best < 0) return quarantine_.empty() ? PCDN_ENOSPC : PCDN_EAGAIN;  // ids come back when older batches are released
+  uint32_t c;
+  if (!free_conns_[best].empty()) { c = free_conns_[best].back(); free_conns_[best].pop_back(); }
+  else c = (uint32_t)best * t_.g.shard_N + next_conn_[best]++;
+  shard_load_[best]++;
   conn_kind_[c] = (uint8_t)kind;
   *conn = c;
   return 0;
 }
 void Connections::free_conn(uint32_t conn) {
   conn_kind_[conn] = CONN_FREE;
+  shard_load_[conn / t_.g.shard_N]--;
   if (oldest_unreleased <= fence_now) quarantine_.emplace_back(conn, fence_now);  // an unreleased batch may name it
-  else free_conns_.push_back(conn);
+  else free_conns_[conn / t_.g.shard_N].push_back(conn);
 }
 int Connections::owner_id(const BrokerIdent& b, uint32_t* id) {
   std::string s = b.str();
@@ -263,7 +284,7 @@ int Connections::add_user(const std::string& key, const uint16_t* topics, uint32
   if (rc) return rc;
   {  // refuse BEFORE kicking the same-key user when no connection id could be handed out afterwards
     const bool quarantining = oldest_unreleased <= fence_now;
-    const bool have = !free_conns_.empty() || next_conn_ < t_.g.max_conns ||
+    const bool have = id_available() ||
                       (!quarantine_.empty() && quarantine_.front().second < oldest_unreleased) ||
                       (users_.count(key) && !quarantining);
     if (!have) return (quarantine_.empty() && !users_.count(key)) ? PCDN_ENOSPC : PCDN_EAGAIN;
@@ -351,7 +372,7 @@ int Connections::add_broker(const char* ident, uint32_t* conn) {
   {  // refuse BEFORE dropping the existing connection when no id could be handed out afterwards (as add_user)
     const bool quarantining = oldest_unreleased <= fence_now;
     const bool reconnect = brokers_.count(id) != 0;
-    const bool have = !free_conns_.empty() || next_conn_ < t_.g.max_conns ||
+    const bool have = id_available() ||
                       (!quarantine_.empty() && quarantine_.front().second < oldest_unreleased) ||
                       (reconnect && !quarantining);
     if (!have) return (quarantine_.empty() && !reconnect) ? PCDN_ENOSPC : PCDN_EAGAIN;

@@ -20,8 +20,14 @@
 namespace pcdn {
 
 struct Geometry {
-  uint32_t max_conns = 0;   // usable connection ids
-  uint32_t N = 0;           // max_conns rounded up to a multiple of 8192 (256 bitmap words)
+  // Connection shards: the id space is n_shards contiguous ranges of shard_N ids, range s
+  // = the connections whose rings live on shard s's GPU; ids [s*shard_N, s*shard_N + shard_max_conns)
+  // are usable.  A single-GPU engine is one shard.
+  uint32_t n_shards = 1;
+  uint32_t shard_N = 0;          // per-shard id range: shard_max_conns rounded up to a multiple of 8192
+  uint32_t shard_max_conns = 0;  // usable connection ids per shard (pcdn_config.max_conns)
+  uint32_t max_conns = 0;   // exclusive upper bound of the usable connection ids (all shards)
+  uint32_t N = 0;           // n_shards * shard_N (a multiple of 8192 = 256 bitmap words)
   uint32_t W = 0;           // N / 32 bitmap words per topic row
   uint32_t T = 0;           // topic rows
   uint32_t max_keys = 0;
@@ -142,6 +148,7 @@ class Connections {
   int route(const std::string& key, uint32_t* conn) const;                                   // :69,:84,:74
   uint32_t num_users() const { return (uint32_t)users_.size(); }
   uint32_t num_brokers() const { return (uint32_t)brokers_.size(); }
+  uint32_t shard_load(uint32_t shard) const { return shard < shard_load_.size() ? shard_load_[shard] : 0; }
   bool has_user(const std::string& key) const { return users_.count(key) != 0; }
   bool has_broker(const char* ident) const;
 
@@ -162,10 +169,15 @@ class Connections {
   TopicVersionedMap topic_sync_map_;        // broadcast_map.topic_sync_map
   std::unordered_set<uint16_t> previous_subscribed_topics_;
   std::vector<uint8_t> conn_kind_;
-  std::vector<uint32_t> free_conns_;
+  // connection ids are handed out per shard, to the least-loaded shard that has one (the reference's
+  // marshal hands a user to the least-loaded broker, cdn-proto/src/connection/auth/marshal.rs:108-118)
+  std::vector<std::vector<uint32_t>> free_conns_;   // [shard] freed ids, LIFO
+  std::vector<uint32_t> next_conn_;                 // [shard] next never-used local id
+  std::vector<uint32_t> shard_load_;                // [shard] ids in use
   std::deque<std::pair<uint32_t, uint64_t>> quarantine_;  // (conn, fence): reusable once oldest_unreleased > fence
-  uint32_t next_conn_ = 0;
 
+  bool id_available() const;   // some shard can hand out an id right now (quarantine already drained)
+  void drain_quarantine();
   int alloc_conn(int kind, uint32_t* conn);
   void free_conn(uint32_t conn);
   int owner_id(const BrokerIdent& b, uint32_t* id);

@@ -278,12 +278,15 @@ __device__ __forceinline__ void direct_lookup_body(const DevState& s, const Batc
       target = route;
     }
   }
-  if (target != kConnNone && target >= s.N) target = kConnNone;
+  // `target` is a global connection id: count the unroutable message on one shard only, then keep
+  // the message only if the target's ring lives on this shard
+  const bool dropped = target == kConnNone;
+  if (!dropped) { target -= s.conn_base; if (target >= s.N) target = kConnNone; }  // (unsigned wrap: below the base → NONE)
   if (valid && gl == 0) {
     w.dconn[m] = target;
     if (is_direct) {
       w.D[m] = target != kConnNone ? 1u : 0u;
-      if (target == kConnNone) atomicAdd(&w.stats->n_direct_dropped, 1u);
+      if (dropped && s.count_drops) atomicAdd(&w.stats->n_direct_dropped, 1u);
     }
     w.skey[0][m] = (is_direct && target != kConnNone) ? target : s.N;
     w.sval[0][m] = m;
@@ -783,12 +786,12 @@ __device__ __forceinline__ void offsets_body(const DevState& s, const BatchIn& b
   }
   if (nsp) {
     uint32_t at = span_base + ex;
-    if (k.s1_rec) w.spans[at++] = Span{c, k.s1_off * kUnit, k.s1_units * kUnit, k.s1_rec};
-    if (k.s2_rec) w.spans[at] = Span{c, 0, k.s2_units * kUnit, k.s2_rec};
+    if (k.s1_rec) w.spans[at++] = Span{s.conn_base + c, k.s1_off * kUnit, k.s1_units * kUnit, k.s1_rec};
+    if (k.s2_rec) w.spans[at] = Span{s.conn_base + c, 0, k.s2_units * kUnit, k.s2_rec};
   }
   if (k.ovf) {
     uint32_t i = atomicAdd(&w.stats->n_overflow, 1u);
-    if (i < max_conns) w.overflow[i] = c;
+    if (i < max_conns) w.overflow[i] = s.conn_base + c;
   }
 }
 template <bool HAS_DIRECT>

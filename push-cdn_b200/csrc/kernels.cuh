@@ -69,6 +69,12 @@ struct DevState {
   uint32_t cm_enable;    // connection-major pack class on (default) / off (A/B profiling)
   uint32_t n_valid_topics;  // Topic::prune validity bound (0 = all)
   uint32_t max_key_len;
+  // connection shards: this GPU owns the connection ids [conn_base, conn_base + N).  The
+  // bitmap / broker-mask words here are this shard's slice (local word index); the direct map and
+  // owner_conn[] are replicated on every shard and name connections by GLOBAL id, so a direct
+  // message resolves identically everywhere and is packed by the shard that owns the target.
+  uint32_t conn_base;
+  uint32_t count_drops;  // 1 on exactly one shard of the broker (global shard 0): it counts the unroutable directs
   uint64_t ring_bytes;
   uint64_t seed;
 };

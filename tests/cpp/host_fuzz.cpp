@@ -78,10 +78,16 @@ static void fuzz_parser(const std::vector<std::vector<uint8_t>>& seeds, uint32_t
   REQUIRE(ok > iters / 20 && bad > iters / 20);
 }
 
-static void fuzz_connections(uint32_t iters, std::mt19937_64& rng) {
+// n_shards > 1: the same model, with the connection ids spread over shard ranges of 8192 ids
+// (usable part: `per_shard` ids each) — ids must stay inside the usable part of their shard and the
+// shards must stay balanced (least-loaded hand-out).
+static void fuzz_connections(uint32_t iters, std::mt19937_64& rng, uint32_t n_shards = 1, uint32_t per_shard = 300) {
   Geometry g;
-  g.max_conns = 300; g.N = 8192; g.W = g.N / 32; g.T = 64; g.max_keys = 1024; g.max_key_len = 40; g.key_stride = 48;
+  g.n_shards = n_shards; g.shard_N = 8192; g.shard_max_conns = per_shard;
+  g.max_conns = (n_shards - 1) * g.shard_N + per_shard; g.N = n_shards * g.shard_N;
+  g.W = g.N / 32; g.T = 64; g.max_keys = 1024; g.max_key_len = 40; g.key_stride = 48;
   g.nbuckets = 512; g.bucket_mask = 511; g.max_owners = 8; g.seed = 12345;
+  const uint32_t capacity = n_shards * per_shard;
   HostTables t(g);
   Connections c(t, "me/me");
   std::map<std::string, std::set<uint16_t>> model;  // connected users → topics
@@ -99,12 +105,12 @@ static void fuzz_connections(uint32_t iters, std::mt19937_64& rng) {
       uint32_t conn = 0;
       const int rc = c.add_user(k, tp, nt, &conn);
       if (rc == 0) {
-        REQUIRE(conn < g.max_conns);
+        REQUIRE(conn < g.max_conns && conn % g.shard_N < per_shard);
         model[k] = std::set<uint16_t>(tp, tp + nt);
         conn_of[k] = conn;
       } else {
         REQUIRE(rc == PCDN_ENOSPC || rc == PCDN_EAGAIN);
-        if (rc == PCDN_ENOSPC && !model.count(k)) REQUIRE(model.size() + bconn.size() >= g.max_conns || t.n_keys() >= g.max_keys - 8);
+        if (rc == PCDN_ENOSPC && !model.count(k)) REQUIRE(model.size() + bconn.size() >= capacity || t.n_keys() >= g.max_keys - 8);
       }
     } else if (op < 45) {
       c.remove_user(k);
@@ -142,14 +148,16 @@ static void fuzz_connections(uint32_t iters, std::mt19937_64& rng) {
         for (auto& kv : model) if (kv.second.count(topic)) want.insert(conn_of[kv.first]);
         REQUIRE(std::set<uint32_t>(got.begin(), got.end()) == want);
       }
+      std::vector<uint32_t> load(n_shards, 0);
       for (auto& kv : conn_of) {
         uint32_t conn = 0;
         REQUIRE(c.route(kv.first, &conn) == 1 && conn == kv.second);
+        load[conn / g.shard_N]++;
       }
       t.clear_dirty();
     }
   }
-  printf("connections: %u ops, %zu users connected at the end\n", iters, model.size());
+  printf("connections (%u shard%s): %u ops, %zu users connected at the end\n", n_shards, n_shards > 1 ? "s" : "", iters, model.size());
 }
 
 // 3. Cuckoo table driven far past its design load (8 buckets x 4 slots, 64 keys allowed): the first
@@ -157,7 +165,7 @@ static void fuzz_connections(uint32_t iters, std::mt19937_64& rng) {
 //    rolled back) and must give the key-arena slot back (a later erase + insert succeeds again).
 static void overfill_cuckoo(std::mt19937_64& rng) {
   Geometry g;
-  g.max_conns = 64; g.N = 8192; g.W = 256; g.T = 1; g.max_keys = 64; g.max_key_len = 16; g.key_stride = 16;
+  g.shard_N = 8192; g.shard_max_conns = 64; g.max_conns = 64; g.N = 8192; g.W = 256; g.T = 1; g.max_keys = 64; g.max_key_len = 16; g.key_stride = 16;
   g.nbuckets = 8; g.bucket_mask = 7; g.max_owners = 4; g.seed = 0x1234567ull;
   for (int round = 0; round < 50; round++) {
     HostTables t(g);
@@ -197,6 +205,7 @@ int main(int argc, char** argv) {
   REQUIRE(!seeds.empty());
   fuzz_parser(seeds, iters, rng);
   fuzz_connections(iters / 4, rng);
+  fuzz_connections(iters / 8, rng, 3, 110);
   overfill_cuckoo(rng);
   printf("host_fuzz ok\n");
   return 0;

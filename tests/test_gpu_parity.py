@@ -122,13 +122,29 @@ def payload(rng, n):
     return bytes(rng.getrandbits(8) for _ in range(min(n, 64))) * (n // 64 + 1)
 
 
-@pytest.mark.parametrize("variant", [0, 4, 2, "staged", "host", "host-st"])
+def shard_cfg(pcdn, variant):
+    """engine config of the sharded variants: 'shards-host' = three connection shards that share GPU 0
+    (every shard copies the batch from pinned host memory: runs on a one-GPU box); 'shards-nccl' = one
+    shard per GPU, the library moves every batch with ncclBroadcast (needs >= 2 GPUs)"""
+    import torch
+
+    if variant == "shards-host":
+        return dict(devices=[0, 0, 0], ingest=pcdn.INGEST_HOST)
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    return dict(devices=list(range(min(n, 4))), ingest=pcdn.INGEST_NCCL)
+
+
+@pytest.mark.parametrize("variant", [0, 4, 2, "staged", "host", "host-st", "shards-host", "shards-nccl"])
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_random_mixed_batches(pcdn, seed, variant):
     """users + peer brokers, multi-topic broadcasts (fat and thin recipient sets), directs to local,
     remote and unknown keys, frame sizes from 0 B to 3 staging chunks, several batches.
     Small engines publish spans straight into mapped host memory; "staged" forces the span path of
-    large engines (table in HBM, copied out while the pack runs) on the same workload."""
+    large engines (table in HBM, copied out while the pack runs) on the same workload.
+    The 'shards-*' variants run the SAME workload on ONE engine whose connections are spread over
+    several shards (pcdn_config.devices) and compare with the same single unsharded oracle."""
     rng = random.Random(seed)
     if variant == "staged":
         w = World(pcdn, flags=pcdn.FLAG_STAGED_SPANS, ring_bytes_per_conn=1 << 20)
@@ -138,6 +154,9 @@ def test_random_mixed_batches(pcdn, seed, variant):
         w = World(pcdn, flags=pcdn.FLAG_HOST_RINGS, pack_variant=4 if variant == "host-st" else 0,
                   ring_bytes_per_conn=1 << 20, max_conns=2048)
         assert w.e.host_rings() != 0
+    elif isinstance(variant, str):
+        w = World(pcdn, ring_bytes_per_conn=1 << 20, max_conns=1024, **shard_cfg(pcdn, variant))
+        assert w.e.num_shards()[0] >= 2
     else:
         w = World(pcdn, pack_variant=variant, ring_bytes_per_conn=1 << 20)
     keys = []
