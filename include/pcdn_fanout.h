@@ -378,6 +378,58 @@ int pcdn_shard_info(pcdn_engine* e, uint32_t local_shard, pcdn_shard_desc* out);
  * span tables concatenated into one engine-owned array (a host copy: convenience, not the fast path). */
 int pcdn_poll_shard(pcdn_engine* e, uint64_t batch_id, uint32_t local_shard, pcdn_batch_result* out, int block);
 
+/* ---- egress: the consumer of the span table -------------------------------------------------
+ * Replaces the per-connection writer task (cdn-proto/src/connection/protocols/mod.rs:156-186: pop a
+ * queued message, write_length_delimited :354-394 to the socket) and Connection::soft_close
+ * (:287-306).  pcdn_egress_drain makes one batch's framed records readable by the host: per local
+ * shard a gather kernel packs the records of a chunk of spans into one contiguous device buffer, one
+ * large DMA per chunk brings it into pinned host memory (double-buffered: PCIe stays busy while the
+ * sink consumes), and the sink is called with the chunk.  With PCDN_FLAG_HOST_RINGS the sink reads the
+ * rings in place (no copy).  The built-in sink (pcdn_egress_write_batch) writes every span to the file
+ * descriptor attached to its connection with writev — u32 BE length + raw bytes per record, padding
+ * skipped, per-connection order kept — on a small thread pool; a failed write detaches the
+ * connection and reports it (pcdn_egress_failed), the analogue of the reference removing a peer
+ * whose send failed (cdn-broker/src/tasks/user/sender.rs:24-30).                                    */
+typedef struct pcdn_egress pcdn_egress;
+typedef struct pcdn_egress_config {
+  uint32_t struct_size; /* = sizeof(pcdn_egress_config)                                              */
+  uint32_t n_threads;   /* writer threads of the fd sink (0 = min(16, cores))                         */
+  uint64_t chunk_bytes; /* pinned staging per chunk (0 = 64 MiB); 3 host + 2 device chunks per shard  */
+} pcdn_egress_config;
+typedef struct pcdn_egress_chunk {
+  uint32_t local_shard;
+  uint32_t n_spans;
+  const pcdn_span* spans;   /* this chunk's spans, span-table order (a wrapped connection's two spans are adjacent) */
+  const uint64_t* data_off; /* [n_spans] byte offset of span i's first record inside `data`            */
+  const uint8_t* data;      /* host memory, valid during the callback                                  */
+  uint64_t bytes;           /* bytes of `data` covered by this chunk                                   */
+} pcdn_egress_chunk;
+typedef int (*pcdn_egress_sink)(void* user, const pcdn_egress_chunk* chunk); /* non-zero aborts the drain */
+typedef struct pcdn_egress_stats {
+  uint64_t bytes;            /* ring bytes made host-readable (record padding included)               */
+  uint64_t spans, chunks;
+  uint64_t records;          /* fd sink: records written                                               */
+  uint64_t fd_bytes;         /* fd sink: bytes accepted by writev (= sum of 4+L)                       */
+  uint64_t fd_writes;        /* fd sink: writev calls                                                  */
+  uint64_t unattached_spans; /* fd sink: spans of connections without a file descriptor (skipped)      */
+  uint64_t failed_conns;     /* connections reported by pcdn_egress_failed and not yet fetched         */
+  double seconds;            /* wall time of the drain                                                 */
+} pcdn_egress_stats;
+int pcdn_egress_create(pcdn_engine* e, const pcdn_egress_config* cfg /* NULL = defaults */, pcdn_egress** out);
+void pcdn_egress_destroy(pcdn_egress* g);
+/* poll + hand every chunk of the batch (all local shards) to `sink` (NULL = only stage the bytes) */
+int pcdn_egress_drain(pcdn_egress* g, uint64_t batch_id, pcdn_egress_sink sink, void* user, pcdn_egress_stats* out);
+/* Connection::from_stream analogue: this connection's socket / pipe / memfd */
+int pcdn_egress_attach(pcdn_egress* g, pcdn_conn conn, int fd);
+int pcdn_egress_detach(pcdn_egress* g, pcdn_conn conn);
+/* drain with the built-in writev sink */
+int pcdn_egress_write_batch(pcdn_egress* g, uint64_t batch_id, pcdn_egress_stats* out);
+/* connections whose write failed since the last call (engine-owned array): the host removes them (R13) */
+int pcdn_egress_failed(pcdn_egress* g, const pcdn_conn** conns, uint32_t* n);
+/* Connection::soft_close protocols/mod.rs:287-306: launches the open batch, writes and RELEASES every
+ * batch in flight (oldest first), then detaches `conn` and hands its descriptor back for closing.  */
+int pcdn_egress_soft_close(pcdn_egress* g, pcdn_conn conn, int* fd_out);
+
 /* ---- introspection (tests, metrics: cdn-proto/src/connection/metrics.rs:12-28) ------------- */
 int pcdn_get_stats(pcdn_engine* e, pcdn_stats* out);
 int pcdn_set_timing(pcdn_engine* e, int on);

@@ -24,8 +24,8 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpcdn_fanout.so")
 INCLUDE = os.path.join(_ROOT, "include")
 
-SOURCES = ["engine.cu", "kernels.cu", "host_state.cpp", "frame_parse.cpp", "nccl_dl.cpp"]
-HEADERS = ["kernels.cuh", "host_state.h", "frame_parse.h", "frame_parse_core.h", "hash.h", "nccl_dl.h"]
+SOURCES = ["engine.cu", "kernels.cu", "egress.cu", "host_state.cpp", "frame_parse.cpp", "nccl_dl.cpp"]
+HEADERS = ["kernels.cuh", "host_state.h", "frame_parse.h", "frame_parse_core.h", "hash.h", "nccl_dl.h", "engine_internal.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-pthread", "-shared",
@@ -125,6 +125,24 @@ class ShardDesc(C.Structure):
                 ("nccl_ranks", C.c_uint32)]
 
 
+class EgressConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("n_threads", C.c_uint32), ("chunk_bytes", C.c_uint64)]
+
+
+class EgressChunk(C.Structure):
+    _fields_ = [("local_shard", C.c_uint32), ("n_spans", C.c_uint32), ("spans", C.POINTER(Span)),
+                ("data_off", C.POINTER(C.c_uint64)), ("data", C.c_void_p), ("bytes", C.c_uint64)]
+
+
+EGRESS_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(EgressChunk))
+
+
+class EgressStats(C.Structure):
+    _fields_ = [("bytes", C.c_uint64), ("spans", C.c_uint64), ("chunks", C.c_uint64), ("records", C.c_uint64),
+                ("fd_bytes", C.c_uint64), ("fd_writes", C.c_uint64), ("unattached_spans", C.c_uint64),
+                ("failed_conns", C.c_uint64), ("seconds", C.c_double)]
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("batches", C.c_uint64), ("msgs", C.c_uint64), ("deliveries", C.c_uint64), ("bytes_out", C.c_uint64),
@@ -191,6 +209,14 @@ ABI = {
     "pcdn_num_shards": (_ci, [_vp, C.POINTER(_u32), C.POINTER(_u32)]),
     "pcdn_shard_info": (_ci, [_vp, _u32, C.POINTER(ShardDesc)]),
     "pcdn_poll_shard": (_ci, [_vp, _u64, _u32, C.POINTER(BatchResult), _ci]),
+    "pcdn_egress_create": (_ci, [_vp, C.POINTER(EgressConfig), C.POINTER(_vp)]),
+    "pcdn_egress_destroy": (None, [_vp]),
+    "pcdn_egress_drain": (_ci, [_vp, _u64, EGRESS_SINK, _vp, C.POINTER(EgressStats)]),
+    "pcdn_egress_attach": (_ci, [_vp, _u32, _ci]),
+    "pcdn_egress_detach": (_ci, [_vp, _u32]),
+    "pcdn_egress_write_batch": (_ci, [_vp, _u64, C.POINTER(EgressStats)]),
+    "pcdn_egress_failed": (_ci, [_vp, C.POINTER(C.POINTER(_u32)), C.POINTER(_u32)]),
+    "pcdn_egress_soft_close": (_ci, [_vp, _u32, C.POINTER(_ci)]),
     "pcdn_get_stats": (_ci, [_vp, C.POINTER(Stats)]),
     "pcdn_set_timing": (_ci, [_vp, _ci]),
     "pcdn_ring_info": (_ci, [_vp, C.POINTER(_vp), C.POINTER(_u64), C.POINTER(_u32)]),
@@ -576,3 +602,68 @@ class Engine:
         kind, conn = C.c_int(), C.c_uint32()
         self._chk(self.L.pcdn_debug_route(self.h, key, len(key), C.byref(kind), C.byref(conn)))
         return kind.value, (-1 if conn.value == CONN_NONE else conn.value)
+
+
+class Egress:
+    """The consumer of span tables (pcdn_egress_*): drains a batch's framed records into host memory
+    chunk by chunk and hands them to a sink — a Python callback, or the built-in writev sink that
+    writes every connection's records to the file descriptor attached to it."""
+
+    def __init__(self, engine: Engine, n_threads: int = 0, chunk_bytes: int = 0):
+        self.e, self.L = engine, engine.L
+        cfg = EgressConfig(C.sizeof(EgressConfig), n_threads, chunk_bytes)
+        h = C.c_void_p()
+        engine._chk(self.L.pcdn_egress_create(engine.h, C.byref(cfg), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pcdn_egress_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def attach(self, conn: int, fd: int) -> None:
+        self.e._chk(self.L.pcdn_egress_attach(self.h, conn, fd))
+
+    def detach(self, conn: int) -> None:
+        self.e._chk(self.L.pcdn_egress_detach(self.h, conn))
+
+    def drain(self, batch_id: int, sink=None) -> EgressStats:
+        """sink(chunk: EgressChunk) -> None, called once per chunk; None only stages the bytes"""
+        st = EgressStats()
+        err = []
+
+        def tramp(_user, chunk):
+            try:
+                sink(chunk.contents)
+                return 0
+            except BaseException as ex:  # never unwind through the C frames
+                err.append(ex)
+                return 1
+
+        cb = EGRESS_SINK(tramp) if sink is not None else C.cast(None, EGRESS_SINK)
+        rc = self.L.pcdn_egress_drain(self.h, batch_id, cb, None, C.byref(st))
+        if err:
+            raise err[0]
+        self.e._chk(rc)
+        return st
+
+    def write_batch(self, batch_id: int) -> EgressStats:
+        st = EgressStats()
+        self.e._chk(self.L.pcdn_egress_write_batch(self.h, batch_id, C.byref(st)))
+        return st
+
+    def failed(self) -> List[int]:
+        p, n = C.POINTER(C.c_uint32)(), C.c_uint32()
+        self.e._chk(self.L.pcdn_egress_failed(self.h, C.byref(p), C.byref(n)))
+        return [p[i] for i in range(n.value)]
+
+    def soft_close(self, conn: int) -> int:
+        fd = C.c_int(-1)
+        self.e._chk(self.L.pcdn_egress_soft_close(self.h, conn, C.byref(fd)))
+        return fd.value
