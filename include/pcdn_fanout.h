@@ -230,6 +230,7 @@ typedef struct pcdn_stats {
   /* the LATENCY histogram (metrics.rs:21-23) of the same launch → release time, log2 buckets in
    * microseconds: [0] < 16 us, [i] = [8 << i, 16 << i) us for i = 1..14, [15] >= 262 ms            */
   uint64_t latency_hist_us[16];
+  uint64_t kernel_launches;     /* CUDA kernels launched by this library in this process (all engines) */
 } pcdn_stats;
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */

@@ -149,7 +149,7 @@ class Stats(C.Structure):
         ("ms_match", C.c_double), ("ms_plan", C.c_double), ("ms_direct", C.c_double), ("ms_pack", C.c_double),
         ("ms_total", C.c_double), ("timed_batches", C.c_uint64), ("inflight_bytes", C.c_uint64),
         ("released_batches", C.c_uint64), ("latency_ms_sum", C.c_double), ("bytes_in", C.c_uint64),
-        ("latency_hist_us", C.c_uint64 * 16),
+        ("latency_hist_us", C.c_uint64 * 16), ("kernel_launches", C.c_uint64),
     ]
 
 

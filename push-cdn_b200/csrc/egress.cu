@@ -239,6 +239,7 @@ int drain_shard(pcdn_egress* g, uint64_t batch_id, uint32_t li, pcdn_egress_sink
     if (s.dev_used[db]) CUDA_TRY(cudaStreamWaitEvent(s.gs, s.ev_dev_free[db], 0));  // the DMA that last read this device buffer
     CUDA_TRY(cudaMemcpyAsync(s.d_desc[db], hd, (size_t)n * sizeof(GatherDesc), cudaMemcpyHostToDevice, s.gs));
     const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sh.n_sms * 8, ((uint64_t)n * 32 + 255) / 256);
+    count_kernel_launch();
     k_gather_spans<<<grid, 256, 0, s.gs>>>(sh.dev.rings, s.d_desc[db], n, s.d_stage[db]);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(s.ev_gather[db], s.gs));

@@ -1592,6 +1592,7 @@ int pcdn_shard_info(pcdn_engine* e, uint32_t local_shard, pcdn_shard_desc* out) 
 int pcdn_get_stats(pcdn_engine* e, pcdn_stats* out) {
   LOCK;
   e->stats.inflight_bytes = e->inflight_bytes;
+  e->stats.kernel_launches = kernel_launches();
   *out = e->stats;
   return 0;
 }

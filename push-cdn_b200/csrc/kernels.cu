@@ -3,9 +3,15 @@
 // bound by HBM bandwidth; there is deliberately no tensor-core code.
 #include "kernels.cuh"
 
+#include <atomic>
+
 #include "frame_parse_core.h"
 
 namespace pcdn {
+
+// every kernel launch of the library is counted (pcdn_stats.kernel_launches: what bench.py reports as gpu_launches)
+std::atomic<unsigned long long> g_kernel_launches{0};
+#define PCDN_COUNT_LAUNCH (void)g_kernel_launches.fetch_add(1, std::memory_order_relaxed)
 
 // =============================================================================== small helpers
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
@@ -123,10 +129,10 @@ void launch_apply_updates(const DevState& s, const Upd32* u32, uint32_t n32, con
                           const uint32_t* key_slots, const uint8_t* key_bytes, uint32_t nkeys, cudaStream_t st) {
   if (nkeys) {
     uint64_t th = (uint64_t)nkeys * (s.key_stride >> 4);
-    k_apply_keys<<<(unsigned)((th + 255) / 256), 256, 0, st>>>(s, key_slots, key_bytes, nkeys);
+    PCDN_COUNT_LAUNCH, k_apply_keys<<<(unsigned)((th + 255) / 256), 256, 0, st>>>(s, key_slots, key_bytes, nkeys);
   }
-  if (nslot) k_apply_slots<<<(nslot + 255) / 256, 256, 0, st>>>(s, us, nslot);
-  if (n32) k_apply_u32<<<(n32 + 255) / 256, 256, 0, st>>>(s, u32, n32);
+  if (nslot) PCDN_COUNT_LAUNCH, k_apply_slots<<<(nslot + 255) / 256, 256, 0, st>>>(s, us, nslot);
+  if (n32) PCDN_COUNT_LAUNCH, k_apply_u32<<<(n32 + 255) / 256, 256, 0, st>>>(s, u32, n32);
 }
 
 // =============================================================================== generic u32 scan
@@ -160,10 +166,10 @@ __global__ void k_scan_c(uint32_t* __restrict__ out, uint32_t n, const uint32_t*
 }
 static void scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp, cudaStream_t st) {
   uint32_t tiles = (n + 1023) / 1024;
-  k_scan_a<<<tiles, 256, 0, st>>>(in, out, n, tmp);
+  PCDN_COUNT_LAUNCH, k_scan_a<<<tiles, 256, 0, st>>>(in, out, n, tmp);
   if (tiles > 1) {
-    k_scan_b<<<1, 256, 0, st>>>(tmp, tiles);
-    k_scan_c<<<(n + 255) / 256, 256, 0, st>>>(out, n, tmp);
+    PCDN_COUNT_LAUNCH, k_scan_b<<<1, 256, 0, st>>>(tmp, tiles);
+    PCDN_COUNT_LAUNCH, k_scan_c<<<(n + 255) / 256, 256, 0, st>>>(out, n, tmp);
   }
 }
 
@@ -207,7 +213,7 @@ __global__ void __launch_bounds__(256) k_parse(DevState s, BatchIn b, Work w) {
 }
 void launch_parse(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st) {
   cudaMemsetAsync(w.msg_status, 0, b.n_msgs, st);
-  k_parse<<<(b.n_msgs + 255) / 256, 256, 0, st>>>(s, b, w);
+  PCDN_COUNT_LAUNCH, k_parse<<<(b.n_msgs + 255) / 256, 256, 0, st>>>(s, b, w);
 }
 
 // =============================================================================== K3 direct lookup
@@ -299,6 +305,8 @@ __global__ void __launch_bounds__(256) k_direct_lookup(DevState s, BatchIn b, Wo
 // ---- stable LSD radix sort of (target conn, msg index), 8-bit digits ---------------------------
 constexpr uint32_t kSortTile = 2048;
 size_t sort_tiles(uint32_t n) { return (n + kSortTile - 1) / kSortTile; }
+unsigned long long kernel_launches() { return g_kernel_launches.load(std::memory_order_relaxed); }
+void count_kernel_launch() { PCDN_COUNT_LAUNCH; }
 
 __global__ void __launch_bounds__(256) k_sort_hist(const uint32_t* __restrict__ key, uint32_t n, uint32_t shift,
                                                    uint32_t* __restrict__ hist, uint32_t ntiles) {
@@ -414,10 +422,10 @@ void launch_batch_begin(const DevState&, const Work& w, const BatchIn&, bool, cu
 
 void launch_direct(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st) {
   const uint32_t n = b.n_msgs;
-  k_direct_lookup<<<(n * 8 + 255) / 256, 256, 0, st>>>(s, b, w);
+  PCDN_COUNT_LAUNCH, k_direct_lookup<<<(n * 8 + 255) / 256, 256, 0, st>>>(s, b, w);
   if (n <= kSmallSort) {
-    k_sort_small<<<1, 256, 0, st>>>(w.skey[0], w.sval[0], n);
-    k_bucket_bounds<<<(n + 255) / 256, 256, 0, st>>>(w.skey[0], n, w.dstart, w.dend, w.dstamp, w.stamp);
+    PCDN_COUNT_LAUNCH, k_sort_small<<<1, 256, 0, st>>>(w.skey[0], w.sval[0], n);
+    PCDN_COUNT_LAUNCH, k_bucket_bounds<<<(n + 255) / 256, 256, 0, st>>>(w.skey[0], n, w.dstart, w.dend, w.dstamp, w.stamp);
     return;
   }
   uint32_t bits = 1;
@@ -426,9 +434,9 @@ void launch_direct(const DevState& s, const Work& w, const BatchIn& b, cudaStrea
   const uint32_t ntiles = (uint32_t)sort_tiles(n);
   int cur = 0;
   for (uint32_t p = 0; p < passes; p++) {
-    k_sort_hist<<<ntiles, 256, 0, st>>>(w.skey[cur], n, p * 8, w.hist, ntiles);
+    PCDN_COUNT_LAUNCH, k_sort_hist<<<ntiles, 256, 0, st>>>(w.skey[cur], n, p * 8, w.hist, ntiles);
     scan_u32(w.hist, w.hist, 256 * ntiles, w.hist_tmp, st);
-    k_sort_scatter<<<ntiles, 256, 0, st>>>(w.skey[cur], w.sval[cur], w.skey[cur ^ 1], w.sval[cur ^ 1], n, p * 8,
+    PCDN_COUNT_LAUNCH, k_sort_scatter<<<ntiles, 256, 0, st>>>(w.skey[cur], w.sval[cur], w.skey[cur ^ 1], w.sval[cur ^ 1], n, p * 8,
                                            w.hist, ntiles);
     cur ^= 1;
   }
@@ -436,7 +444,7 @@ void launch_direct(const DevState& s, const Work& w, const BatchIn& b, cudaStrea
     cudaMemcpyAsync(w.skey[0], w.skey[1], (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(w.sval[0], w.sval[1], (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
   }
-  k_bucket_bounds<<<(n + 255) / 256, 256, 0, st>>>(w.skey[0], n, w.dstart, w.dend, w.dstamp, w.stamp);
+  PCDN_COUNT_LAUNCH, k_bucket_bounds<<<(n + 255) / 256, 256, 0, st>>>(w.skey[0], n, w.dstart, w.dend, w.dstamp, w.stamp);
 }
 
 // =============================================================================== K1a topic match
@@ -528,7 +536,7 @@ __global__ void __launch_bounds__(256) k_match(DevState s, BatchIn b, Work w) {
 void launch_match(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st) {
   if (!b.n_bcast) return;
   dim3 grid((s.nblk + 7) / 8, b.n_bcast);
-  k_match<<<grid, 256, 0, st>>>(s, b, w);
+  PCDN_COUNT_LAUNCH, k_match<<<grid, 256, 0, st>>>(s, b, w);
 }
 
 // =============================================================================== K1p plan
@@ -658,15 +666,15 @@ __global__ void __launch_bounds__(256) k_plan_direct_c(BatchIn b, Work w) {
 void launch_plan(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st) {
   const uint32_t nblk = (b.n_msgs + 255) / 256;
   if (b.n_bcast == 0 && nblk > 1) {
-    k_plan_direct_a<<<nblk, 256, 0, st>>>(b, w);
-    k_plan_direct_b<<<1, 256, 0, st>>>(w, nblk);
-    k_plan_direct_c<<<(b.n_msgs + 1 + 255) / 256, 256, 0, st>>>(b, w);
+    PCDN_COUNT_LAUNCH, k_plan_direct_a<<<nblk, 256, 0, st>>>(b, w);
+    PCDN_COUNT_LAUNCH, k_plan_direct_b<<<1, 256, 0, st>>>(w, nblk);
+    PCDN_COUNT_LAUNCH, k_plan_direct_c<<<(b.n_msgs + 1 + 255) / 256, 256, 0, st>>>(b, w);
     return;
   }
-  k_plan_a<<<nblk, 256, 0, st>>>(s, b, w, nblk);
+  PCDN_COUNT_LAUNCH, k_plan_a<<<nblk, 256, 0, st>>>(s, b, w, nblk);
   if (nblk == 1) return;  // finished inside k_plan_a
-  k_plan_b<<<4, 256, 0, st>>>(w, nblk);
-  k_plan_c<<<(b.n_msgs + 1 + 255) / 256, 256, 0, st>>>(b, w, nblk);
+  PCDN_COUNT_LAUNCH, k_plan_b<<<4, 256, 0, st>>>(w, nblk);
+  PCDN_COUNT_LAUNCH, k_plan_c<<<(b.n_msgs + 1 + 255) / 256, 256, 0, st>>>(b, w, nblk);
 }
 
 // =============================================================================== K1b offsets
@@ -799,8 +807,8 @@ __global__ void __launch_bounds__(256) k_offsets(DevState s, BatchIn b, Work w, 
   offsets_body<HAS_DIRECT, 256>(s, b, w, max_conns, blockIdx.x * 256 + threadIdx.x);  // N is a multiple of 8192
 }
 void launch_offsets(const DevState& s, const Work& w, const BatchIn& b, bool has_direct, cudaStream_t st) {
-  if (has_direct) k_offsets<true><<<s.N / 256, 256, 0, st>>>(s, b, w, s.N);
-  else k_offsets<false><<<s.N / 256, 256, 0, st>>>(s, b, w, s.N);
+  if (has_direct) PCDN_COUNT_LAUNCH, k_offsets<true><<<s.N / 256, 256, 0, st>>>(s, b, w, s.N);
+  else PCDN_COUNT_LAUNCH, k_offsets<false><<<s.N / 256, 256, 0, st>>>(s, b, w, s.N);
 }
 
 // =============================================================================== fused control (small engines)
@@ -925,8 +933,8 @@ k_ctrl_small(DevState s, BatchIn b, Work w, int zero_stats, BatchStats* publish)
 }
 void launch_ctrl_small(const DevState& s, const Work& w, const BatchIn& b, bool has_direct, bool zero_stats,
                        BatchStats* publish, cudaStream_t st) {
-  if (has_direct) k_ctrl_small<true><<<8, 1024, 0, st>>>(s, b, w, zero_stats ? 1 : 0, publish);
-  else k_ctrl_small<false><<<8, 1024, 0, st>>>(s, b, w, zero_stats ? 1 : 0, publish);
+  if (has_direct) PCDN_COUNT_LAUNCH, k_ctrl_small<true><<<8, 1024, 0, st>>>(s, b, w, zero_stats ? 1 : 0, publish);
+  else PCDN_COUNT_LAUNCH, k_ctrl_small<false><<<8, 1024, 0, st>>>(s, b, w, zero_stats ? 1 : 0, publish);
 }
 
 // =============================================================================== K2a pack (fat)
@@ -1253,9 +1261,9 @@ void launch_pack(const DevState& s, const Work& w, const BatchIn& b, uint32_t va
   // the 128 KB message-major tile (DevState::fat_tile_bytes); bits 8+ = CTAs per SM.
   const uint32_t ctas_per_sm = (variant >> 8) ? (variant >> 8) : 3;
   const uint32_t grid = (uint32_t)n_sms * ctas_per_sm;
-  if (variant & 4) k_pack<0><<<grid, 256, 0, st>>>(s, b, w, thin_separate ? 0 : 1);
-  else k_pack<1><<<grid, 256, 0, st>>>(s, b, w, thin_separate ? 0 : 1);
-  if (thin_separate) k_pack_thin<<<(uint32_t)n_sms * 8, 256, 0, st>>>(s, b, w);
+  if (variant & 4) PCDN_COUNT_LAUNCH, k_pack<0><<<grid, 256, 0, st>>>(s, b, w, thin_separate ? 0 : 1);
+  else PCDN_COUNT_LAUNCH, k_pack<1><<<grid, 256, 0, st>>>(s, b, w, thin_separate ? 0 : 1);
+  if (thin_separate) PCDN_COUNT_LAUNCH, k_pack_thin<<<(uint32_t)n_sms * 8, 256, 0, st>>>(s, b, w);
 }
 
 // =============================================================================== release
@@ -1276,7 +1284,7 @@ __global__ void __launch_bounds__(256) k_release(DevState s, const uint32_t* __r
   }
 }
 void launch_release(const DevState& s, const uint32_t* batch_units, const BatchStats* stats, cudaStream_t st) {
-  k_release<<<(s.N / 4 + 255) / 256, 256, 0, st>>>(s, batch_units, stats);
+  PCDN_COUNT_LAUNCH, k_release<<<(s.N / 4 + 255) / 256, 256, 0, st>>>(s, batch_units, stats);
 }
 
 }  // namespace pcdn

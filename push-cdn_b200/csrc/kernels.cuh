@@ -169,5 +169,7 @@ void launch_ctrl_small(const DevState& s, const Work& w, const BatchIn& b, bool 
 void launch_pack(const DevState& s, const Work& w, const BatchIn& b, uint32_t variant, int n_sms, cudaStream_t st);
 void launch_release(const DevState& s, const uint32_t* batch_units, const BatchStats* stats, cudaStream_t st);
 size_t sort_tiles(uint32_t n);
+unsigned long long kernel_launches();   // launches issued by this library in this process so far
+void count_kernel_launch();
 
 }  // namespace pcdn

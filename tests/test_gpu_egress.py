@@ -66,6 +66,7 @@ def test_drain_to_host_memory_matches_oracle(pcdn, mode):
         b = w.e.flush()
         got = {}
         st = eg.drain(b, lambda ch: chunk_streams(ch, got))
+        assert w.e.poll(b).n_overflow == 0
         w.e.release_batch(b)
         want = {c: wire(fr) for c, fr in w.expect().items()}
         assert {c: bytes(v) for c, v in got.items()} == want
@@ -80,7 +81,7 @@ def test_drain_to_host_memory_matches_oracle(pcdn, mode):
 def test_writer_to_file_descriptors(pcdn, mode):
     """>= 1 K sinks: every attached connection's memfd must hold exactly the oracle's stream for that
     connection over several batches; connections without a descriptor are counted, not written."""
-    cfg = dict(max_conns=2048, ring_bytes_per_conn=1 << 17)
+    cfg = dict(max_conns=2048, ring_bytes_per_conn=3 << 18)   # 768 KiB: a batch never overflows a ring, several wrap it
     if mode == "host-rings":
         cfg["flags"] = pcdn.FLAG_HOST_RINGS
     if mode == "shards-host":
@@ -101,6 +102,7 @@ def test_writer_to_file_descriptors(pcdn, mode):
         traffic(w, rng, keys, 30)
         b = w.e.flush()
         st = eg.write_batch(b)
+        assert w.e.poll(b).n_overflow == 0
         w.e.release_batch(b)
         exp = w.expect()
         for c, fr in exp.items():
