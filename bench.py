@@ -133,24 +133,29 @@ def reference_arm(args, rank, world):
     cores = min(cores, max(1, n_conns // 1024))  # the port starts its worker threads per step: tiny shapes run serially
     cal = run_cpu_reference(n_conns, payload, 1, 1, 0, cores)
     per_msg = max(cal["seconds"], 1e-6)
-    budget = 150.0
-    msgs = args.msgs
-    while msgs > 1 and per_msg * msgs * (args.steps + args.warmup) > budget:
-        msgs //= 2
-    r = run_cpu_reference(n_conns, payload, msgs, args.steps, args.warmup, cores)
+    budget = 240.0
+    msgs = args.msgs            # the SAME batch as the GPU arm (same_config): a long run is cut in steps, never in the batch
+    steps, warmup = args.steps, args.warmup
+    est = lambda: per_msg * msgs * (steps + warmup) / max(1, min(msgs, cores // 2))
+    while steps > 1 and est() > budget:
+        steps = max(1, steps // 2)
+        warmup = min(warmup, 1)
+    r = run_cpu_reference(n_conns, payload, msgs, steps, warmup, cores)
     gbps = r["gbps"]
     line = {
-        "impl": "reference", "metric": METRIC, "value": gbps, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(1, args.steps), "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": gbps, "unit": "GB/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "steps_requested": args.steps, "ms_per_step": 1e3 * r["seconds"] / max(1, steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "deliveries_per_s": r["deliveries_per_s"],
         "config": {"workload": "C2: 2^20 subscribers, 1 topic, 1 KiB broadcast" if (n_conns, payload) == (N_CONNS, PAYLOAD) else
                    "%d subscribers, 1 topic, %d B broadcast" % (n_conns, payload), "n_conns": n_conns, "payload": payload,
-                   "msgs_per_step": msgs, "note": "C++ restatement of cdn-broker's CPU path (reference is Rust, not buildable here); "
-                   "bounded sample: %d of %d messages per step" % (msgs, args.msgs)},
+                   "msgs_per_step": msgs, "frame_bytes": r["frame_bytes"],
+                   "note": "C++ restatement of cdn-broker's CPU path (reference is Rust, not buildable here): persistent threads, "
+                           "writer tasks overlap the receive loops; same batch as the GPU arm, %d of the %d requested steps timed" % (steps, args.steps)},
         "cpu_baseline": {"value": gbps, "unit": "GB/s", "cores": r["threads"], "kind": "port",
-                         "sample": "%d msgs x %d subscribers per step, %d steps" % (msgs, n_conns, args.steps),
-                         "stage12_s": r["stage12_s"], "stage3_s": r["stage3_s"]},
+                         "sample": "%d msgs x %d subscribers per step, %d steps" % (msgs, n_conns, steps),
+                         "median_step_value": r.get("gbps_median_step"), "router_threads": r.get("router_threads"),
+                         "writer_threads": r.get("writer_threads"), "stage12_s": r["stage12_s"], "stage3_s": r["stage3_s"]},
         "e2e": {"value": gbps, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -170,6 +175,8 @@ def main():
     ap.add_argument("--ring-records", type=int, default=RING_RECORDS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configs (C4 direct, C5 sparse, C3 mixed; N=1 only)")
+    ap.add_argument("--sustain", type=float, default=2.0, help="seconds of the sustained window reported beside the K-step number (0 = skip)")
     ap.add_argument("--no-e2e-host", action="store_true", help="skip the e2e_host leg (egress drain of every byte to host memory)")
     ap.add_argument("--ingest", choices=["nccl", "host"], default="nccl",
                     help="N>1: how the library brings a batch to every GPU (pcdn_config.ingest). nccl = H2D on shard 0 + one "
@@ -295,6 +302,7 @@ def main():
         sync_all()
         sampler = ClockSampler(local)
         sampler.start()
+        launches0 = eng.stats().kernel_launches
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
         for _ in range(args.steps):
@@ -302,6 +310,7 @@ def main():
         drain_device()                        # waits (on the stream) for the last pack
         ev1.record(stream)
         sync_all()
+        gpu_launches = int(eng.stats().kernel_launches - launches0)   # counted by the library at every launch site
     ms = ev0.elapsed_time(ev1)
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -310,6 +319,33 @@ def main():
     deliveries_step = M * n_conns
     egress_step = deliveries_step * F
     value = world * egress_step * args.steps / (ms_max * 1e-3) / 1e9
+
+    # ---- sustained window: the same loop for >= 2 s (K steps take ~30 ms: too short to see clocks settle) ----
+    sustained = None
+    if args.sustain > 0:
+        n_sus = max(args.steps, int(args.sustain * 1e3 / max(ms_max / args.steps, 1e-3)) + 1)
+        with torch.cuda.stream(stream):
+            sync_all()
+            s2 = ClockSampler(local)
+            s2.start()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(n_sus):
+                step_device()
+            drain_device()
+            e1.record(stream)
+            sync_all()
+        t_s = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_s, op=dist.ReduceOp.MAX)
+        sus_ms = float(t_s.item())
+        sustained = {"value": world * egress_step * n_sus / (sus_ms * 1e-3) / 1e9, "unit": "GB/s", "steps": n_sus,
+                     "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / n_sus, "clocks": s2.stop()}
+    # `clocks`: sampled from the start of the K-step region to the end of the sustained window (the same
+    # loop, continuously under load; the K steps alone last ~30 ms = less than one nvidia-smi sample)
+    clocks_timed = sampler.stop()
+    sampler = ClockSampler(local)   # (the e2e legs below keep their own clock record)
+    sampler.start()
 
     # ---- correctness of what was just timed: counters + every ring byte ----------------------------
     verify = "skipped"
@@ -362,11 +398,12 @@ def main():
     pack_bytes = M * (n_conns * F + L)          # algorithmic bytes of one pack launch: D*F stores + L read per message
     peak, peak_src = measured_peak()
     achieved = pack_bytes / (ms_pack * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_source = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
             traffic = json.load(open(tp)).get("k_pack_dram_bytes_per_launch")
+            traffic_source = "static ncu capture (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one --set full launch)"
         except Exception:
             traffic = None
 
@@ -460,15 +497,34 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
             cores = os.cpu_count() or 1
-            r = run_cpu_reference(n_conns, args.payload, M, 2, 1, cores, timeout=600)
-            cpu = {"value": r["gbps"], "unit": "GB/s", "cores": r["threads"], "kind": "port",
-                   "sample": "%d msgs x %d subscribers per step, 2 steps after 1 warm-up" % (M, n_conns),
+            r = run_cpu_reference(n_conns, args.payload, M, 3, 1, cores, timeout=600)
+            cpu = {"value": r["gbps_median_step"], "unit": "GB/s", "cores": r["threads"], "kind": "port",
+                   "sample": "%d msgs x %d subscribers per step, median of 3 steps after 1 warm-up (mean over the 3: %.3f GB/s)" % (M, n_conns, r["gbps"]),
+                   "model": r.get("model"),
                    "deliveries_per_s": r["deliveries_per_s"], "stage12_s": r["stage12_s"], "stage3_s": r["stage3_s"]}
         except Exception as ex:  # the baseline is reported, never required for our number
             cpu = {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
 
+    # ---- secondary configs (BASELINE.json C4 / C5 sparse / C3) so that the driver's run covers them ----
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        eng.close()          # the C2 engine's 18 GB of rings go back before the next engines are built
+        eng = None
+        secondary = {}
+        for wl, extra in (("C4", []), ("C5sparse", []), ("C3", [])):
+            try:
+                out = subprocess.run([sys.executable, os.path.join(ROOT, "bench_configs.py"), "--workload", wl, "--steps", "10", "--warmup", "3"] + extra,
+                                     capture_output=True, text=True, timeout=420, check=True)
+                d = json.loads(out.stdout.strip().splitlines()[-1])
+                secondary[wl] = {"workload": d["config"]["workload"], "value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"],
+                                 "msgs_per_s": d["msgs_per_s"], "deliveries_per_s": d["deliveries_per_s"],
+                                 "algorithmic_GBps": d["algorithmic_GBps"], "frac": d["frac_of_hbm_peak"],
+                                 "frac_note": "ALGORITHMIC bytes of the whole step (SURVEY 8d) / step time / measured HBM peak",
+                                 "stage_ms": d["roofline"]["stage_ms"], "verify": d["verify"], "clocks": d["clocks"]}
+            except Exception as ex:
+                secondary[wl] = {"error": repr(ex)[:300]}
+
     if rank == 0:
-        launches_per_step = 5  # k_match, k_plan_a, k_offsets, k_pack, k_release
         line = {
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -485,7 +541,7 @@ def main():
                        if world > 1 else "single GPU", "l2": "outputs 9.1 GB/step >> L2; inputs 8.7 KB (algorithmically resident)",
                        "pack_variant": args.variant, "verify": verify, "setup_s": round(setup_s, 2)},
             "roofline": {"bound": "hbm", "kernel": "k_pack (connection-major phase)" if not (args.variant & 2) else "k_pack (message-major phase)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": pack_bytes, "ms_per_launch": ms_pack,
                          "stage_ms": {"match": ms_match, "plan_offsets": ms_plan, "pack": ms_pack}},
             "cpu_baseline": cpu,
@@ -496,11 +552,16 @@ def main():
                             "host reads back counters + span table only.  e2e_host below is the same step with every byte brought "
                             "to host memory"},
             "e2e_host": e2e_host,
-            "clocks": clocks,
-            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks_timed, "clocks_e2e": clocks,
+            "gpu_launches": gpu_launches,
+            "gpu_launches_note": "kernels launched by libpcdn_fanout.so inside the timed region (library-side counter at every launch site): "
+                                 "k_match, k_plan_a, k_offsets, k_pack, k_release per step",
+            "sustained": sustained,
+            "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
-    eng.close()
+    if eng is not None:
+        eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

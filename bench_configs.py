@@ -93,9 +93,6 @@ def main():
     ap.add_argument("--hit", type=float, default=1.0, help="C4: fraction of recipients that exist")
     ap.add_argument("--ingest", choices=["host", "device"], default=None,
                     help="C4 only: measure end-to-end ingest of RAW FRAMES from host memory through pcdn_receive_frames with the host parser or the device parse kernel")
-    ap.add_argument("--mgpu-ingest", choices=["nccl", "p2p"], default="nccl",
-                    help="config 5 under torchrun: NCCL broadcast of the batch per step, or peer-memory ingest (rank 0's buffer "
-                         "mapped with CUDA IPC; the pack kernel stages frames from it over NVLink, no collective)")
     args = ap.parse_args()
     import torch
 
@@ -321,58 +318,42 @@ def main():
         dense = wl == "C5dense"
         M = 8 if dense else 64
         T = 1 if dense else 1024
-        rng = np.random.default_rng(7 + 1000 * rank)   # every rank: a different shard of the population
-        keys = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
-        keys[:, :8] = np.arange(n, dtype=np.uint64).view(np.uint8).reshape(n, 8)
-        keys[:, 8] = rank
+        # N > 1: ONE sharded engine (pcdn_config.world_shards = N, this process drives shard `rank`);
+        # every rank replays the same control plane over the whole population of N x 2^20 subscribers
+        n_total = world * n
+        rng = np.random.default_rng(7)
+        keys = rng.integers(0, 256, size=(n_total, 32), dtype=np.uint8)
+        keys[:, :8] = np.arange(n_total, dtype=np.uint64).view(np.uint8).reshape(n_total, 8)
         if dense:
-            subs = np.zeros((n, 1), dtype=np.uint16)
+            subs = np.zeros((n_total, 1), dtype=np.uint16)
         else:
-            subs = np.stack([rng.permutation(T)[:4] for _ in range(1024)])[rng.integers(0, 1024, size=n)].astype(np.uint16)
+            subs = np.stack([rng.permutation(T)[:4] for _ in range(1024)])[rng.integers(0, 1024, size=n_total)].astype(np.uint16)
         frames = [bcast_frame_n(bytes([m & 0xFF]), bytes(((i * 31 + m) & 0xFF) for i in range(K))) for m in range(M)]
         L = len(frames[0]); slot = (4 + L + 15) // 16 * 16; rec = (4 + L + 31) // 32 * 32
-        eng = pkg.Engine(device=local, stream=stream.cuda_stream, max_conns=n, max_topics=max(T, 16), max_keys=n, max_key_len=32,
+        shard_kw = {}
+        if world > 1:
+            uid = [pkg.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            shard_kw = dict(devices=[local], world_shards=world, first_shard=rank, nccl_unique_id=uid[0])
+        eng = pkg.Engine(device=local, stream=stream.cuda_stream, max_conns=n, max_topics=max(T, 16), max_keys=n_total, max_key_len=32,
                          ring_bytes_per_conn=16 * rec, max_batch_msgs=M, max_batch_bcast=M, max_batch_bytes=4 << 20,
-                         max_batch_deliveries=M * n if dense else 1 << 22, batch_slots=2, pack_variant=args.variant)
+                         max_batch_deliveries=M * n if dense else 1 << 22, batch_slots=2, pack_variant=args.variant, **shard_kw)
         nsub = subs.shape[1]
-        eng.add_users_bulk(keys, 32, subs.reshape(-1).copy(), (np.arange(n + 1) * nsub).astype(np.uint32))
+        conn_ids = eng.add_users_bulk(keys, 32, subs.reshape(-1).copy(), (np.arange(n_total + 1) * nsub).astype(np.uint32))
+        sd = eng.shard_info(0)
+        mine = (conn_ids // sd.shard_stride) == rank          # the connections whose rings live on this GPU
+        assert int(mine.sum()) == n == sd.n_conns and (world == 1 or sd.nccl_ranks == world)
+        subs = subs[mine]
         topics = np.zeros(M, dtype=np.int64) if dense else np.random.default_rng(70).integers(0, T, size=M)  # same on all ranks
         arena = np.zeros(M * slot + 64, dtype=np.uint8)
         for m, fr in enumerate(frames):
             arena[m * slot + 4:m * slot + 4 + L] = np.frombuffer(fr, dtype=np.uint8)
         mk = lambda a: DeviceBatch(pkg, torch, dev, a, np.full(M, 4), np.zeros(M), np.arange(M) * (slot // 16), np.full(M, L),
                                    np.arange(M), np.ones(M), topics, np.arange(M))
-        db = mk(arena)
-        p2p = world > 1 and args.mgpu_ingest == "p2p"
-        if p2p:
-            from cuda.bindings import runtime as rt
-
-            def ck(res):
-                assert int(res[0]) == 0, "CUDA runtime error %r" % (res[0],)
-                return res[1] if len(res) > 1 else None
-
-            nbytes = db.arena.numel()
-            blob = [None]
-            if rank == 0:
-                p2p_ptr = int(ck(rt.cudaMalloc(nbytes)))
-                ck(rt.cudaMemcpy(p2p_ptr, db.arena.data_ptr(), nbytes, rt.cudaMemcpyKind.cudaMemcpyDeviceToDevice))
-                blob[0] = bytes(ck(rt.cudaIpcGetMemHandle(p2p_ptr)).reserved)
-            dist.broadcast_object_list(blob, src=0)
-            if rank != 0:
-                h = rt.cudaIpcMemHandle_t()
-                h.reserved = blob[0]
-                p2p_ptr = int(ck(rt.cudaIpcOpenMemHandle(h, rt.cudaIpcMemLazyEnablePeerAccess)))
-            # same descriptors, frames read from rank 0's HBM (peer memory) by the pack kernel
-            d0 = db.db
-            db.db = pkg.DeviceBatch(d0.n_msgs, d0.n_bcast, p2p_ptr, nbytes, db.kind.data_ptr(), db.flags.data_ptr(), db.slot.data_ptr(),
-                                    db.len.data_ptr(), db.aoff.data_ptr(), db.alen.data_ptr(), db.topics.data_ptr(), len(topics),
-                                    db.bidx.data_ptr())
-            if rank != 0:
-                db.arena.zero_()   # nothing local to fall back on
-            dist.barrier()
-        elif world > 1:
-            # ranks other than 0 start from zeroed ingest buffers: the frames they fan out arrive by NCCL
-            dbs = [mk(arena if rank == 0 else np.zeros_like(arena)) for _ in range(2)]
+        db = None
+        # two ingest buffers alternate (the library's broadcast of step i+1 runs while step i's pack reads
+        # the other one); ranks other than 0 hold zeros: what they fan out arrives over NVLink
+        dbs = [mk(arena if rank == 0 else np.zeros_like(arena)) for _ in range(2)]
         per_topic = np.bincount(subs.reshape(-1), minlength=max(T, 1))
         expect_deliveries = int(per_topic[topics].sum())
         alg_bytes = lambda d, bo: bo + M * L + M * (n // 8)
@@ -417,46 +398,23 @@ def main():
 
     prev = 0
     it = 0
-    p2p = world > 1 and args.mgpu_ingest == "p2p"
-    nccl_ingest = world > 1 and not p2p
-    if nccl_ingest:
-        comm = torch.cuda.Stream(device=dev)
-        ev_ready = [torch.cuda.Event(), torch.cuda.Event()]
-        ev_free = [torch.cuda.Event(), torch.cuda.Event()]
-
-        def prefetch(k):  # NCCL ingest of the next batch on a side stream, overlapping the current pack
-            with torch.cuda.stream(comm):
-                comm.wait_event(ev_free[k])
-                dist.broadcast(dbs[k].arena, src=0)
-                ev_ready[k].record(comm)
+    multi = wl in ("C5dense", "C5sparse")
 
     with torch.cuda.stream(stream):
         def step():
             nonlocal prev, it
-            if nccl_ingest:
-                k = it & 1
-                if it == 0:
-                    prefetch(0)
-                stream.wait_event(ev_ready[k])
-                it += 1
-                b = eng.submit_device(dbs[k].db)
-            else:
-                b = eng.submit_device(db.db)
+            b = eng.submit_device((dbs[it & 1] if multi else db).db)   # N > 1: the library broadcasts it to every shard
+            it += 1
             if prev:
                 eng.release_batch(prev)
             prev = b
-            if nccl_ingest:
-                ev_free[k].record(stream)
-                prefetch(k ^ 1)
 
         def drain():
             nonlocal prev, it
             if prev:
                 eng.release_batch(prev)
                 prev = 0
-            if nccl_ingest:
-                torch.cuda.current_stream().wait_stream(comm)
-                it = 0
+            it = 0
 
         for _ in range(max(3, args.warmup)):
             step()
@@ -480,15 +438,12 @@ def main():
             tm = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)   # max over ranks
             ms = float(tm.item())
-            if nccl_ingest:  # what was fanned out on this rank arrived over NCCL: must equal rank 0's frames
-                want = torch.from_numpy(arena).to(dev)
-                assert torch.equal(dbs[0].arena, want) and torch.equal(dbs[1].arena, want), "NCCL ingest differs"
         # counters of one batch + per-stage device times
         eng.set_timing(True)
         s0 = eng.stats()
         res = None
         for _ in range(max(3, args.steps // 2)):
-            b = eng.submit_device((dbs[0] if nccl_ingest else db).db)
+            b = eng.submit_device((dbs[0] if multi else db).db)
             res = eng.poll(b)
             d, bo, dropped, ovf, status = res.n_deliveries, res.bytes_out, res.n_direct_dropped, res.n_overflow, res.status
             eng.release_batch(b)
@@ -502,15 +457,14 @@ def main():
     peak, peak_src = B.measured_peak()
     step_s = ms * 1e-3 / args.steps
     ab = alg_bytes(d, bo)
-    pack_bytes = bo + int(db.len.sum().item())
+    pack_bytes = bo + int((dbs[0] if multi else db).len.sum().item())
     bo_all, d_all = bo, d
     if world > 1:
         tot = torch.tensor([bo, d], dtype=torch.float64, device=dev)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)   # whole job = sum of the shards
         bo_all, d_all = float(tot[0].item()), float(tot[1].item())
-        desc = dict(desc, parallelism="connection shards x%d (2^20 per GPU), " % world +
-                    ("peer-memory ingest: the pack kernel stages the frames from rank 0's HBM over NVLink (CUDA IPC), no collective" if p2p
-                     else "one NCCL broadcast of the batch per step, prefetched on a side stream"))
+        desc = dict(desc, parallelism="connection shards x%d (2^20 per GPU) behind one sharded engine; the library broadcasts each batch "
+                                      "from rank 0's GPU with ncclBroadcast on its ingest stream (%d ranks)" % (world, sd.nccl_ranks))
         if rank != 0:
             eng.close()
             dist.barrier()
@@ -526,6 +480,8 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "k_pack", "achieved": pack_bytes / (st["ms_pack"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": pack_bytes / (st["ms_pack"] * 1e-3) / 1e9 / peak, "peak_source": peak_src, "stage_ms": st},
         "clocks": clocks,
+        "verify": "engine counters == analytically expected deliveries (%d per step), no overflow, status 0" % int(d) if expect_deliveries is not None
+                  else "engine counters consistent (hit rate < 1: dropped = %d), no overflow" % int(dropped),
     }
     print(json.dumps(line), flush=True)
     eng.close()

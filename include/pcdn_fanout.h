@@ -53,7 +53,8 @@ enum {
   PCDN_EKIND = -9,     /* message kind not allowed on this connection type (=> disconnect)      */
   PCDN_ENOENT = -10,   /* unknown batch id / connection                                         */
   PCDN_EAGAIN = -11,   /* all batch slots in flight: poll + release one first                   */
-  PCDN_E2BIG = -12     /* batch exceeded max_batch_deliveries on the device; nothing was packed */
+  PCDN_E2BIG = -12,    /* batch exceeded max_batch_deliveries on the device; nothing was packed */
+  PCDN_EHOOK = -13     /* the message hook returned an error (=> caller disconnects peer)       */
 };
 
 /* ---- vocabulary --------------------------------------------------------------------------- */
@@ -317,6 +318,38 @@ int pcdn_user_receive(pcdn_engine* e, const uint8_t* sender_key, uint32_t key_le
  * Broadcast only (to_user(s)_only = true, no prune); other kinds return 1 = "not routed here". */
 int pcdn_broker_receive(pcdn_engine* e, const char* identifier, const uint8_t* raw,
                         uint32_t raw_len);
+/* ---- MessageHookDef (cdn-proto/src/def.rs:79-92) -------------------------------------------------
+ * The reference calls `hook.on_message_received(&mut message)` after Message::deserialize and before
+ * the dispatch, in user_receive_loop (cdn-broker/src/tasks/user/handler.rs:110-118) and in
+ * broker_receive_loop (tasks/broker/handler.rs:137-144): Ok(SkipMessage) => the frame is ignored,
+ * Ok(ProcessMessage) => dispatch (with whatever the hook changed in the parsed message), Err => the
+ * receive loop ends (the peer is disconnected).  The hook sees the PARSED message and may rewrite its
+ * routing fields; the bytes that are forwarded stay the inbound frame (the reference forwards
+ * `raw_message`, not a re-serialisation).
+ *
+ * The callback runs on the thread that calls pcdn_user_receive / pcdn_broker_receive /
+ * pcdn_receive_frames, with the engine lock held: it must not call back into the same engine.
+ * A hooked origin is always parsed on the host: PCDN_FLAG_DEVICE_PARSE is bypassed for its frames
+ * (the device parser never shows a message to the host) and pcdn_receive_frames takes its
+ * sequential path.  pcdn_handle_*_message / pcdn_submit are below the hook, as in the reference.   */
+enum { PCDN_HOOK_PROCESS = 0, PCDN_HOOK_SKIP = 1 };  /* HookResult; any negative return = Err */
+typedef struct pcdn_hook_message {
+  uint8_t kind;             /* PCDN_KIND_*                                                          */
+  uint8_t origin;           /* 0 = user connection, 1 = broker connection                           */
+  uint16_t n_topics;        /* Broadcast / Subscribe / Unsubscribe: entries of `topics`; may be lowered */
+  uint8_t* topics;          /* the parsed topic list (wire values, before Topic::prune); rewritable  */
+  const uint8_t* recipient; /* Direct: recipient key; may be re-pointed (read before the hook returns) */
+  uint32_t recipient_len;
+  uint32_t raw_len;
+  const uint8_t* raw;       /* the inbound frame (read-only; forwarded verbatim)                    */
+  const uint8_t* sender;    /* set_identifier analogue: the user's public key / the broker identifier string */
+  uint32_t sender_len;
+  uint32_t reserved;
+} pcdn_hook_message;
+typedef int (*pcdn_message_hook)(void* user, pcdn_hook_message* msg);
+/* origin 0 = Inner::user_message_hook, 1 = Inner::broker_message_hook (cdn-broker/src/lib.rs); cb NULL removes it */
+int pcdn_set_message_hook(pcdn_engine* e, int origin, pcdn_message_hook cb, void* user);
+
 /* Many inbound frames in one call (one lock, no per-call FFI cost): frame i enters
  * user_receive_loop (origin 0, `sender` = that user's key) or broker_receive_loop (origin 1).
  * rc_out[i] (optional) gets what pcdn_user_receive / pcdn_broker_receive would have returned.

@@ -43,7 +43,7 @@ CONN_NONE = 0xFFFFFFFF
 ERRORS = {
     -1: "PCDN_EINVAL", -2: "PCDN_ENOMEM", -3: "PCDN_ENODEV", -4: "PCDN_ECUDA", -5: "PCDN_ENOSPC",
     -6: "PCDN_EKEYLEN", -7: "PCDN_EPARSE", -8: "PCDN_EPRUNE", -9: "PCDN_EKIND", -10: "PCDN_ENOENT",
-    -11: "PCDN_EAGAIN", -12: "PCDN_E2BIG",
+    -11: "PCDN_EAGAIN", -12: "PCDN_E2BIG", -13: "PCDN_EHOOK",
 }
 
 
@@ -143,6 +143,16 @@ class EgressStats(C.Structure):
                 ("failed_conns", C.c_uint64), ("seconds", C.c_double)]
 
 
+class HookMessage(C.Structure):
+    _fields_ = [("kind", C.c_uint8), ("origin", C.c_uint8), ("n_topics", C.c_uint16), ("topics", C.POINTER(C.c_uint8)),
+                ("recipient", C.c_void_p), ("recipient_len", C.c_uint32), ("raw_len", C.c_uint32), ("raw", C.c_void_p),
+                ("sender", C.c_void_p), ("sender_len", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+MESSAGE_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(HookMessage))
+HOOK_PROCESS, HOOK_SKIP = 0, 1
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("batches", C.c_uint64), ("msgs", C.c_uint64), ("deliveries", C.c_uint64), ("bytes_out", C.c_uint64),
@@ -197,6 +207,7 @@ ABI = {
     "pcdn_handle_direct_message": (_ci, [_vp, _u8p, _u32, _u8p, _u32, _ci]),
     "pcdn_user_receive": (_ci, [_vp, _u8p, _u32, _u8p, _u32]),
     "pcdn_broker_receive": (_ci, [_vp, _cp, _u8p, _u32]),
+    "pcdn_set_message_hook": (_ci, [_vp, _ci, MESSAGE_HOOK, _vp]),
     "pcdn_receive_frames": (_ci, [_vp, C.POINTER(Frame), _u32, C.POINTER(C.c_int32)]),
     "pcdn_flush": (_ci, [_vp, C.POINTER(_u64)]),
     "pcdn_submit": (_ci, [_vp, C.POINTER(Msg), _u32, C.POINTER(_u64)]),
@@ -427,6 +438,19 @@ class Engine:
 
     def handle_direct_message(self, recipient: bytes, raw: bytes, to_user_only: bool = False) -> None:
         self._chk(self.L.pcdn_handle_direct_message(self.h, recipient, len(recipient), raw, len(raw), int(to_user_only)))
+
+    def set_message_hook(self, origin: int, fn) -> None:
+        """MessageHookDef (cdn-proto/src/def.rs:79-92).  fn(msg: HookMessage) -> HOOK_PROCESS | HOOK_SKIP | negative
+        (error: the receive call returns PCDN_EHOOK and the host disconnects the peer); None removes the hook."""
+        if not hasattr(self, "_hooks"):
+            self._hooks = {}
+        if fn is None:
+            self._chk(self.L.pcdn_set_message_hook(self.h, origin, C.cast(None, MESSAGE_HOOK), None))
+            self._hooks.pop(origin, None)
+            return
+        cb = MESSAGE_HOOK(lambda _u, m: int(fn(m.contents)))
+        self._hooks[origin] = cb   # keep the trampoline alive
+        self._chk(self.L.pcdn_set_message_hook(self.h, origin, cb, None))
 
     def user_receive(self, sender_key: bytes, raw: bytes) -> int:
         """One iteration of user_receive_loop; negative = the loop would have ended (disconnect)."""

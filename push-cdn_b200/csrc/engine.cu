@@ -940,22 +940,58 @@ static int append_frame_devparse(pcdn_engine* e, int kind, bool from_broker, con
   return rc;
 }
 
+// MessageHookDef::on_message_received on the parsed message (def.rs:79-92).  Returns 0 = process,
+// 1 = skip, negative = error (the receive loop ends).  The hook may shrink / rewrite the topic list
+// (a private copy) and re-point the recipient.
+static int run_hook(pcdn_engine* e, int origin, const ParsedFrame& pf, const uint8_t* sender, uint32_t sender_len,
+                    const uint8_t* raw, uint32_t raw_len, std::vector<uint8_t>& topic_copy, const uint8_t** f0, uint32_t* f0_len) {
+  *f0 = raw + pf.f0_off; *f0_len = pf.f0_len;
+  if (!e->hook[origin]) return 0;
+  pcdn_hook_message m{};
+  m.kind = (uint8_t)pf.kind; m.origin = (uint8_t)origin;
+  m.raw = raw; m.raw_len = raw_len; m.sender = sender; m.sender_len = sender_len;
+  const bool has_topics = pf.kind == PCDN_KIND_BROADCAST || pf.kind == PCDN_KIND_SUBSCRIBE || pf.kind == PCDN_KIND_UNSUBSCRIBE;
+  if (has_topics) {
+    if (pf.f0_len > 65535) return fail(PCDN_EPARSE, "topic list too long");
+    topic_copy.assign(raw + pf.f0_off, raw + pf.f0_off + pf.f0_len);
+    m.topics = topic_copy.data(); m.n_topics = (uint16_t)pf.f0_len;
+  } else if (pf.kind == PCDN_KIND_DIRECT) {
+    m.recipient = raw + pf.f0_off; m.recipient_len = pf.f0_len;
+  }
+  const int r = e->hook[origin](e->hook_user[origin], &m);
+  if (r < 0) return fail(PCDN_EHOOK, "hook failed: " + std::to_string(r));
+  if (r == PCDN_HOOK_SKIP) return 1;
+  if (has_topics) {
+    if (m.n_topics > topic_copy.size() || m.topics != topic_copy.data()) return fail(PCDN_EHOOK, "hook returned an invalid topic list");
+    *f0 = topic_copy.data(); *f0_len = m.n_topics;
+  } else if (pf.kind == PCDN_KIND_DIRECT) {
+    if (m.recipient_len && !m.recipient) return fail(PCDN_EHOOK, "hook returned a null recipient");
+    *f0 = m.recipient; *f0_len = m.recipient_len;
+  }
+  return 0;
+}
+
 static int user_receive_locked(pcdn_engine* e, const uint8_t* sender_key, uint32_t key_len, const uint8_t* raw, uint32_t raw_len) {
-  if (e->cfg.flags & PCDN_FLAG_DEVICE_PARSE) {
+  if ((e->cfg.flags & PCDN_FLAG_DEVICE_PARSE) && !e->hook[0]) {
     const int k = peek_kind_core(raw, raw_len);
     if (k == PCDN_KIND_DIRECT || k == PCDN_KIND_BROADCAST) return append_frame_devparse(e, k, false, raw, raw_len);
   }
   ParsedFrame pf;
   if (!parse_frame(raw, raw_len, &pf)) return fail(PCDN_EPARSE, "failed to deserialize message");
+  std::vector<uint8_t> hooked_topics;
+  const uint8_t* f0; uint32_t f0_len;
+  int hr = run_hook(e, 0, pf, sender_key, key_len, raw, raw_len, hooked_topics, &f0, &f0_len);
+  if (hr < 0) return hr;
+  if (hr == 1) return 0;  // Ok(HookResult::SkipMessage) => continue
   uint16_t topics[65536 / 8];
   switch (pf.kind) {
     case PCDN_KIND_DIRECT:
-      return append_msg(e, PCDN_KIND_DIRECT, 0, nullptr, 0, raw + pf.f0_off, pf.f0_len, raw, raw_len);
+      return append_msg(e, PCDN_KIND_DIRECT, 0, nullptr, 0, f0, f0_len, raw, raw_len);
     case PCDN_KIND_BROADCAST:
     case PCDN_KIND_SUBSCRIBE:
     case PCDN_KIND_UNSUBSCRIBE: {
-      if (pf.f0_len > sizeof(topics) / 2) return fail(PCDN_EPARSE, "topic list too long");
-      uint32_t n = prune_topics(raw + pf.f0_off, pf.f0_len, e->cfg.n_valid_topics, topics);
+      if (f0_len > sizeof(topics) / 2) return fail(PCDN_EPARSE, "topic list too long");
+      uint32_t n = prune_topics(f0, f0_len, e->cfg.n_valid_topics, topics);
       if (n == 0) return fail(PCDN_EPRUNE, "supplied no valid topics");
       if (pf.kind == PCDN_KIND_BROADCAST) return append_msg(e, PCDN_KIND_BROADCAST, 0, topics, n, nullptr, 0, raw, raw_len);
       int rc = before_state_change(e);
@@ -970,20 +1006,25 @@ static int user_receive_locked(pcdn_engine* e, const uint8_t* sender_key, uint32
   }
 }
 
-static int broker_receive_locked(pcdn_engine* e, const uint8_t* raw, uint32_t raw_len) {
-  if (e->cfg.flags & PCDN_FLAG_DEVICE_PARSE) {
+static int broker_receive_locked(pcdn_engine* e, const uint8_t* identifier, uint32_t identifier_len, const uint8_t* raw, uint32_t raw_len) {
+  if ((e->cfg.flags & PCDN_FLAG_DEVICE_PARSE) && !e->hook[1]) {
     const int k = peek_kind_core(raw, raw_len);
     if (k == PCDN_KIND_DIRECT || k == PCDN_KIND_BROADCAST) return append_frame_devparse(e, k, true, raw, raw_len);
   }
   ParsedFrame pf;
   if (!parse_frame(raw, raw_len, &pf)) return fail(PCDN_EPARSE, "failed to deserialize message");
+  std::vector<uint8_t> hooked_topics;
+  const uint8_t* f0; uint32_t f0_len;
+  int hr = run_hook(e, 1, pf, identifier, identifier_len, raw, raw_len, hooked_topics, &f0, &f0_len);
+  if (hr < 0) return hr;
+  if (hr == 1) return 0;  // Ok(HookResult::SkipMessage) => continue
   if (pf.kind == PCDN_KIND_DIRECT)
-    return append_msg(e, PCDN_KIND_DIRECT, PCDN_TO_USERS_ONLY, nullptr, 0, raw + pf.f0_off, pf.f0_len, raw, raw_len);
+    return append_msg(e, PCDN_KIND_DIRECT, PCDN_TO_USERS_ONLY, nullptr, 0, f0, f0_len, raw, raw_len);
   if (pf.kind == PCDN_KIND_BROADCAST) {
     uint16_t topics[65536 / 8];
-    if (pf.f0_len > sizeof(topics) / 2) return fail(PCDN_EPARSE, "topic list too long");
-    for (uint32_t i = 0; i < pf.f0_len; i++) topics[i] = raw[pf.f0_off + i];  // broker-origin: no prune (handler.rs:157)
-    return append_msg(e, PCDN_KIND_BROADCAST, PCDN_TO_USERS_ONLY, topics, pf.f0_len, nullptr, 0, raw, raw_len);
+    if (f0_len > sizeof(topics) / 2) return fail(PCDN_EPARSE, "topic list too long");
+    for (uint32_t i = 0; i < f0_len; i++) topics[i] = f0[i];  // broker-origin: no prune (handler.rs:157)
+    return append_msg(e, PCDN_KIND_BROADCAST, PCDN_TO_USERS_ONLY, topics, f0_len, nullptr, 0, raw, raw_len);
   }
   return 1;
 }
@@ -995,10 +1036,10 @@ int pcdn_user_receive(pcdn_engine* e, const uint8_t* sender_key, uint32_t key_le
   GUARD_END
 }
 
-int pcdn_broker_receive(pcdn_engine* e, const char* /*identifier*/, const uint8_t* raw, uint32_t raw_len) {
+int pcdn_broker_receive(pcdn_engine* e, const char* identifier, const uint8_t* raw, uint32_t raw_len) {
   GUARD_BEGIN
   LOCK;
-  return broker_receive_locked(e, raw, raw_len);
+  return broker_receive_locked(e, (const uint8_t*)identifier, identifier ? (uint32_t)std::strlen(identifier) : 0, raw, raw_len);
   GUARD_END
 }
 
@@ -1047,10 +1088,10 @@ int receive_frames_locked(pcdn_engine* e, const pcdn_frame* frames, uint32_t n, 
   const pcdn_config& c = e->cfg;
   const bool dev = (c.flags & PCDN_FLAG_DEVICE_PARSE) != 0;
   const uint32_t T = ingest_threads();
-  if (n < 2048 || T <= 1 || !e->has_device) {
+  if (n < 2048 || T <= 1 || !e->has_device || e->hook[0] || e->hook[1]) {  // a hook sees every parsed message, in order
     for (uint32_t i = 0; i < n; i++) {
       const pcdn_frame& f = frames[i];
-      int rc = f.origin ? broker_receive_locked(e, f.raw, f.raw_len) : user_receive_locked(e, f.sender, f.sender_len, f.raw, f.raw_len);
+      int rc = f.origin ? broker_receive_locked(e, f.sender, f.sender_len, f.raw, f.raw_len) : user_receive_locked(e, f.sender, f.sender_len, f.raw, f.raw_len);
       if (rc_out) rc_out[i] = rc;
       if (rc == PCDN_EAGAIN || rc == PCDN_ECUDA || rc == PCDN_ENODEV) return i ? (int)i : rc;
     }
@@ -1092,7 +1133,7 @@ int receive_frames_locked(pcdn_engine* e, const pcdn_frame* frames, uint32_t n, 
     if (p0.kind == -2) { if (rc_out) rc_out[i] = p0.rc; i++; continue; }
     if (p0.kind == -1) {
       const pcdn_frame& f = frames[i];
-      int rc = f.origin ? broker_receive_locked(e, f.raw, f.raw_len) : user_receive_locked(e, f.sender, f.sender_len, f.raw, f.raw_len);
+      int rc = f.origin ? broker_receive_locked(e, f.sender, f.sender_len, f.raw, f.raw_len) : user_receive_locked(e, f.sender, f.sender_len, f.raw, f.raw_len);
       if (rc_out) rc_out[i] = rc;
       if (rc == PCDN_EAGAIN || rc == PCDN_ECUDA || rc == PCDN_ENODEV) return i ? (int)i : rc;
       i++;
@@ -1179,6 +1220,16 @@ int receive_frames_locked(pcdn_engine* e, const pcdn_frame* frames, uint32_t n, 
 
 }  // namespace
 }  // extern "C++"
+
+int pcdn_set_message_hook(pcdn_engine* e, int origin, pcdn_message_hook cb, void* user) {
+  GUARD_BEGIN
+  LOCK;
+  if (origin != 0 && origin != 1) return fail(PCDN_EINVAL, "origin must be 0 (user) or 1 (broker)");
+  e->hook[origin] = cb;
+  e->hook_user[origin] = cb ? user : nullptr;
+  return 0;
+  GUARD_END
+}
 
 int pcdn_receive_frames(pcdn_engine* e, const pcdn_frame* frames, uint32_t n, int32_t* rc_out) {
   GUARD_BEGIN

@@ -183,6 +183,8 @@ struct pcdn_engine {
   size_t desc_cap = 0, topics_cap = 0, arena_cap = 0;
   std::vector<UpdSlot> h_slot; std::vector<uint32_t> h_kslot; std::vector<uint8_t> h_kbytes;  // journal parts common to all shards
   bool timing = false;
+  pcdn_message_hook hook[2] = {nullptr, nullptr};  // [origin]: MessageHookDef of user / broker connections
+  void* hook_user[2] = {nullptr, nullptr};
   uint64_t inflight_bytes = 0;  // Limiter analogue: accepted frame bytes whose batch is not released yet
   pcdn_stats stats{};
   // buffers behind pcdn_get_*_sync

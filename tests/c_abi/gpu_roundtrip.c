@@ -18,7 +18,10 @@
 
 static uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
 
-static int run(uint32_t flags) {
+/* shards: 0 = one GPU; 2 = the SAME calls on an engine whose connections are spread over two shards
+ * (pcdn_config.devices): GPUs 0 and 1 with the library's ncclBroadcast ingest when the box has two,
+ * else both shards on GPU 0 with PCDN_INGEST_HOST */
+static int run(uint32_t flags, int shards) {
   pcdn_config cfg;
   pcdn_config_default(&cfg);
   cfg.device = 0;
@@ -28,7 +31,18 @@ static int run(uint32_t flags) {
   cfg.identity = "pub/priv";
   cfg.flags = flags;
   pcdn_engine* e = NULL;
-  CHECK(pcdn_create(&cfg, &e) == 0);
+  const int32_t two_gpus[2] = {0, 1}, one_gpu[2] = {0, 0};
+  if (shards) {
+    cfg.n_devices = 2; cfg.devices = two_gpus; cfg.ingest = PCDN_INGEST_NCCL;
+    if (pcdn_create(&cfg, &e) != 0) {   /* a one-GPU box */
+      cfg.devices = one_gpu; cfg.ingest = PCDN_INGEST_HOST;
+      CHECK(pcdn_create(&cfg, &e) == 0);
+    }
+    uint32_t nl = 0, nw = 0;
+    CHECK(pcdn_num_shards(e, &nl, &nw) == 0 && nl == 2 && nw == 2);
+  } else {
+    CHECK(pcdn_create(&cfg, &e) == 0);
+  }
 
   const uint8_t k0[8] = {0}, k1[8] = {1}, k2[8] = {2};
   const uint16_t t0[1] = {0}, t1[1] = {1};
@@ -57,11 +71,17 @@ static int run(uint32_t flags) {
   const void* hbase = NULL;
   const int in_place = pcdn_host_rings(e, &hbase) == 0;
   CHECK(in_place == ((flags & PCDN_FLAG_HOST_RINGS) != 0));
+  if (shards) {   /* connections went to the least-loaded shard: ids 0, stride, 1 */
+    pcdn_shard_desc d0, d1;
+    CHECK(pcdn_shard_info(e, 0, &d0) == 0 && pcdn_shard_info(e, 1, &d1) == 0);
+    CHECK(d0.conn_base == 0 && d1.conn_base == d0.shard_stride && d0.n_conns == 2 && d1.n_conns == 1);
+    CHECK(c1 == d1.conn_base && c0 == 0 && c2 == 1);
+  }
   int seen = 0;
   for (uint32_t i = 0; i < r.n_spans; i++) {
     const pcdn_span* s = &r.spans[i];
     uint8_t* buf = (uint8_t*)malloc(s->len);
-    if (in_place) memcpy(buf, (const uint8_t*)hbase + (size_t)s->conn * cfg.ring_bytes_per_conn + s->ring_off, s->len);
+    if (in_place && !shards) memcpy(buf, (const uint8_t*)hbase + (size_t)s->conn * cfg.ring_bytes_per_conn + s->ring_off, s->len);
     else CHECK(pcdn_read(e, s->conn, s->ring_off, s->len, buf) == 0);
     if (s->conn == c0) {
       CHECK(s->n_records == 1 && be32(buf) == sizeof m1 && memcmp(buf + 4, m1, sizeof m1) == 0);
@@ -86,8 +106,10 @@ static int run(uint32_t flags) {
 }
 
 int main(void) {
-  if (run(0)) return 1;
-  if (run(PCDN_FLAG_HOST_RINGS)) return 1;
+  if (run(0, 0)) return 1;
+  if (run(PCDN_FLAG_HOST_RINGS, 0)) return 1;
+  if (run(0, 2)) return 1;
+  if (run(PCDN_FLAG_HOST_RINGS, 2)) return 1;
   printf("gpu_roundtrip ok\n");
   return 0;
 }

@@ -287,3 +287,37 @@ def test_add_broker_reconnect_refused_before_anything_changes(pcdn):
     assert ei.value.code == -5
     assert e.debug_interested([3]) == [c] and e.num_users() == (1, 1)
     assert e.add_broker("b/b") == c  # a reconnect reuses its own id (no batch in flight)
+
+
+def test_message_hook_seam_on_state_messages(pcdn):
+    """MessageHookDef (cdn-proto/src/def.rs:79-92, called at cdn-broker/src/tasks/user/handler.rs:110-118):
+    SkipMessage => the frame is ignored, Err => the receive loop ends, ProcessMessage => dispatch with
+    whatever the hook changed in the parsed message.  Subscribe / Unsubscribe need no GPU."""
+    import ctypes as C
+
+    e = pcdn.Engine(device=-1, max_conns=64, max_keys=256, identity="a/a", n_valid_topics=8)
+    c = e.add_user(b"alice", [])
+    seen = []
+
+    def hook(m):
+        seen.append((m.kind, m.origin, C.string_at(m.sender, m.sender_len), [m.topics[i] for i in range(m.n_topics)]))
+        if m.kind == pcdn.KIND_UNSUBSCRIBE:
+            return pcdn.HOOK_SKIP
+        if m.n_topics and m.topics[0] == 7:
+            return -1                      # Err => disconnect
+        if m.n_topics == 3:                # rewrite the parsed message: [1, 2, 3] -> [2, 5]
+            m.topics[0], m.topics[1] = 2, 5
+            m.n_topics = 2
+        return pcdn.HOOK_PROCESS
+
+    e.set_message_hook(0, hook)
+    assert e.user_receive(b"alice", orc.serialize(pcdn.KIND_SUBSCRIBE, bytes([1, 2, 3]))) == 0
+    assert e.debug_interested([2]) == [c] and e.debug_interested([5]) == [c] and e.debug_interested([1, 3]) == []
+    assert e.user_receive(b"alice", orc.serialize(pcdn.KIND_UNSUBSCRIBE, bytes([2]))) == 0    # skipped
+    assert e.debug_interested([2]) == [c]
+    assert e.user_receive(b"alice", orc.serialize(pcdn.KIND_SUBSCRIBE, bytes([7]))) == -13    # PCDN_EHOOK
+    assert e.debug_interested([7]) == []
+    assert seen[0] == (pcdn.KIND_SUBSCRIBE, 0, b"alice", [1, 2, 3]) and len(seen) == 3
+    e.set_message_hook(0, None)
+    assert e.user_receive(b"alice", orc.serialize(pcdn.KIND_UNSUBSCRIBE, bytes([2]))) == 0    # hook removed: processed
+    assert e.debug_interested([2]) == []
