@@ -137,7 +137,10 @@ int launch_shard_pipeline(pcdn_engine* e, Shard& sh, uint32_t si, uint32_t n_dir
   if (++s.w.stamp == 0) s.w.stamp = 1;  // validity stamp of this batch's direct buckets
   // latency path of the smallest geometry: match + plan + offsets in one cluster launch that also
   // zeroes / publishes the counters (kernels.cu: k_ctrl_small)
-  const bool fused = dp && sh.dev.N <= kSmallCtrlConns && s.in.n_msgs <= kSmallCtrlMsgs;
+  // (one cluster of 8 CTAs: worth it while the whole match is a few passes — a 128-message batch on a
+  //  65536-slot engine is 1024 (message, block) items and runs 10x faster through the regular kernels)
+  const bool fused = dp && sh.dev.N <= kSmallCtrlConns && s.in.n_msgs <= kSmallCtrlMsgs &&
+                     (uint64_t)s.in.n_bcast * sh.dev.nblk <= kSmallCtrlItems;
   // Spans go straight into mapped host memory when few are expected (16-byte PCIe writes: a table
   // of 16 K spans measured 20 us slower than the staged copy): the smallest geometry, or a batch
   // without broadcasts and with few messages (at most one span per message).  Otherwise they are staged in HBM and copied
@@ -149,7 +152,7 @@ int launch_shard_pipeline(pcdn_engine* e, Shard& sh, uint32_t si, uint32_t n_dir
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[0], st));
   if (!zero_in_kernel) launch_batch_begin(sh.dev, s.w, s.in, has_direct, st);
   if (devparse) launch_parse(sh.dev, s.w, s.in, st);
-  if (has_direct && !fused) launch_direct(sh.dev, s.w, s.in, st);  // fused: lookup + sort inside k_ctrl_small
+  if (has_direct && !fused) launch_direct(sh.dev, s.w, s.in, n_direct, st);  // fused: lookup + sort inside k_ctrl_small
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[1], st));
   if (fused) {
     launch_ctrl_small(sh.dev, s.w, s.in, has_direct, zero_in_kernel, s.d_stats_pub, st);
@@ -173,7 +176,7 @@ int launch_shard_pipeline(pcdn_engine* e, Shard& sh, uint32_t si, uint32_t n_dir
   // (mapped spans: k_offsets wrote spans / overflow into host memory; everything stays on one
   //  stream and the host waits for ev_done only)
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[4], ps));
-  launch_pack(sh.dev, s.w, s.in, e->cfg.pack_variant, sh.n_sms, ps);
+  launch_pack(sh.dev, s.w, s.in, n_direct, e->cfg.pack_variant, sh.n_sms, ps);
   if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[5], ps));
   CUDA_TRY(cudaGetLastError());
   if (!fused) CUDA_TRY(cudaMemcpyAsync(s.h_stats, s.w.stats, sizeof(BatchStats), cudaMemcpyDeviceToHost, ps));
@@ -425,7 +428,8 @@ int pcdn_detail::find_slot_index(pcdn_engine* e, uint64_t id) {
 namespace {
 
 void destroy_shard(pcdn_engine* e, Shard& sh) {
-  cudaSetDevice(sh.device);
+  if (!sh.stream && sh.dev_allocs.empty() && sh.pin_allocs.empty()) return;  // never initialised (create failed earlier)
+  if (cudaSetDevice(sh.device) != cudaSuccess) { cudaGetLastError(); return; }
   if (sh.stream) cudaStreamSynchronize(sh.stream);
   if (sh.pack_stream) cudaStreamSynchronize(sh.pack_stream);
   if (sh.copy_stream) cudaStreamSynchronize(sh.copy_stream);
@@ -460,6 +464,7 @@ void destroy_engine(pcdn_engine* e) {
       if (s.h_desc) cudaFreeHost(s.h_desc);
     }
     if (prev >= 0) cudaSetDevice(prev);
+    cudaGetLastError();  // a failed create must not leave its error behind for the next engine's launches
   }
   delete e;
 }
@@ -487,7 +492,7 @@ void destroy_engine(pcdn_engine* e) {
 int init_shard(pcdn_engine* e, Shard& sh, int ndev, void* user_stream) {
   const pcdn_config& c = e->cfg;
   const Geometry& g = e->geo;
-  if (sh.device < 0 || sh.device >= ndev) return fail(PCDN_ENODEV, "device ordinal out of range");
+  if (sh.device < 0 || sh.device >= ndev) return fail(PCDN_ENODEV, "device ordinal " + std::to_string(sh.device) + " out of range (" + std::to_string(ndev) + " CUDA devices)");
   CUDA_TRY(cudaSetDevice(sh.device));
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, sh.device));
@@ -542,7 +547,6 @@ int init_shard(pcdn_engine* e, Shard& sh, int ndev, void* user_stream) {
   const uint32_t M = c.max_batch_msgs, MB = c.max_batch_bcast;
   const size_t cap_fat = (size_t)c.max_batch_deliveries;
   const size_t cap_thin = std::min<size_t>(c.max_batch_deliveries, (size_t)M * (kFatMin - 1));
-  const size_t ntiles = sort_tiles(M);
   sh.slots.resize(c.batch_slots);
   for (ShardSlot& s : sh.slots) {
     DEV_ALLOC(s.d_arena, e->arena_cap);
@@ -569,9 +573,15 @@ int init_shard(pcdn_engine* e, Shard& sh, int ndev, void* user_stream) {
     DEV_ALLOC(w.ethin, cap_thin);
     w.cap_fat = (uint32_t)std::min<size_t>(cap_fat, 0xFFFFFFFFu);
     w.cap_thin = (uint32_t)std::min<size_t>(cap_thin, 0xFFFFFFFFu);
-    for (int k = 0; k < 2; k++) { DEV_ALLOC(w.skey[k], M); DEV_ALLOC(w.sval[k], M); }
-    DEV_ALLOC(w.hist, 256 * ntiles);
-    DEV_ALLOC(w.hist_tmp, 256 * ntiles / 1024 + 2);
+    DEV_ALLOC(w.dcount, (size_t)Ns + 2);
+    DEV_ALLOC(w.dloc, (size_t)Ns + 2);
+    DEV_ALLOC(w.dtile, (size_t)Ns / 1024 + 3);
+    DEV_ALLOC(w.dlist, M);
+    DEV_ALLOC(w.hot_list, (size_t)M / kHotMin + 2);
+    DEV_ALLOC(w.hot_bitmap, (size_t)kHotCtas * ((size_t)M / 32 + 1));
+    DEV_ALLOC(w.scan_done, 1);
+    CUDA_TRY(cudaMemsetAsync(w.scan_done, 0, 4, sh.stream));
+    DEV_ALLOC(w.edir, M);
     DEV_ALLOC(w.dstart, (size_t)Ns + 1);
     DEV_ALLOC(w.dend, (size_t)Ns + 1);
     DEV_ALLOC(w.dstamp, (size_t)Ns + 1);

@@ -13,6 +13,9 @@ namespace pcdn {
 std::atomic<unsigned long long> g_kernel_launches{0};
 #define PCDN_COUNT_LAUNCH (void)g_kernel_launches.fetch_add(1, std::memory_order_relaxed)
 
+unsigned long long kernel_launches() { return g_kernel_launches.load(std::memory_order_relaxed); }
+void count_kernel_launch() { PCDN_COUNT_LAUNCH; }
+
 // =============================================================================== small helpers
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
@@ -135,44 +138,6 @@ void launch_apply_updates(const DevState& s, const Upd32* u32, uint32_t n32, con
   if (n32) PCDN_COUNT_LAUNCH, k_apply_u32<<<(n32 + 255) / 256, 256, 0, st>>>(s, u32, n32);
 }
 
-// =============================================================================== generic u32 scan
-__global__ void k_scan_a(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n,
-                         uint32_t* __restrict__ tile_tot) {
-  __shared__ uint32_t sm[9];
-  uint32_t base = blockIdx.x * 1024 + threadIdx.x * 4;
-  uint32_t v[4], s = 0;
-#pragma unroll
-  for (int k = 0; k < 4; k++) { v[k] = (base + k < n) ? in[base + k] : 0; s += v[k]; }
-  uint32_t tot, ex = block256_excl_scan(s, &tot, sm);
-#pragma unroll
-  for (int k = 0; k < 4; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
-  if (threadIdx.x == 0) tile_tot[blockIdx.x] = tot;
-}
-// single block: in-place exclusive scan of `n` tile totals
-__global__ void k_scan_b(uint32_t* __restrict__ t, uint32_t n) {
-  __shared__ uint32_t sm[9];
-  uint32_t carry = 0;
-  for (uint32_t b = 0; b < n; b += 256) {
-    uint32_t i = b + threadIdx.x;
-    uint32_t v = i < n ? t[i] : 0;
-    uint32_t tot, ex = block256_excl_scan(v, &tot, sm);
-    if (i < n) t[i] = ex + carry;
-    carry += tot;
-  }
-}
-__global__ void k_scan_c(uint32_t* __restrict__ out, uint32_t n, const uint32_t* __restrict__ tile_tot) {
-  uint32_t i = blockIdx.x * 256 + threadIdx.x;
-  if (i < n) out[i] += tile_tot[i >> 10];
-}
-static void scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp, cudaStream_t st) {
-  uint32_t tiles = (n + 1023) / 1024;
-  PCDN_COUNT_LAUNCH, k_scan_a<<<tiles, 256, 0, st>>>(in, out, n, tmp);
-  if (tiles > 1) {
-    PCDN_COUNT_LAUNCH, k_scan_b<<<1, 256, 0, st>>>(tmp, tiles);
-    PCDN_COUNT_LAUNCH, k_scan_c<<<(n + 255) / 256, 256, 0, st>>>(out, n, tmp);
-  }
-}
-
 // =============================================================================== K0 ingress parse
 // Thread per message (device-parse mode): the same Cap'n Proto walk the host parser
 // runs (frame_parse_core.h, compiled for both), on the raw frame already resident in the arena.
@@ -232,6 +197,7 @@ __device__ __forceinline__ uint32_t key_word32(const uint8_t* kp, uint32_t j, ui
 // reduced inside the group), probe both 4-slot buckets with the 8 lanes, verify the full key
 // against the key arena, resolve the route (handler.rs:204-236).  Also seeds the (conn, msg) sort.
 // (gtid = global thread index: 8 consecutive threads serve message gtid / 8)
+template <bool COUNT>
 __device__ __forceinline__ void direct_lookup_body(const DevState& s, const BatchIn& b, const Work& w, uint32_t gtid) {
   const uint32_t lane = lane_id(), grp = lane >> 3, gl = lane & 7;
   const uint32_t m = (gtid >> 5) * 4 + grp;
@@ -290,161 +256,114 @@ __device__ __forceinline__ void direct_lookup_body(const DevState& s, const Batc
   if (!dropped) { target -= s.conn_base; if (target >= s.N) target = kConnNone; }  // (unsigned wrap: below the base → NONE)
   if (valid && gl == 0) {
     w.dconn[m] = target;
+    w.edir[m] = make_uint2(kConnNone, kOffInvalid);  // k_offsets fills in the ring offset of a delivered message
     if (is_direct) {
-      w.D[m] = target != kConnNone ? 1u : 0u;
+      w.D[m] = 0;  // direct messages never enter the broadcast classes' scatter lists
       if (dropped && s.count_drops) atomicAdd(&w.stats->n_direct_dropped, 1u);
+      if (COUNT && target != kConnNone) atomicAdd(&w.dcount[target], 1u);
     }
-    w.skey[0][m] = (is_direct && target != kConnNone) ? target : s.N;
-    w.sval[0][m] = m;
   }
 }
 __global__ void __launch_bounds__(256) k_direct_lookup(DevState s, BatchIn b, Work w) {
-  direct_lookup_body(s, b, w, blockIdx.x * blockDim.x + threadIdx.x);
+  direct_lookup_body<true>(s, b, w, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
-// ---- stable LSD radix sort of (target conn, msg index), 8-bit digits ---------------------------
-constexpr uint32_t kSortTile = 2048;
-size_t sort_tiles(uint32_t n) { return (n + kSortTile - 1) / kSortTile; }
-unsigned long long kernel_launches() { return g_kernel_launches.load(std::memory_order_relaxed); }
-void count_kernel_launch() { PCDN_COUNT_LAUNCH; }
+// ---- hits per connection → segments of dlist (no sort) ------------------------------------------
+// start of connection c's segment of dlist (c may be N: the end of the last segment)
+__device__ __forceinline__ uint32_t dseg_start(const Work& w, uint32_t c) { return w.dloc[c] + w.dtile[c >> 10]; }
 
-__global__ void __launch_bounds__(256) k_sort_hist(const uint32_t* __restrict__ key, uint32_t n, uint32_t shift,
-                                                   uint32_t* __restrict__ hist, uint32_t ntiles) {
-  __shared__ uint32_t h[256];
-  h[threadIdx.x] = 0;
-  __syncthreads();
-  const uint32_t base = blockIdx.x * kSortTile;
+// One launch: every CTA scans a tile of 1024 counts (exclusive, tile-local → dloc) and publishes the
+// tile total; the CTA that finishes last turns the totals into tile bases in place (dtile).  Readers
+// add the two (dseg_start).  Connections with more than kHotMin hits are listed for k_dsort_hot.
+__global__ void __launch_bounds__(256) k_dscan(Work w, uint32_t n, uint32_t ntiles) {
+  __shared__ uint32_t sm[9];
+  __shared__ uint32_t is_last;
+  const uint32_t base = blockIdx.x * 1024 + threadIdx.x * 4;
+  uint32_t v[4], sum = 0;
 #pragma unroll
-  for (int r = 0; r < 8; r++) {
-    uint32_t i = base + r * 256 + threadIdx.x;
-    if (i < n) atomicAdd(&h[(key[i] >> shift) & 255u], 1u);
+  for (int k = 0; k < 4; k++) {
+    v[k] = (base + k < n) ? w.dcount[base + k] : 0;
+    sum += v[k];
+    if (v[k] > kHotMin) w.hot_list[atomicAdd(&w.stats->n_hot, 1u)] = base + k;
+  }
+  uint32_t tot, ex = block256_excl_scan(sum, &tot, sm);
+#pragma unroll
+  for (int k = 0; k < 4; k++) { if (base + k < n) w.dloc[base + k] = ex; ex += v[k]; }
+  if (threadIdx.x == 0) {
+    w.dtile[blockIdx.x] = tot;
+    __threadfence();
+    is_last = atomicAdd(w.scan_done, 1u) == ntiles - 1 ? 1u : 0u;
   }
   __syncthreads();
-  hist[threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];  // digit-major for the global scan
+  if (!is_last) return;
+  __threadfence();
+  uint32_t carry = 0;
+  for (uint32_t bb = 0; bb < ntiles; bb += 256) {
+    const uint32_t i = bb + threadIdx.x;
+    const uint32_t t = i < ntiles ? __ldcg(w.dtile + i) : 0;
+    uint32_t tt, e2 = block256_excl_scan(t, &tt, sm);
+    if (i < ntiles) w.dtile[i] = carry + e2;
+    carry += tt;
+  }
+  if (threadIdx.x == 0) { w.dtile[ntiles] = carry; *w.scan_done = 0; }
 }
 
-__global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin,
-                                                      uint32_t* __restrict__ kout, uint32_t* __restrict__ vout,
-                                                      uint32_t n, uint32_t shift, const uint32_t* __restrict__ hist,
-                                                      uint32_t ntiles) {
-  // The tile's 2048 items are taken as 8 rounds x 8 warps x 32 lanes in index order.  Every
-  // (round, warp) cell counts its digits with one match_any; one pass of "thread = digit" turns the
-  // 64 cells of each digit into exclusive offsets; then all 8 rounds scatter.  Three barriers per
-  // tile and all 16 loads of a thread in flight at once (the per-round version had 32 barriers).
-  __shared__ uint32_t run[256];       // output position of the tile's first item of each digit
-  __shared__ uint16_t cnt[64][256];   // per (round, warp) cell: digit count, then exclusive prefix
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, lt = (1u << lane) - 1u;
-  {
-    uint4* z = reinterpret_cast<uint4*>(&cnt[0][0]);
-#pragma unroll
-    for (int k = 0; k < 8; k++) z[k * 256 + threadIdx.x] = make_uint4(0, 0, 0, 0);
-  }
-  run[threadIdx.x] = hist[threadIdx.x * ntiles + blockIdx.x];
-  const uint32_t base = blockIdx.x * kSortTile;
-  uint32_t key[8], val[8];
-#pragma unroll
-  for (int r = 0; r < 8; r++) {
-    const uint32_t i = base + r * 256 + threadIdx.x;
-    key[r] = i < n ? kin[i] : 0;
-    val[r] = i < n ? vin[i] : 0;
-  }
-  __syncthreads();
-  uint32_t rk[8];  // rank of the item among equal digits of its cell
-#pragma unroll
-  for (int r = 0; r < 8; r++) {
-    const bool valid = base + r * 256 + threadIdx.x < n;
-    const uint32_t d = (key[r] >> shift) & 255u;
-    const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xFFFFFFFFu);
-    rk[r] = __popc(peers & lt);
-    if (valid && rk[r] == 0) cnt[r * 8 + warp][d] = (uint16_t)__popc(peers);
-  }
-  __syncthreads();
-  {  // thread = digit: exclusive prefix over the 64 cells (cell order = index order → stable)
-    uint32_t off = 0;
-#pragma unroll 8
-    for (int k = 0; k < 64; k++) {
-      const uint32_t c = cnt[k][threadIdx.x];
-      cnt[k][threadIdx.x] = (uint16_t)off;
-      off += c;
+// every delivered direct message drops its index into its connection's segment (arbitrary slot)
+__global__ void __launch_bounds__(256) k_dfill(BatchIn b, Work w) {
+  const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= b.n_msgs) return;
+  const uint32_t t = w.dconn[m];
+  if (t == kConnNone) return;
+  const uint32_t slot = atomicSub(&w.dcount[t], 1u) - 1u;
+  w.dlist[dseg_start(w, t) + slot] = m;
+}
+
+// Hot connections (votes to a leader: thousands of directs to ONE key in a batch): the segment's
+// entries are distinct message indices below n_msgs, so "sorting" them is marking a bitmap of n_msgs
+// bits and reading the set bits back in order — O(n_msgs / 32) per hot connection whatever its
+// hit count.  One CTA per hot connection (grid-stride), its own bitmap row.
+__global__ void __launch_bounds__(256) k_dsort_hot(BatchIn b, Work w, uint32_t words) {
+  __shared__ uint32_t sm[9];
+  const uint32_t nh = w.stats->n_hot;
+  uint32_t* bm = w.hot_bitmap + (size_t)blockIdx.x * words;
+  for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
+    const uint32_t c = w.hot_list[h];
+    const uint32_t s0 = dseg_start(w, c), e0 = dseg_start(w, c + 1);
+    for (uint32_t i = threadIdx.x; i < words; i += 256) bm[i] = 0;
+    __syncthreads();
+    for (uint32_t i = s0 + threadIdx.x; i < e0; i += 256) {
+      const uint32_t m = w.dlist[i];
+      atomicOr(&bm[m >> 5], 1u << (m & 31));
     }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < 8; r++) {
-    if (base + r * 256 + threadIdx.x < n) {
-      const uint32_t d = (key[r] >> shift) & 255u;
-      const uint32_t pos = run[d] + cnt[r * 8 + warp][d] + rk[r];
-      kout[pos] = key[r];
-      vout[pos] = val[r];
-    }
-  }
-}
-
-// sorted keys → [dstart, dend) per connection.  The bounds of a connection are valid for this batch
-// iff dstamp[conn] == stamp (a per-slot batch counter): nothing has to be cleared between batches.
-__global__ void k_bucket_bounds(const uint32_t* __restrict__ skey, uint32_t n, uint32_t* __restrict__ dstart,
-                                uint32_t* __restrict__ dend, uint32_t* __restrict__ dstamp, uint32_t stamp) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t k = skey[i];
-  if (i == 0 || skey[i - 1] != k) { dstart[k] = i; dstamp[k] = stamp; }
-  if (i + 1 == n || skey[i + 1] != k) dend[k] = i + 1;
-}
-
-// Small batches (<= 2048 messages): one block sorts the 64-bit composites (conn << 32 | msg) with a
-// bitonic network in shared memory — one launch instead of the ~15 of the multi-pass radix sort,
-// which is what a latency-sensitive batch of a few votes needs.  The composite key makes the
-// result (conn, msg)-ordered by construction.
-constexpr uint32_t kSmallSort = 2048;
-__global__ void __launch_bounds__(256) k_sort_small(uint32_t* __restrict__ skey, uint32_t* __restrict__ sval, uint32_t n) {
-  __shared__ unsigned long long a[kSmallSort];
-  for (uint32_t i = threadIdx.x; i < kSmallSort; i += 256)
-    a[i] = i < n ? (((unsigned long long)skey[i] << 32) | sval[i]) : ~0ull;
-  __syncthreads();
-  for (uint32_t k = 2; k <= kSmallSort; k <<= 1) {
-    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-      for (uint32_t t = threadIdx.x; t < kSmallSort / 2; t += 256) {
-        const uint32_t i = 2 * t - (t & (j - 1));  // index of the lower element of pair t
-        const uint32_t l = i + j;
-        const bool up = (i & k) == 0;
-        const unsigned long long x = a[i], y = a[l];
-        if ((x > y) == up) { a[i] = y; a[l] = x; }
+    __syncthreads();
+    uint32_t carry = 0;
+    for (uint32_t w0 = 0; w0 < words; w0 += 256) {
+      uint32_t word = (w0 + threadIdx.x < words) ? bm[w0 + threadIdx.x] : 0;
+      uint32_t tot, ex = block256_excl_scan(__popc(word), &tot, sm);
+      uint32_t pos = s0 + carry + ex;
+      while (word) {
+        const uint32_t bit = __ffs(word) - 1;
+        word &= word - 1;
+        w.dlist[pos++] = (w0 + threadIdx.x) * 32 + bit;
       }
-      __syncthreads();
+      carry += tot;
     }
+    __syncthreads();
   }
-  for (uint32_t i = threadIdx.x; i < n; i += 256) { skey[i] = (uint32_t)(a[i] >> 32); sval[i] = (uint32_t)a[i]; }
 }
 
 void launch_batch_begin(const DevState&, const Work& w, const BatchIn&, bool, cudaStream_t st) {
   cudaMemsetAsync(w.stats, 0, sizeof(BatchStats), st);
 }
 
-void launch_direct(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st) {
+void launch_direct(const DevState& s, const Work& w, const BatchIn& b, uint32_t n_direct, cudaStream_t st) {
   const uint32_t n = b.n_msgs;
+  const uint32_t nseg = s.N + 1, ntiles = (nseg + 1023) / 1024;
+  cudaMemsetAsync(w.dcount, 0, (size_t)(s.N + 2) * 4, st);
   PCDN_COUNT_LAUNCH, k_direct_lookup<<<(n * 8 + 255) / 256, 256, 0, st>>>(s, b, w);
-  if (n <= kSmallSort) {
-    PCDN_COUNT_LAUNCH, k_sort_small<<<1, 256, 0, st>>>(w.skey[0], w.sval[0], n);
-    PCDN_COUNT_LAUNCH, k_bucket_bounds<<<(n + 255) / 256, 256, 0, st>>>(w.skey[0], n, w.dstart, w.dend, w.dstamp, w.stamp);
-    return;
-  }
-  uint32_t bits = 1;
-  while ((1ull << bits) <= (uint64_t)s.N) bits++;  // keys are in [0, N]
-  const uint32_t passes = (bits + 7) / 8;
-  const uint32_t ntiles = (uint32_t)sort_tiles(n);
-  int cur = 0;
-  for (uint32_t p = 0; p < passes; p++) {
-    PCDN_COUNT_LAUNCH, k_sort_hist<<<ntiles, 256, 0, st>>>(w.skey[cur], n, p * 8, w.hist, ntiles);
-    scan_u32(w.hist, w.hist, 256 * ntiles, w.hist_tmp, st);
-    PCDN_COUNT_LAUNCH, k_sort_scatter<<<ntiles, 256, 0, st>>>(w.skey[cur], w.sval[cur], w.skey[cur ^ 1], w.sval[cur ^ 1], n, p * 8,
-                                           w.hist, ntiles);
-    cur ^= 1;
-  }
-  if (cur != 0) {  // leave the result in buffer 0
-    cudaMemcpyAsync(w.skey[0], w.skey[1], (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
-    cudaMemcpyAsync(w.sval[0], w.sval[1], (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
-  }
-  PCDN_COUNT_LAUNCH, k_bucket_bounds<<<(n + 255) / 256, 256, 0, st>>>(w.skey[0], n, w.dstart, w.dend, w.dstamp, w.stamp);
+  PCDN_COUNT_LAUNCH, k_dscan<<<ntiles, 256, 0, st>>>(w, nseg, ntiles);
+  PCDN_COUNT_LAUNCH, k_dfill<<<(n + 255) / 256, 256, 0, st>>>(b, w);
+  if (n_direct > kHotMin) PCDN_COUNT_LAUNCH, k_dsort_hot<<<kHotCtas, 256, 0, st>>>(b, w, (n + 31) / 32);
 }
 
 // =============================================================================== K1a topic match
@@ -635,42 +554,11 @@ __global__ void __launch_bounds__(256) k_plan_c(BatchIn b, Work w, uint32_t nblk
     w.cm_rank[m] = w.stats->n_cm;
   }
 }
-// Direct-only batches (no broadcast in the batch): every message is "thin" with D in {0, 1}, so the
-// plan is ONE exclusive scan (the thin scatter-list bases) instead of four; classes, fat bases, tiles
-// and the connection-major list are never read (the batch counters were zeroed at batch begin).
-__global__ void __launch_bounds__(256) k_plan_direct_a(BatchIn b, Work w) {
-  __shared__ uint32_t sm[9];
-  const uint32_t m = blockIdx.x * 256 + threadIdx.x;
-  uint32_t tot, ex = block256_excl_scan(m < b.n_msgs ? w.D[m] : 0, &tot, sm);
-  if (m < b.n_msgs) w.eb_thin[m] = ex;
-  if (threadIdx.x == 0) w.scan_tmp[blockIdx.x] = tot;
-}
-__global__ void __launch_bounds__(256) k_plan_direct_b(Work w, uint32_t nblk) {
-  __shared__ uint32_t sm[9];
-  uint32_t carry = 0;
-  for (uint32_t bb = 0; bb < nblk; bb += 256) {
-    const uint32_t i = bb + threadIdx.x;
-    const uint32_t v = i < nblk ? w.scan_tmp[i] : 0;
-    uint32_t tot, ex = block256_excl_scan(v, &tot, sm);
-    if (i < nblk) w.scan_tmp[i] = ex + carry;
-    carry += tot;
-  }
-  if (threadIdx.x == 0) { w.stats->n_thin_entries = carry; if (carry > w.cap_thin) w.stats->status = 1; }  // PCDN_E2BIG
-}
-__global__ void __launch_bounds__(256) k_plan_direct_c(BatchIn b, Work w) {
-  const uint32_t m = blockIdx.x * 256 + threadIdx.x;
-  if (m < b.n_msgs) w.eb_thin[m] += w.scan_tmp[blockIdx.x];
-  else if (m == b.n_msgs) w.eb_thin[m] = w.stats->n_thin_entries;
-}
-
 void launch_plan(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st) {
+  // Direct messages need no plan: message m owns entry m of the direct list (edir).  A batch without
+  // broadcasts has nothing to classify (the batch counters were zeroed at batch begin).
+  if (b.n_bcast == 0) return;
   const uint32_t nblk = (b.n_msgs + 255) / 256;
-  if (b.n_bcast == 0 && nblk > 1) {
-    PCDN_COUNT_LAUNCH, k_plan_direct_a<<<nblk, 256, 0, st>>>(b, w);
-    PCDN_COUNT_LAUNCH, k_plan_direct_b<<<1, 256, 0, st>>>(w, nblk);
-    PCDN_COUNT_LAUNCH, k_plan_direct_c<<<(b.n_msgs + 1 + 255) / 256, 256, 0, st>>>(b, w);
-    return;
-  }
   PCDN_COUNT_LAUNCH, k_plan_a<<<nblk, 256, 0, st>>>(s, b, w, nblk);
   if (nblk == 1) return;  // finished inside k_plan_a
   PCDN_COUNT_LAUNCH, k_plan_b<<<4, 256, 0, st>>>(w, nblk);
@@ -706,7 +594,8 @@ __device__ __forceinline__ uint32_t alloc_record(ConnCursor& k, uint32_t u, uint
 // deterministic rank (block base + word prefix + lane rank).
 // (body shared by k_offsets — 256-thread CTAs, any N — and the fused small-engine control kernel —
 //  eight 1024-thread CTAs of one cluster, N = 8192; NT = threads per CTA, c = this thread's connection)
-template <bool HAS_DIRECT, int NT>
+// SPARSE_BOUNDS: the fused small-engine kernel's direct segments (rank-sorted, bounds valid iff stamped)
+template <bool HAS_DIRECT, int NT, bool SPARSE_BOUNDS>
 __device__ __forceinline__ void offsets_body(const DevState& s, const BatchIn& b, const Work& w, uint32_t max_conns,
                                              uint32_t c) {
   constexpr int NW = NT / 32;
@@ -720,14 +609,31 @@ __device__ __forceinline__ void offsets_body(const DevState& s, const BatchIn& b
   k.pt = s.ptail[c]; k.us = s.used[c]; k.bu = 0;
   k.s1_off = 0; k.s1_units = 0; k.s1_rec = 0; k.s2_units = 0; k.s2_rec = 0; k.ovf = 0; k.in2 = 0; k.bytes = 0;
   uint32_t dp = 0, de = 0;
-  if (HAS_DIRECT && w.dstamp[c] == w.stamp) { dp = w.dstart[c]; de = w.dend[c]; }
-  const uint32_t* dmsg = w.sval[0];
+  if (HAS_DIRECT) {
+    if (SPARSE_BOUNDS) {
+      if (w.dstamp[c] == w.stamp) { dp = w.dstart[c]; de = w.dend[c]; }
+    } else {
+      dp = dseg_start(w, c); de = dseg_start(w, c + 1);
+      // The fill pass left this connection's few hits in arbitrary order: put them into batch order
+      // (R9) here, in place — the segment belongs to this thread alone.  Segments of more than
+      // kHotMin entries were ordered by k_dsort_hot.
+      if (de - dp >= 2 && de - dp <= kHotMin) {
+        for (uint32_t i = dp + 1; i < de; i++) {
+          const uint32_t x = w.dlist[i];
+          uint32_t j = i;
+          while (j > dp && w.dlist[j - 1] > x) { w.dlist[j] = w.dlist[j - 1]; j--; }
+          w.dlist[j] = x;
+        }
+      }
+    }
+  }
+  const uint32_t* dmsg = w.dlist;
 
-  // direct hit (always the thin list, rank 0)
+  // direct hit: message m owns entry m of the direct list
   auto emit_direct = [&](uint32_t m) {
     const uint32_t len = b.raw_len[m];
     const uint32_t off = alloc_record(k, frame_units(len), R, len);
-    w.ethin[w.eb_thin[m]] = make_uint4(c, off, b.slot_off16[m], len);
+    w.edir[m] = make_uint2(c, off);
   };
 
   // Broadcasts are taken 32 at a time: the block stages their per-message metadata in shared
@@ -804,7 +710,7 @@ __device__ __forceinline__ void offsets_body(const DevState& s, const BatchIn& b
 }
 template <bool HAS_DIRECT>
 __global__ void __launch_bounds__(256) k_offsets(DevState s, BatchIn b, Work w, uint32_t max_conns) {
-  offsets_body<HAS_DIRECT, 256>(s, b, w, max_conns, blockIdx.x * 256 + threadIdx.x);  // N is a multiple of 8192
+  offsets_body<HAS_DIRECT, 256, false>(s, b, w, max_conns, blockIdx.x * 256 + threadIdx.x);  // N is a multiple of 8192
 }
 void launch_offsets(const DevState& s, const Work& w, const BatchIn& b, bool has_direct, cudaStream_t st) {
   if (has_direct) PCDN_COUNT_LAUNCH, k_offsets<true><<<s.N / 256, 256, 0, st>>>(s, b, w, s.N);
@@ -831,23 +737,22 @@ k_ctrl_small(DevState s, BatchIn b, Work w, int zero_stats, BatchStats* publish)
   const uint32_t tid = threadIdx.x, rank = blockIdx.x;  // grid = one cluster
   if (zero_stats && rank == 0 && tid < sizeof(BatchStats) / 4) reinterpret_cast<uint32_t*>(w.stats)[tid] = 0;
 
-  // ---- direct messages (= k_direct_lookup + k_sort_small + k_bucket_bounds) on CTA 0; at most
-  //      kSmallCtrlMsgs of them, so the stable (connection, message) sort is a rank count
+  // ---- direct messages (= k_direct_lookup + the grouping by connection) on CTA 0; at most
+  //      kSmallCtrlMsgs of them, so the (connection, message) order is a rank count
   if (HAS_DIRECT && rank == 0) {
     __shared__ uint32_t skey_s[kSmallCtrlMsgs], sorted_s[kSmallCtrlMsgs];
     __syncthreads();  // counters are zero before the lookup counts dropped messages
-    for (uint32_t g0 = 0; g0 < b.n_msgs * 8; g0 += 1024) direct_lookup_body(s, b, w, g0 + tid);  // 128 messages per pass
+    for (uint32_t g0 = 0; g0 < b.n_msgs * 8; g0 += 1024) direct_lookup_body<false>(s, b, w, g0 + tid);  // 128 messages per pass
     __syncthreads();
     const uint32_t n = b.n_msgs;
-    if (tid < n) skey_s[tid] = w.skey[0][tid];
+    if (tid < n) { const uint32_t t = w.dconn[tid]; skey_s[tid] = t == kConnNone ? s.N : t; }
     __syncthreads();
     if (tid < n) {
       const uint32_t key = skey_s[tid];
       uint32_t r = 0;
       for (uint32_t o = 0; o < n; o++) r += (skey_s[o] < key || (skey_s[o] == key && o < tid)) ? 1u : 0u;
       sorted_s[r] = key;
-      w.skey[0][r] = key;
-      w.sval[0][r] = tid;
+      w.dlist[r] = tid;
     }
     __syncthreads();
     if (tid < n) {
@@ -922,7 +827,7 @@ k_ctrl_small(DevState s, BatchIn b, Work w, int zero_stats, BatchStats* publish)
   cluster_sync_all();
 
   // ---- offsets: thread = connection (one pass per 8192 connections)
-  for (uint32_t c0 = 0; c0 < s.N; c0 += 8192) offsets_body<HAS_DIRECT, 1024>(s, b, w, s.N, c0 + rank * 1024 + tid);
+  for (uint32_t c0 = 0; c0 < s.N; c0 += 8192) offsets_body<HAS_DIRECT, 1024, true>(s, b, w, s.N, c0 + rank * 1024 + tid);
 
   // ---- final counters straight into the host's (mapped, pinned) result block
   if (publish) {
@@ -1193,43 +1098,68 @@ __device__ __forceinline__ void pack_cm_phase(const DevState& s, const BatchIn& 
   if (VARIANT == 1) bulk_wait_read0();  // the next phase reuses buf
 }
 
-// =============================================================================== K2b pack (thin)
-// Warp per scatter-list entry (messages with < kFatMin recipients, all direct messages): 16-byte
-// read-only loads from the frame slot, length prefix patched into the first vector, 16-byte stores.
+// =============================================================================== K2b pack (thin / direct)
+// warp copies one framed record: 16-byte read-only loads from the frame slot, length prefix patched
+// into the first vector, 16-byte streaming stores (four vectors per lane in flight)
+__device__ __forceinline__ void copy_record(const uint4* __restrict__ src, uint4* __restrict__ dst, uint32_t raw_len, uint32_t lane) {
+  const uint32_t nvec = (4u + raw_len + 15u) >> 4;
+  const uint32_t hdr = bswap32(raw_len);
+  for (uint32_t v = lane; v < nvec; v += 128) {
+    uint4 x0, x1, x2, x3;
+    const bool p1 = v + 32 < nvec, p2 = v + 64 < nvec, p3 = v + 96 < nvec;
+    x0 = ld_nc16(src + v);
+    if (p1) x1 = ld_nc16(src + v + 32);
+    if (p2) x2 = ld_nc16(src + v + 64);
+    if (p3) x3 = ld_nc16(src + v + 96);
+    if (v == 0) x0.x = hdr;
+    st_stream16(dst + v, x0);
+    if (p1) st_stream16(dst + v + 32, x1);
+    if (p2) st_stream16(dst + v + 64, x2);
+    if (p3) st_stream16(dst + v + 96, x3);
+  }
+}
+// Warp per scatter-list entry (broadcasts with < kFatMin recipients).
 __device__ __forceinline__ void pack_thin_phase(const DevState& s, const BatchIn& b, const Work& w) {
   const uint32_t n = w.stats->n_thin_entries;
   const uint32_t lane = lane_id();
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  // (a variant with four entries in flight per warp measured no faster: the phase is bound by the
-  // scattered sub-KB writes, not by load latency — profiles/r1_cfg_C4*.json)
   for (uint32_t e = gw; e < n; e += nw) {
     const uint4 ent = w.ethin[e];
     if (ent.y == kOffInvalid) continue;
-    const uint4* src = reinterpret_cast<const uint4*>(b.arena + (size_t)ent.z * 16);
-    uint4* dst = reinterpret_cast<uint4*>(s.rings + (size_t)ent.x * s.ring_bytes + (size_t)ent.y * kUnit);
-    const uint32_t nvec = (4u + ent.w + 15u) >> 4;
-    const uint32_t hdr = bswap32(ent.w);
-    for (uint32_t v = lane; v < nvec; v += 128) {
-      uint4 x0, x1, x2, x3;
-      const bool p1 = v + 32 < nvec, p2 = v + 64 < nvec, p3 = v + 96 < nvec;
-      x0 = ld_nc16(src + v);
-      if (p1) x1 = ld_nc16(src + v + 32);
-      if (p2) x2 = ld_nc16(src + v + 64);
-      if (p3) x3 = ld_nc16(src + v + 96);
-      if (v == 0) x0.x = hdr;
-      st_stream16(dst + v, x0);
-      if (p1) st_stream16(dst + v + 32, x1);
-      if (p2) st_stream16(dst + v + 64, x2);
-      if (p3) st_stream16(dst + v + 96, x3);
-    }
+    copy_record(reinterpret_cast<const uint4*>(b.arena + (size_t)ent.z * 16),
+                reinterpret_cast<uint4*>(s.rings + (size_t)ent.x * s.ring_bytes + (size_t)ent.y * kUnit), ent.w, lane);
+  }
+}
+// Direct messages: warp per MESSAGE — entry m of the direct list, the frame slot and the length are
+// all indexed by the message, so the warps of a CTA stream the arena in order; only the record
+// stores are scattered (one ~700 B record per ring).
+// (a variant with four entries in flight per warp measured no faster: the phase is bound by the
+// scattered sub-KB writes, not by load latency — profiles/r1_cfg_C4*.json)
+__device__ __forceinline__ void pack_direct_phase(const DevState& s, const BatchIn& b, const Work& w) {
+  const uint32_t n = b.n_msgs;
+  const uint32_t lane = lane_id();
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  // The three per-message words (list entry, slot, length) of the NEXT message are fetched while the
+  // current record is being copied: the chain entry → frame → stores loses its first DRAM round trip.
+  uint2 ent = make_uint2(0, kOffInvalid);
+  uint32_t so = 0, len = 0;
+  if (gw < n) { ent = w.edir[gw]; so = b.slot_off16[gw]; len = b.raw_len[gw]; }
+  for (uint32_t m = gw; m < n; m += nw) {
+    const uint2 cur = ent;
+    const uint32_t cso = so, clen = len;
+    const uint32_t nx = m + nw;
+    if (nx < n) { ent = w.edir[nx]; so = b.slot_off16[nx]; len = b.raw_len[nx]; }
+    if (cur.y == kOffInvalid) continue;
+    copy_record(reinterpret_cast<const uint4*>(b.arena + (size_t)cso * 16),
+                reinterpret_cast<uint4*>(s.rings + (size_t)cur.x * s.ring_bytes + (size_t)cur.y * kUnit), clen, lane);
   }
 }
 
-// One launch runs the three pack phases back to back in persistent CTAs (each phase pulls its own
+// One launch runs the pack phases back to back in persistent CTAs (each phase pulls its own
 // work from its own cursor, so CTAs drift from phase to phase without a grid barrier; the phases
 // write disjoint records).
 template <int VARIANT>
-__global__ void __launch_bounds__(256) k_pack(DevState s, BatchIn b, Work w, int do_thin) {
+__global__ void __launch_bounds__(256) k_pack(DevState s, BatchIn b, Work w, int do_direct) {
   __shared__ __align__(128) uint8_t buf[kCmGroup * kCmMaxBytes];  // 32 KB; the fat phase uses the first 16 KB
   __shared__ __align__(8) uint64_t bars[2];
   if (w.stats->status) return;
@@ -1242,28 +1172,32 @@ __global__ void __launch_bounds__(256) k_pack(DevState s, BatchIn b, Work w, int
   pack_cm_phase<VARIANT>(s, b, w, buf, &bars[0]);
   __syncthreads();
   pack_fat_phase<VARIANT>(s, b, w, buf, &bars[1]);
-  if (do_thin) pack_thin_phase(s, b, w);
-}
-// Batches dominated by direct messages run the thin phase as its own launch at full occupancy
-// (no shared memory, 8 CTAs per SM): a warp per record is a chain of two dependent DRAM reads
-// (scatter entry, frame) before its stores, so the phase scales with warps in flight — 24 → 48
-// warps per SM measured +25 % on the 1 M x 512 B direct workload (profiles/r1_sweep_secondary.txt).
-__global__ void __launch_bounds__(256, 8) k_pack_thin(DevState s, BatchIn b, Work w) {
-  if (w.stats->status) return;
   pack_thin_phase(s, b, w);
+  if (do_direct) pack_direct_phase(s, b, w);
+}
+// Batches dominated by direct messages run the direct phase as its own launch at full occupancy
+// (no shared memory, 8 CTAs per SM): a warp per record is a chain of two dependent DRAM reads
+// (list entry, frame) before its stores, so the phase scales with warps in flight — 24 → 48
+// warps per SM measured +25 % on the 1 M x 512 B direct workload (profiles/r1_sweep_secondary.txt).
+__global__ void __launch_bounds__(256, 8) k_pack_direct(DevState s, BatchIn b, Work w) {
+  if (w.stats->status) return;
+  pack_direct_phase(s, b, w);
 }
 
-void launch_pack(const DevState& s, const Work& w, const BatchIn& b, uint32_t variant, int n_sms, cudaStream_t st) {
-  const bool thin_separate = b.n_msgs - b.n_bcast >= kThinSeparateMin;
+void launch_pack(const DevState& s, const Work& w, const BatchIn& b, uint32_t n_direct, uint32_t variant, int n_sms, cudaStream_t st) {
+  const bool direct_separate = n_direct >= kThinSeparateMin;
   // Default (variant 0): TMA bulk stores, 3 CTAs per SM — the best of the sweep in profiles/.
   // A/B switches for profiling: bit 2 = st.global.cs.v4 stores instead of bulk stores; bit 1 = no
   // connection-major class (DevState::cm_enable, read by k_plan_a); bits 4-7 = log2 multiplier of
   // the 128 KB message-major tile (DevState::fat_tile_bytes); bits 8+ = CTAs per SM.
   const uint32_t ctas_per_sm = (variant >> 8) ? (variant >> 8) : 3;
   const uint32_t grid = (uint32_t)n_sms * ctas_per_sm;
-  if (variant & 4) PCDN_COUNT_LAUNCH, k_pack<0><<<grid, 256, 0, st>>>(s, b, w, thin_separate ? 0 : 1);
-  else PCDN_COUNT_LAUNCH, k_pack<1><<<grid, 256, 0, st>>>(s, b, w, thin_separate ? 0 : 1);
-  if (thin_separate) PCDN_COUNT_LAUNCH, k_pack_thin<<<(uint32_t)n_sms * 8, 256, 0, st>>>(s, b, w);
+  const int do_direct = (n_direct && !direct_separate) ? 1 : 0;
+  if (b.n_bcast || do_direct) {  // (a batch of nothing but many direct messages has no work for this kernel)
+    if (variant & 4) PCDN_COUNT_LAUNCH, k_pack<0><<<grid, 256, 0, st>>>(s, b, w, do_direct);
+    else PCDN_COUNT_LAUNCH, k_pack<1><<<grid, 256, 0, st>>>(s, b, w, do_direct);
+  }
+  if (direct_separate) PCDN_COUNT_LAUNCH, k_pack_direct<<<(uint32_t)n_sms * 8, 256, 0, st>>>(s, b, w);
 }
 
 // =============================================================================== release

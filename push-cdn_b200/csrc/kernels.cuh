@@ -2,8 +2,11 @@
 //
 // Per batch the engine runs (all on one stream, no host round trip in between):
 //   K0  k_parse         (device-parse mode) thread per frame: Cap'n Proto walk, Topic::prune, recipient
-//   K3  k_direct_lookup 8 lanes per direct message: cuckoo probe pubkey → route → target connection
-//       sort            stable (conn, msg) order: one-block bitonic (<= 2048 msgs) or 8-bit LSD radix
+//   K3  k_direct_lookup 8 lanes per direct message: cuckoo probe pubkey → route → target connection,
+//                       hit count per connection
+//       k_dscan/k_dfill counts → segment starts (one scan launch), message indices dropped into their
+//                       connection's segment (no sort: the connection's thread orders its few entries
+//                       in k_offsets; k_dsort_hot orders connections with > 32 hits by bitmap)
 //   K1a k_match         OR of subscription-bitmap rows per broadcast → match words + popcount ranks
 //   K1p k_plan_*        D_m per message, class (thin / message-major / connection-major), scatter-list
 //                       bases and pack tiles by prefix sums (one launch when <= 256 messages)
@@ -39,7 +42,10 @@ constexpr uint32_t kCmGroup = 8;             // messages staged together in shar
 constexpr uint32_t kCmMaxBytes = 4096;       // largest padded record that takes the cm path
 constexpr uint32_t kSmallCtrlConns = 65536;   // largest geometry served by the fused control kernel (<= 8 match blocks per message)
 constexpr uint32_t kSmallCtrlMsgs = 256;      // largest batch it takes
-constexpr uint32_t kThinSeparateMin = 2048;  // direct messages in a batch from which the thin pack gets its own launch
+constexpr uint32_t kSmallCtrlItems = 256;     // ... and at most this many (broadcast, 8192-connection block) match items
+constexpr uint32_t kThinSeparateMin = 2048;  // direct messages in a batch from which the direct pack gets its own launch
+constexpr uint32_t kHotMin = 32;             // more direct hits than this on one connection: ordered by k_dsort_hot
+constexpr uint32_t kHotCtas = 32;            // CTAs (and bitmap scratch rows) of k_dsort_hot
 constexpr uint32_t kCmTileWords = 16;        // bitmap words (512 connections) per cm tile
 constexpr uint32_t kCmDenseShift = 4;        // cm needs D >= N/16 recipients
 enum : uint8_t { CLS_THIN = 0, CLS_FAT = 1, CLS_CM = 2 };
@@ -106,6 +112,8 @@ struct BatchStats {
   uint32_t tile_cursor;
   uint32_t n_cm;            // messages on the connection-major path
   uint32_t cm_cursor;
+  uint32_t n_hot;           // connections with more than kHotMin direct hits in this batch
+  uint32_t reserved;
 };
 
 struct Span { uint32_t conn, ring_off, len, n_records; };
@@ -132,14 +140,24 @@ struct Work {
                          //            implied by the rank, so 4 bytes per delivery instead of 8)
   uint4* ethin;          // [cap_thin] {conn, ring offset in units, slot_off16, raw_len}
   uint32_t cap_fat, cap_thin;
-  // direct buckets
-  uint32_t* skey[2];     // [max_msgs] sort keys (target conn, N = none)
-  uint32_t* sval[2];     // [max_msgs] msg index
-  uint32_t* hist;        // [256 * ntiles]
-  uint32_t* hist_tmp;    // scan scratch
+  // Direct hits grouped by target connection WITHOUT a sort: the lookup counts hits per connection
+  // (dcount), one scan turns the counts into segment starts (dloc + dtile), a fill pass drops every
+  // message index into its connection's segment of dlist (atomic slot: arbitrary order), and the
+  // connection's own thread in k_offsets puts its handful of entries into batch order (R9).
+  // Connections with more than kHotMin hits are ordered by k_dsort_hot before that.
+  uint32_t* dcount;      // [N+2] hits per connection (zeroed per batch)
+  uint32_t* dloc;        // [N+2] exclusive prefix of dcount inside its 1024-entry tile
+  uint32_t* dtile;       // [N/1024+3] exclusive prefix of the tile totals (raw totals until the last CTA of k_dscan has run)
+  uint32_t* dlist;       // [max_msgs] message indices grouped by connection
+  uint32_t* hot_list;    // [max_msgs/kHotMin+1] connections with more than kHotMin hits
+  uint32_t* hot_bitmap;  // [kHotCtas][max_msgs/32+1] scratch of k_dsort_hot
+  uint32_t* scan_done;   // finished tiles of k_dscan (zero between batches)
+  uint2* edir;           // [max_msgs] direct message m → {connection, ring offset in units}; offset invalid = not delivered by this shard
+  // fused small-engine path: the (connection, message) order comes from a rank sort inside the kernel
+  // and the segment bounds are sparse (valid iff dstamp == stamp: nothing to clear between batches)
   uint32_t* dstart;      // [N+1]
   uint32_t* dend;        // [N+1]
-  uint32_t* dstamp;      // [N+1] dstart/dend of a connection are valid iff dstamp == stamp
+  uint32_t* dstamp;      // [N+1]
   uint32_t stamp;        // per-slot batch counter (never 0)
   // outputs
   uint32_t* batch_units; // [N] units consumed by this batch per connection (for release)
@@ -159,16 +177,15 @@ void launch_apply_updates(const DevState& s, const Upd32* u32, uint32_t n32, con
                           uint32_t nkeys, cudaStream_t st);
 void launch_batch_begin(const DevState& s, const Work& w, const BatchIn& b, bool has_direct, cudaStream_t st);
 void launch_parse(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st);
-void launch_direct(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st);
+void launch_direct(const DevState& s, const Work& w, const BatchIn& b, uint32_t n_direct, cudaStream_t st);
 void launch_match(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st);
 void launch_plan(const DevState& s, const Work& w, const BatchIn& b, cudaStream_t st);
 void launch_offsets(const DevState& s, const Work& w, const BatchIn& b, bool has_direct, cudaStream_t st);
 // fused match + plan + offsets for N <= kSmallCtrlConns and n_msgs <= kSmallCtrlMsgs (one cluster launch)
 void launch_ctrl_small(const DevState& s, const Work& w, const BatchIn& b, bool has_direct, bool zero_stats,
                        BatchStats* publish, cudaStream_t st);
-void launch_pack(const DevState& s, const Work& w, const BatchIn& b, uint32_t variant, int n_sms, cudaStream_t st);
+void launch_pack(const DevState& s, const Work& w, const BatchIn& b, uint32_t n_direct, uint32_t variant, int n_sms, cudaStream_t st);
 void launch_release(const DevState& s, const uint32_t* batch_units, const BatchStats* stats, cudaStream_t st);
-size_t sort_tiles(uint32_t n);
 unsigned long long kernel_launches();   // launches issued by this library in this process so far
 void count_kernel_launch();
 
