@@ -111,15 +111,28 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def run_cpu_reference(n_conns, payload, msgs, steps, warmup, threads=0, timeout=900):
+def run_cpu_reference(n_conns, payload, msgs, steps, warmup, threads=0, timeout=900, model=1):
     """oracle/cpu_broker_timed: the C++ restatement of the reference's CPU path (the reference is
     Rust and cannot be built here).  This is the ONLY place bench.py executes anything in oracle/."""
     from oracle import oracle as orc
 
     orc.build()
-    out = subprocess.run([orc.TIMED_PATH, str(n_conns), str(payload), str(msgs), str(steps), str(warmup), str(threads)],
+    out = subprocess.run([orc.TIMED_PATH, str(n_conns), str(payload), str(msgs), str(steps), str(warmup), str(threads), str(model)],
                          capture_output=True, text=True, timeout=timeout, check=True)
     return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def pick_cpu_model(n_conns, payload, msgs, cores):
+    """The port has two threading models (writer tasks after / concurrent with the receive loops); one
+    step of each decides which is faster ON THIS BOX — the baseline is always the faster one."""
+    cal = {}
+    for model in (0, 1):
+        try:
+            cal[model] = run_cpu_reference(n_conns, payload, msgs, 1, 0, cores, model=model)["gbps"]
+        except Exception:
+            cal[model] = 0.0
+    best = max(cal, key=lambda k: cal[k])
+    return best, {"two_phases_GBps": cal[0], "overlapped_GBps": cal[1]}
 
 
 def reference_arm(args, rank, world):
@@ -131,16 +144,15 @@ def reference_arm(args, rank, world):
     # literal shape (cdn-broker/benches/broadcast.rs:58-62)
     n_conns, payload = args.conns, args.payload
     cores = min(cores, max(1, n_conns // 1024))  # the port starts its worker threads per step: tiny shapes run serially
-    cal = run_cpu_reference(n_conns, payload, 1, 1, 0, cores)
-    per_msg = max(cal["seconds"], 1e-6)
-    budget = 240.0
     msgs = args.msgs            # the SAME batch as the GPU arm (same_config): a long run is cut in steps, never in the batch
+    model, calib = pick_cpu_model(n_conns, payload, msgs, cores)
+    per_step = n_conns * msgs * (4 + 8 * (7 + (payload + 7) // 8)) / 1e9 / max(max(calib.values()), 1e-3)
+    budget = 200.0
     steps, warmup = args.steps, args.warmup
-    est = lambda: per_msg * msgs * (steps + warmup) / max(1, min(msgs, cores // 2))
-    while steps > 1 and est() > budget:
+    while steps > 1 and per_step * (steps + warmup) > budget:
         steps = max(1, steps // 2)
         warmup = min(warmup, 1)
-    r = run_cpu_reference(n_conns, payload, msgs, steps, warmup, cores)
+    r = run_cpu_reference(n_conns, payload, msgs, steps, warmup, cores, model=model)
     gbps = r["gbps"]
     line = {
         "impl": "reference", "metric": METRIC, "value": gbps, "unit": "GB/s", "n_gpus": args.gpus, "steps": steps,
@@ -150,10 +162,11 @@ def reference_arm(args, rank, world):
         "config": {"workload": "C2: 2^20 subscribers, 1 topic, 1 KiB broadcast" if (n_conns, payload) == (N_CONNS, PAYLOAD) else
                    "%d subscribers, 1 topic, %d B broadcast" % (n_conns, payload), "n_conns": n_conns, "payload": payload,
                    "msgs_per_step": msgs, "frame_bytes": r["frame_bytes"],
-                   "note": "C++ restatement of cdn-broker's CPU path (reference is Rust, not buildable here): persistent threads, "
-                           "writer tasks overlap the receive loops; same batch as the GPU arm, %d of the %d requested steps timed" % (steps, args.steps)},
+                   "note": "C++ restatement of cdn-broker's CPU path (reference is Rust, not buildable here): %s (the faster of the "
+                           "port's two threading models on this box); same batch as the GPU arm, %d of the %d requested steps timed" % (r.get("model"), steps, args.steps)},
         "cpu_baseline": {"value": gbps, "unit": "GB/s", "cores": r["threads"], "kind": "port",
                          "sample": "%d msgs x %d subscribers per step, %d steps" % (msgs, n_conns, steps),
+                         "model": r.get("model"), "model_calibration": calib, "model_calibration": calib,
                          "median_step_value": r.get("gbps_median_step"), "router_threads": r.get("router_threads"),
                          "writer_threads": r.get("writer_threads"), "stage12_s": r["stage12_s"], "stage3_s": r["stage3_s"]},
         "e2e": {"value": gbps, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -175,6 +188,8 @@ def main():
     ap.add_argument("--ring-records", type=int, default=RING_RECORDS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--pool", action="store_true", help="one shared output pool (PCDN_FLAG_OUTPUT_POOL, same bytes as the rings) instead of a ring per connection")
+    ap.add_argument("--plain-spans", action="store_true", help="one 16-byte span per connection instead of the run-length span table (PCDN_FLAG_SPAN_RUNS)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configs (C4 direct, C5 sparse, C3 mixed; N=1 only)")
     ap.add_argument("--sustain", type=float, default=2.0, help="seconds of the sustained window reported beside the K-step number (0 = skip)")
     ap.add_argument("--no-e2e-host", action="store_true", help="skip the e2e_host leg (egress drain of every byte to host memory)")
@@ -226,7 +241,9 @@ def main():
     eng = pkg.Engine(device=local, stream=stream.cuda_stream, max_conns=n_conns, max_topics=256, max_keys=world * n_conns,
                      max_key_len=KEY_LEN, ring_bytes_per_conn=ring_bytes, max_batch_msgs=max(64, M), max_batch_bcast=max(16, M),
                      max_batch_bytes=max(1 << 20, 4 * M * (rec + 64)), max_batch_deliveries=M * n_conns + 1024, batch_slots=4,
-                     pack_variant=args.variant, flags=pkg.FLAG_HOST_RINGS if args.host_rings else 0, **shard_kw)
+                     pack_variant=args.variant,
+                     flags=(pkg.FLAG_HOST_RINGS if args.host_rings else 0) | (0 if args.plain_spans else pkg.FLAG_SPAN_RUNS) |
+                           (pkg.FLAG_OUTPUT_POOL if args.pool else 0), **shard_kw)
     # world x 2^20 subscribers, all on topic 0.  Every rank replays the same control plane (the SPMD
     # contract of a multi-process group): connections go to the least-loaded shard, i.e. round robin,
     # so each GPU ends up owning exactly n_conns of them.
@@ -357,24 +374,44 @@ def main():
         assert res.n_spans == n_conns and res.n_overflow == 0
         if not args.no_verify:
             base, rb, mc = eng.ring_info()
-
-            class _Arr:
-                __cuda_array_interface__ = {"shape": (n_conns, rb), "typestr": "|u1", "data": (base, False), "version": 3}
-
-            ring = torch.as_tensor(_Arr(), device=dev)
             image = bytearray()
             for fr in frames:
                 image += L.to_bytes(4, "big") + fr + bytes(rec - F)
             # pad bytes are unspecified: compare only the F framed bytes of each record
             img = torch.from_numpy(np.frombuffer(bytes(image), dtype=np.uint8).copy()).to(dev).view(M, rec)[:, :F]
-            off = res.spans[0].ring_off
             ok = True
-            for c0 in range(0, n_conns, 1 << 16):
-                blk = ring[c0:c0 + (1 << 16), off:off + M * rec].reshape(-1, M, rec)[:, :, :F]
-                ok = ok and bool((blk == img.unsqueeze(0)).all().item())
-            spans = np.ctypeslib.as_array(C.cast(res.spans, C.POINTER(C.c_uint32)), shape=(res.n_spans, 4))
-            ok = ok and bool((spans[:, 1] == off).all()) and bool((spans[:, 2] == M * rec).all()) and \
-                bool((spans[:, 3] == M).all()) and len(np.unique(spans[:, 0])) == n_conns
+            if args.pool:
+                # output pool: the batch is ONE region [pool_base, +n_conns * M * rec), connection after connection
+                pb = int(res.pool_base) * 32
+
+                class _Pool:
+                    __cuda_array_interface__ = {"shape": (n_conns * M * rec,), "typestr": "|u1", "data": (base + pb, False), "version": 3}
+
+                region = torch.as_tensor(_Pool(), device=dev).view(n_conns, M, rec)
+                for c0 in range(0, n_conns, 1 << 16):
+                    ok = ok and bool((region[c0:c0 + (1 << 16), :, :F] == img.unsqueeze(0)).all().item())
+                runs = np.ctypeslib.as_array(C.cast(res.runs, C.POINTER(C.c_uint32)), shape=(res.n_runs, 6)).astype(np.int64)
+                stride = M * rec // 32
+                ok = ok and bool((runs[:, 2] == (runs[:, 0] - rank * sd.shard_stride) * stride).all()) and bool((runs[:, 3] == M * rec).all()) and \
+                    bool((runs[:, 4] == M).all()) and bool((runs[:, 5] == stride).all()) and int(runs[:, 1].sum()) == n_conns
+            else:
+                class _Arr:
+                    __cuda_array_interface__ = {"shape": (n_conns, rb), "typestr": "|u1", "data": (base, False), "version": 3}
+
+                ring = torch.as_tensor(_Arr(), device=dev)
+                off = res.runs[0].ring_off if res.runs else res.spans[0].ring_off
+                for c0 in range(0, n_conns, 1 << 16):
+                    blk = ring[c0:c0 + (1 << 16), off:off + M * rec].reshape(-1, M, rec)[:, :, :F]
+                    ok = ok and bool((blk == img.unsqueeze(0)).all().item())
+                if res.runs:   # run-length span table: {conn0, n_conns, ring_off, len, n_records, off_stride}
+                    runs = np.ctypeslib.as_array(C.cast(res.runs, C.POINTER(C.c_uint32)), shape=(res.n_runs, 6))
+                    covered = np.concatenate([np.arange(c0, c0 + n, dtype=np.int64) for c0, n in runs[:, :2]])
+                    ok = ok and bool((runs[:, 2] == off).all()) and bool((runs[:, 3] == M * rec).all()) and \
+                        bool((runs[:, 4] == M).all()) and len(np.unique(covered)) == n_conns == len(covered)
+                else:
+                    spans = np.ctypeslib.as_array(C.cast(res.spans, C.POINTER(C.c_uint32)), shape=(res.n_spans, 4))
+                    ok = ok and bool((spans[:, 1] == off).all()) and bool((spans[:, 2] == M * rec).all()) and \
+                        bool((spans[:, 3] == M).all()) and len(np.unique(spans[:, 0])) == n_conns
             assert ok, "ring contents differ from the expected framed records"
             verify = "all %d connections x %d records bit-exact" % (n_conns, M)
         eng.release_batch(b)
@@ -484,23 +521,24 @@ def main():
             assert seen["spans"] == n_conns and seen["bad"] == 0, seen
             host_verify = "all %d connections x %d records bit-exact in host memory" % (n_conns, M)
         e2e_host = {"value": world * egress_step * nh / float(t_h.item()) / 1e9, "unit": "GB/s", "steps": nh,
-                    "d2h_bytes_per_step": n_conns * M * rec + 16 * n_conns + 64, "h2d_bytes_per_step": M * slot + 64 + 22 * M + 64 + 24 * n_conns,
+                    "d2h_bytes_per_step": n_conns * M * rec + (16 * n_conns if args.plain_spans else 24 * int(r.n_runs)) + 64, "h2d_bytes_per_step": M * slot + 64 + 22 * M + 64 + 24 * n_conns,
                     "chunks_per_step": int(st.chunks), "verify": host_verify,
                     "note": "pcdn_submit (host buffers) -> pcdn_egress_drain: every framed record lands in pinned host memory "
                             "(gather kernel + one DMA per 64 MiB chunk, double-buffered); PCIe-bound"}
         eg.close()
     clocks = sampler.stop()  # sampled from the start of the timed region to the end of the e2e loop (all under load)
     h2d = M * slot + 64 + 22 * M + 64 if (world == 1 or rank == 0) else 0
-    d2h = 64 + 16 * n_conns
+    d2h = 64 + (16 * n_conns if args.plain_spans else 24 * int(r.n_runs))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
             cores = os.cpu_count() or 1
-            r = run_cpu_reference(n_conns, args.payload, M, 3, 1, cores, timeout=600)
+            cmodel, calib = pick_cpu_model(n_conns, args.payload, M, cores)
+            r = run_cpu_reference(n_conns, args.payload, M, 3, 1, cores, timeout=600, model=cmodel)
             cpu = {"value": r["gbps_median_step"], "unit": "GB/s", "cores": r["threads"], "kind": "port",
                    "sample": "%d msgs x %d subscribers per step, median of 3 steps after 1 warm-up (mean over the 3: %.3f GB/s)" % (M, n_conns, r["gbps"]),
-                   "model": r.get("model"),
+                   "model": r.get("model"), "model_calibration": calib,
                    "deliveries_per_s": r["deliveries_per_s"], "stage12_s": r["stage12_s"], "stage3_s": r["stage3_s"]}
         except Exception as ex:  # the baseline is reported, never required for our number
             cpu = {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
@@ -539,6 +577,7 @@ def main():
                                                                           ("every shard copies the batch from host memory" if args.ingest == "host" else
                                                                            "library-issued ncclBroadcast ingest over NVLink (%d ranks)" % sd.nccl_ranks))
                        if world > 1 else "single GPU", "l2": "outputs 9.1 GB/step >> L2; inputs 8.7 KB (algorithmically resident)",
+                       "output": "shared output pool (PCDN_FLAG_OUTPUT_POOL)" if args.pool else "per-connection rings",
                        "pack_variant": args.variant, "verify": verify, "setup_s": round(setup_s, 2)},
             "roofline": {"bound": "hbm", "kernel": "k_pack (connection-major phase)" if not (args.variant & 2) else "k_pack (message-major phase)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source, "peak_source": peak_src,

@@ -91,6 +91,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--hit", type=float, default=1.0, help="C4: fraction of recipients that exist")
+    ap.add_argument("--msgs", type=int, default=0, help="C3: messages per batch (default 128; SURVEY 8d asks for 1024, which needs --pool)")
+    ap.add_argument("--pool", type=float, default=0.0, help="GB of shared output pool (PCDN_FLAG_OUTPUT_POOL) instead of per-connection rings")
     ap.add_argument("--ingest", choices=["host", "device"], default=None,
                     help="C4 only: measure end-to-end ingest of RAW FRAMES from host memory through pcdn_receive_frames with the host parser or the device parse kernel")
     args = ap.parse_args()
@@ -115,7 +117,7 @@ def main():
     if wl == "latency":
         # one message at a time through the host-buffer API: submit → poll (counters + span table back)
         out = {"metric": "single-message fan-out latency, host buffers in, pcdn_submit → pcdn_poll complete (wall clock)", "unit": "us", "cases": []}
-        for n, host_rings in ((128, False), (128, True), (1 << 14, False), (1 << 20, False)):
+        for n, host_rings, runs in ((128, False, False), (128, True, False), (1 << 14, False, False), (1 << 20, False, False), (1 << 20, False, True)):
             rng = np.random.default_rng(9)
             keys = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
             keys[:, :8] = np.arange(n, dtype=np.uint64).view(np.uint8).reshape(n, 8)
@@ -124,12 +126,14 @@ def main():
             eng = pkg.Engine(device=0, stream=stream.cuda_stream, max_conns=n, max_topics=16, max_keys=n, max_key_len=32,
                              ring_bytes_per_conn=16 * rec, max_batch_msgs=64, max_batch_bcast=16, max_batch_bytes=1 << 20,
                              max_batch_deliveries=n + 1024, batch_slots=2, pack_variant=args.variant,
-                             flags=pkg.FLAG_HOST_RINGS if host_rings else 0)
+                             flags=(pkg.FLAG_HOST_RINGS if host_rings else 0) | (pkg.FLAG_SPAN_RUNS if runs else 0))
             eng.add_users_bulk(keys, 32, np.zeros(n, dtype=np.uint16), np.arange(n + 1, dtype=np.uint32))
             rcpt = keys[n // 2].tobytes()
             tmpl, roff, poff = direct_frame_template(32, 512)
             draw = bytearray(tmpl); draw[roff:roff + 32] = rcpt; draw = bytes(draw)
             tag = " — rings in host memory (PCDN_FLAG_HOST_RINGS): framed bytes readable in place when poll returns" if host_rings else ""
+            if runs:
+                tag += " — run-length span table (PCDN_FLAG_SPAN_RUNS)"
             for name, msgs in (("broadcast 1 KiB to all %d subscribers%s" % (n, tag), [("b", [0], raw, False)]),
                                ("direct 512 B to one of %d users%s" % (n, tag), [("d", rcpt, draw, False)])):
                 ts, tsub = [], []
@@ -285,15 +289,16 @@ def main():
                 "hit_rate": args.hit}
         F = 4 + L
     elif wl == "C3":
-        n, T, M = 65536, 4096, 128
+        n, T, M = 65536, 4096, (args.msgs or 128)
         rng = np.random.default_rng(3)
         p = zipf_p(T)
         keys = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
         keys[:, :8] = np.arange(n, dtype=np.uint64).view(np.uint8).reshape(n, 8)
         subs = np.stack([rng.choice(T, size=8, replace=False, p=p) for _ in range(n)]).astype(np.uint16)
+        pool_kw = dict(flags=pkg.FLAG_OUTPUT_POOL, pool_bytes=int(args.pool * 1e9)) if args.pool else {}
         eng = pkg.Engine(device=0, stream=stream.cuda_stream, max_conns=n, max_topics=T, max_keys=n, max_key_len=32,
-                         ring_bytes_per_conn=1 << 20, max_batch_msgs=M, max_batch_bcast=M, max_batch_bytes=16 << 20,
-                         max_batch_deliveries=M * n, batch_slots=2, pack_variant=args.variant)
+                         ring_bytes_per_conn=1 << 20, max_batch_msgs=M, max_batch_bcast=M, max_batch_bytes=max(16, M // 8) << 20,
+                         max_batch_deliveries=min(M * n, 1 << 27), batch_slots=2, pack_variant=args.variant, **pool_kw)
         eng.add_users_bulk(keys, 32, subs.reshape(-1).copy(), (np.arange(n + 1) * 8).astype(np.uint32))
         rng4, rng5 = np.random.default_rng(4), np.random.default_rng(5)
         topics = rng4.choice(T, size=M, p=p)
@@ -311,7 +316,8 @@ def main():
         per_topic = np.bincount(subs.reshape(-1), minlength=T)
         expect_deliveries = int(per_topic[topics].sum())
         alg_bytes = lambda d, bo: bo + int(lens.sum()) + M * (n // 8)
-        desc = {"workload": "C3: 64 K subscribers, 4 K topics (extended ids) Zipf-0.99, 8 subscriptions each, payloads 256 B-64 KiB, %d msgs per step" % M}
+        desc = {"workload": "C3: 64 K subscribers, 4 K topics (extended ids) Zipf-0.99, 8 subscriptions each, payloads 256 B-64 KiB, %d msgs per step" % M,
+                "output": ("shared output pool of %.0f GB (PCDN_FLAG_OUTPUT_POOL)" % args.pool) if args.pool else "per-connection rings of 1 MiB"}
         F = None
     else:
         n, K = 1 << 20, 4096
@@ -403,6 +409,9 @@ def main():
     with torch.cuda.stream(stream):
         def step():
             nonlocal prev, it
+            if prev and args.pool and wl == "C3" and M > 512:
+                eng.release_batch(prev)          # the pool holds ONE such batch: its consumer must be done before the next fits
+                prev = 0
             b = eng.submit_device((dbs[it & 1] if multi else db).db)   # N > 1: the library broadcasts it to every shard
             it += 1
             if prev:

@@ -119,6 +119,7 @@ typedef struct pcdn_config {
   uint32_t world_shards;        /* total shards of the broker over all processes (0 = n_devices)            */
   uint32_t first_shard;         /* global index of devices[0]                                               */
   const void* nccl_unique_id;   /* world_shards > n_devices: the 128-byte id from pcdn_nccl_unique_id(), identical in every process */
+  uint64_t pool_bytes;          /* PCDN_FLAG_OUTPUT_POOL: bytes of the output pool per shard (0 = max_conns * ring_bytes_per_conn; < 128 GiB) */
   uint64_t global_memory_pool_size; /* Limiter analogue (cdn-proto/src/connection/limiter/mod.rs:56-68,
                                  * cdn-broker/src/binaries/broker.rs:71-72 default 1 GiB): bytes of inbound frames
                                  * that may be in flight (accepted, their batch not yet released); 0 = unlimited.
@@ -156,7 +157,25 @@ enum {
    * returns: pcdn_host_rings() gives the base pointer, a span's bytes are at
    * base + conn * ring_bytes_per_conn + ring_off.  Egress is then bounded by PCIe (≈50 GB/s, above
    * any NIC) instead of HBM; rings in HBM (default) are for GPUDirect hand-off and measurement.   */
-  PCDN_FLAG_HOST_RINGS = 4
+  PCDN_FLAG_HOST_RINGS = 4,
+  /* Run-length span table: pcdn_batch_result.runs / n_runs instead of spans (spans == NULL; n_spans
+   * still counts the spans the runs stand for).  A run = n_conns CONSECUTIVE connection ids that each
+   * own an identical span.  A dense broadcast batch to 2^20 connections is 4096 runs (96 KB) instead
+   * of a 16 MB table over PCIe per batch; sparse batches degrade to one run per span.              */
+  PCDN_FLAG_SPAN_RUNS = 8,
+  /* One shared OUTPUT POOL per GPU instead of a fixed ring per connection: every batch gets one
+   * contiguous region of the pool, laid out connection by connection (each connection's records back
+   * to back, in batch order), and the region is freed as a whole by pcdn_release_batch.  Memory is
+   * sized by traffic (pcdn_config.pool_bytes), not by max_conns x the hottest connection, and no
+   * connection can overflow: n_overflow is always 0.  A batch that does not fit the free part of the
+   * pool is REFUSED AS A WHOLE — pcdn_batch_result.status = PCDN_EAGAIN (as a positive number), nothing
+   * written — and so is every batch launched after it (order!); the host releases older batches and
+   * calls pcdn_retry_batch, oldest first.  This is the reference Limiter's ingress back-pressure
+   * (cdn-proto/src/connection/limiter/mod.rs:56-68) in place of a per-connection drop.
+   * Span offsets in this mode: pcdn_span.ring_off is in units of PCDN_RECORD_ALIGN (32 B), relative to
+   * pcdn_batch_result.pool_base; the bytes are at pool + (pool_base + ring_off) * 32 (pcdn_shard_info:
+   * rings_dev / rings_host = the pool).  pcdn_read takes the absolute unit offset pool_base + ring_off. */
+  PCDN_FLAG_OUTPUT_POOL = 16
 };
 
 /* One routed message.  `raw` is the inbound frame body and is forwarded verbatim (R1). */
@@ -181,6 +200,17 @@ typedef struct pcdn_span {
   uint32_t n_records; /* deliveries in this run                                                */
 } pcdn_span;
 
+/* PCDN_FLAG_SPAN_RUNS: connections conn0 .. conn0 + n_conns - 1 each have a span {ring_off, len, n_records} */
+typedef struct pcdn_span_run {
+  pcdn_conn conn0;
+  uint32_t n_conns;
+  uint32_t ring_off;   /* of conn0 */
+  uint32_t len;
+  uint32_t n_records;
+  uint32_t off_stride; /* added to ring_off per following connection: 0 with per-connection rings (same offset in each
+                        * connection's own ring), len / 32 units with PCDN_FLAG_OUTPUT_POOL (the regions follow each other) */
+} pcdn_span_run;
+
 typedef struct pcdn_batch_result {
   uint64_t batch_id;
   uint32_t n_msgs;
@@ -195,6 +225,9 @@ typedef struct pcdn_batch_result {
   const int8_t* msg_status;        /* device-parse batches: per message 0 or PCDN_EPARSE / PCDN_EPRUNE (the reference would have ended that sender's receive loop); NULL otherwise */
   uint32_t n_msg_errors;           /* number of non-zero entries in msg_status                  */
   uint32_t reserved;
+  const pcdn_span_run* runs;       /* PCDN_FLAG_SPAN_RUNS: the span table in run-length form (then spans == NULL) */
+  uint32_t n_runs;
+  uint32_t pool_base;              /* PCDN_FLAG_OUTPUT_POOL: first 32-byte unit of this batch's region; span offsets are relative to it (0 otherwise) */
 } pcdn_batch_result;
 
 /* Device-resident batch (inputs already in HBM; used by bench `value` and the NCCL ingest path).
@@ -383,6 +416,10 @@ int pcdn_poll(pcdn_engine* e, uint64_t batch_id, pcdn_batch_result* out, int blo
 /* Copy `len` ring bytes of a connection to host memory (what a socket writer would send).
  * With PCDN_FLAG_HOST_RINGS this is a plain memcpy; prefer pcdn_host_rings() and read in place.  */
 int pcdn_read(pcdn_engine* e, pcdn_conn conn, uint32_t ring_off, uint32_t len, void* dst);
+/* PCDN_FLAG_OUTPUT_POOL: run a refused batch (status PCDN_EAGAIN) again after older batches have been
+ * released.  Only the oldest unreleased batch can be retried; its result is polled again afterwards.
+ * The batch is routed against the tables as they are at the retry. */
+int pcdn_retry_batch(pcdn_engine* e, uint64_t batch_id);
 /* The host has written every span of the batch: free its ring space and its slot.  This is the
  * analogue of dropping the last `Bytes` clone (limiter/pool.rs:44-52).  In order, oldest first. */
 int pcdn_release_batch(pcdn_engine* e, uint64_t batch_id);
@@ -399,7 +436,7 @@ typedef struct pcdn_shard_desc {
   uint32_t shard_stride;  /* id range per shard (max_conns rounded up to a multiple of 8192)         */
   void* rings_dev;        /* device address of this shard's rings [max_conns][ring_bytes_per_conn]    */
   const void* rings_host; /* PCDN_FLAG_HOST_RINGS: host address of the same rings, else NULL          */
-  uint64_t ring_bytes;
+  uint64_t ring_bytes;    /* per-connection ring; PCDN_FLAG_OUTPUT_POOL: bytes of the whole pool      */
   uint32_t n_conns;       /* connections currently living on this shard                               */
   uint32_t nccl_ranks;    /* size of the ingest communicator this shard belongs to (0 = none)        */
 } pcdn_shard_desc;

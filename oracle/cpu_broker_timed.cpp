@@ -24,11 +24,12 @@
 // It is deliberately generous to the CPU: no tokio scheduling, no syscalls/TLS, no allocator
 // contention between stages, perfect static load balance.
 //
-// usage: cpu_broker_timed <n_conns> <payload_bytes> <msgs_per_step> <steps> <warmup> <threads>
+// usage: cpu_broker_timed <n_conns> <payload_bytes> <msgs_per_step> <steps> <warmup> <threads> [model 0|1]
 // prints one JSON object.
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -83,6 +84,10 @@ int main(int argc, char** argv) {
   const size_t N = strtoull(argv[1], 0, 10), K = strtoull(argv[2], 0, 10), M = strtoull(argv[3], 0, 10);
   const int steps = atoi(argv[4]), warmup = atoi(argv[5]);
   int T = atoi(argv[6]);
+  // model 0 = "phases": all threads run the receive loops, then all threads run the writer tasks
+  //           (partitioned); model 1 = "overlap": writer tasks run concurrently with the receive loops
+  //           and are woken per connection.  bench.py calibrates both and reports the FASTER one.
+  const int model = argc > 7 ? atoi(argv[7]) : 1;
   if (T <= 0) T = (int)std::thread::hardware_concurrency();
   if (T <= 0) T = 1;
   const size_t L = 8 * (6 + 1 + (K + 7) / 8), F = 4 + L;  // single-segment Broadcast, one topic
@@ -114,18 +119,32 @@ int main(int argc, char** argv) {
 
   // Persistent worker threads (the reference's tokio runtime is started once), and the writer tasks
   // run CONCURRENTLY with the receive loops: routers = one thread per in-flight message (a receive
-  // loop handles its sender's messages sequentially), every other thread is a writer that keeps
-  // draining the queues of its connection partition until the routers are done and the queues empty.
-  const int R = (int)std::min<size_t>(M, (size_t)std::max(1, T / 2));  // router threads
-  const int Wt = std::max(1, T - R);                                   // writer threads
+  // loop handles its sender's messages sequentially), every other thread runs writer tasks.  A writer
+  // task is WOKEN when its connection's queue becomes non-empty (the first push after it went idle
+  // schedules the connection on its writer thread's ready list, like tokio waking the task), drains
+  // the queue, and goes idle again — writers never poll connections that have nothing queued.
+  const int R = model == 0 ? T : (int)std::min<size_t>(M, (size_t)std::max(1, T / 2));  // router threads
+  const int Wt = model == 0 ? T : std::max(1, T - R);                                   // writer threads
   struct Step { std::atomic<size_t> next{0}; std::atomic<int> routers_left{0}; };
   Step st;
+  struct Ready { std::mutex mu; std::condition_variable cv; std::vector<uint32_t> q; char pad[64]; };
+  std::vector<Ready> ready(Wt);
+  std::vector<std::atomic<uint8_t>> scheduled(N);
+  for (auto& x : scheduled) x.store(0);
+  std::vector<uint32_t> conn_index_of;  // Connection* → index
+  std::unordered_map<const Connection*, uint32_t> cidx;
+  cidx.reserve(N * 2);
+  for (size_t i = 0; i < N; i++) cidx.emplace(conns[i].get(), (uint32_t)i);
   std::atomic<int> phase{0};          // bumped by the main thread to start a step
   std::atomic<int> done{0};
   std::atomic<bool> quit{false};
   std::vector<uint64_t> cs(T, 0), dl(T, 0), by(T, 0);
   std::vector<double> router_busy(T, 0), writer_busy(T, 0);
   auto now = [] { return std::chrono::steady_clock::now(); };
+  // the users map hands out the connection; its index (for the writer partition) rides along
+  std::unordered_map<Key, std::pair<std::shared_ptr<Connection>, uint32_t>, Sip13, KeyEq> users_ix;
+  users_ix.reserve(N * 2);
+  for (auto& kv : users) users_ix.emplace(kv.first, std::make_pair(kv.second, cidx[kv.second.get()]));
 
   auto router = [&](int t) {
     auto a = now();
@@ -141,32 +160,53 @@ int main(int argc, char** argv) {
       std::vector<Key> list(recipients.begin(), recipients.end());  // into_iter().collect()
       // stage 2
       for (const Key& k : list) {
-        auto it2 = users.find(k);                                  // get_user_connection
-        if (it2 == users.end()) continue;
-        std::shared_ptr<Connection> c = it2->second;               // Connection clone
+        auto it2 = users_ix.find(k);                               // get_user_connection
+        if (it2 == users_ix.end()) continue;
+        std::shared_ptr<Connection> c = it2->second.first;         // Connection clone
+        const uint32_t ci = it2->second.second;
         Bytes b = msgs[m];                                         // message.clone()
-        std::lock_guard<std::mutex> g(c->mu);
-        c->q.push_back(std::move(b));                              // send_message_raw
+        {
+          std::lock_guard<std::mutex> g(c->mu);
+          c->q.push_back(std::move(b));                            // send_message_raw
+        }
+        if (model == 1 && !scheduled[ci].exchange(1, std::memory_order_acq_rel)) {   // wake the writer task
+          Ready& r = ready[(size_t)ci * Wt / N];
+          bool was_empty;
+          {
+            std::lock_guard<std::mutex> g(r.mu);
+            was_empty = r.q.empty();
+            r.q.push_back(ci);
+          }
+          if (was_empty) r.cv.notify_one();   // the writer thread sleeps while it has nothing to do
+        }
       }
     }
-    st.routers_left.fetch_sub(1);
+    if (st.routers_left.fetch_sub(1) == 1 && model == 1)
+      for (auto& r : ready) { std::lock_guard<std::mutex> g(r.mu); r.cv.notify_all(); }   // let idle writers see the end of the step
     router_busy[t] += std::chrono::duration<double>(now() - a).count();
   };
   auto writer = [&](int t, int wi) {
     auto a = now();
-    const size_t lo = N * wi / Wt, hi = N * (wi + 1) / Wt;
+    Ready& r = ready[wi];
+    std::vector<uint32_t> woken;
     std::vector<Bytes> take;
     for (;;) {
-      const bool last = st.routers_left.load() == 0;   // read BEFORE the sweep: a sweep that starts after the routers finished sees everything
-      for (size_t c = lo; c < hi; c++) {
+      bool last;
+      {
+        std::unique_lock<std::mutex> g(r.mu);
+        r.cv.wait(g, [&] { return !r.q.empty() || st.routers_left.load() == 0; });   // blocked, not spinning: idle threads must not steal SMT cycles
+        last = st.routers_left.load() == 0;   // read BEFORE taking the list: a list taken after the routers finished is complete
+        woken.swap(r.q);
+      }
+      for (uint32_t c : woken) {
         Connection& cn = *conns[c];
+        scheduled[c].store(0, std::memory_order_release);   // a push from now on wakes the task again
         {
           std::lock_guard<std::mutex> g(cn.mu);
-          if (cn.q.empty()) continue;
           take.swap(cn.q);
         }
         for (Bytes& msg : take) {
-          uint8_t* dst = &out[(c * depth + (wr[c]++ % depth)) * slot];
+          uint8_t* dst = &out[((size_t)c * depth + (wr[c]++ % depth)) * slot];
           uint32_t len = (uint32_t)msg->size();
           dst[0] = len >> 24; dst[1] = len >> 16; dst[2] = len >> 8; dst[3] = len;  // write_u32 (BE)
           memcpy(dst + 4, msg->data(), len);                                          // write_all
@@ -175,7 +215,30 @@ int main(int argc, char** argv) {
         }
         take.clear();
       }
-      if (last) break;
+      const bool idle = woken.empty();
+      woken.clear();
+      if (last && idle) break;
+    }
+    writer_busy[t] += std::chrono::duration<double>(now() - a).count();
+  };
+  // model 0: stage 3 after a barrier — every thread walks its partition of the connections
+  std::atomic<int> routed{0};
+  std::mutex gm;
+  std::condition_variable gcv, bcv, dcv;   // step start, stage barrier, step done
+  auto phase_writer = [&](int t) {
+    auto a = now();
+    const size_t lo = N * (size_t)t / T, hi = N * (size_t)(t + 1) / T;
+    for (size_t c = lo; c < hi; c++) {
+      Connection& cn = *conns[c];
+      for (Bytes& msg : cn.q) {
+        uint8_t* dst = &out[(c * depth + (wr[c]++ % depth)) * slot];
+        uint32_t len = (uint32_t)msg->size();
+        dst[0] = len >> 24; dst[1] = len >> 16; dst[2] = len >> 8; dst[3] = len;  // write_u32 (BE)
+        memcpy(dst + 4, msg->data(), len);                                          // write_all
+        cs[t] += dst[4 + (len >> 1)];
+        dl[t]++; by[t] += 4 + len;
+      }
+      cn.q.clear();
     }
     writer_busy[t] += std::chrono::duration<double>(now() - a).count();
   };
@@ -184,11 +247,25 @@ int main(int argc, char** argv) {
     pool.emplace_back([&, t] {
       int seen = 0;
       for (;;) {
-        while (phase.load(std::memory_order_acquire) == seen && !quit.load()) std::this_thread::yield();
+        {
+          std::unique_lock<std::mutex> g(gm);
+          gcv.wait(g, [&] { return phase.load() != seen || quit.load(); });
+        }
         if (quit.load()) return;
         seen = phase.load();
-        if (t < R) router(t); else writer(t, t - R);
-        done.fetch_add(1, std::memory_order_release);
+        if (model == 0) {
+          router(t);
+          {   // barrier between the stages (threads without a message to route sleep here)
+            std::unique_lock<std::mutex> g(gm);
+            if (routed.fetch_add(1) + 1 == T) bcv.notify_all();
+            else bcv.wait(g, [&] { return routed.load() >= T; });
+          }
+          phase_writer(t);
+        } else if (t < R) router(t); else writer(t, t - R);
+        {
+          std::lock_guard<std::mutex> g(gm);
+          if (done.fetch_add(1) + 1 == T) dcv.notify_all();
+        }
       }
     });
 
@@ -199,14 +276,25 @@ int main(int argc, char** argv) {
     if (it == warmup) {
       for (int t = 0; t < T; t++) { dl[t] = by[t] = cs[t] = 0; router_busy[t] = writer_busy[t] = 0; }
     }
-    st.next.store(0); st.routers_left.store(R); done.store(0);
+    st.next.store(0); st.routers_left.store(R); done.store(0); routed.store(0);
     auto a = now();
-    phase.fetch_add(1, std::memory_order_release);
-    while (done.load(std::memory_order_acquire) < T) std::this_thread::yield();
+    {
+      std::lock_guard<std::mutex> g(gm);
+      phase.fetch_add(1);
+    }
+    gcv.notify_all();
+    {
+      std::unique_lock<std::mutex> g(gm);
+      dcv.wait(g, [&] { return done.load() >= T; });
+    }
     const double d = std::chrono::duration<double>(now() - a).count();
     if (it >= warmup) { step_s.push_back(d); sec += d; }
   }
-  quit.store(true);
+  {
+    std::lock_guard<std::mutex> g(gm);
+    quit.store(true);
+  }
+  gcv.notify_all();
   for (auto& x : pool) x.join();
   for (int t = 0; t < T; t++) { deliveries += dl[t]; bytes += by[t]; checksum += cs[t]; }
   double t12 = 0, t3 = 0;
@@ -219,8 +307,9 @@ int main(int argc, char** argv) {
          "\"router_threads\": %d, \"writer_threads\": %d, "
          "\"deliveries\": %llu, \"bytes\": %llu, \"seconds\": %.6f, \"stage12_s\": %.6f, \"stage3_s\": %.6f, "
          "\"gbps\": %.4f, \"gbps_median_step\": %.4f, \"median_step_s\": %.6f, \"deliveries_per_s\": %.1f, \"checksum\": %llu, "
-         "\"model\": \"persistent threads; writer tasks overlap the receive loops\"}\n",
+         "\"model\": \"%s\"}\n",
          N, K, F, M, steps, T, R, Wt, (unsigned long long)deliveries, (unsigned long long)bytes, sec, t12, t3,
-         bytes / sec / 1e9, med > 0 ? step_bytes / med / 1e9 : 0.0, med, deliveries / sec, (unsigned long long)checksum);
+         bytes / sec / 1e9, med > 0 ? step_bytes / med / 1e9 : 0.0, med, deliveries / sec, (unsigned long long)checksum,
+         model == 0 ? "persistent threads; receive loops then writer tasks (two phases)" : "persistent threads; writer tasks woken per connection, concurrent with the receive loops");
   return 0;
 }

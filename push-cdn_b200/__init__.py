@@ -35,6 +35,8 @@ KIND_DIRECT, KIND_BROADCAST, KIND_SUBSCRIBE, KIND_UNSUBSCRIBE = 3, 4, 5, 6
 TO_USERS_ONLY = 1
 FLAG_DEVICE_PARSE = 1
 FLAG_HOST_RINGS = 4     # rings in mapped pinned host memory: spans are readable in place (egress hand-off)
+FLAG_OUTPUT_POOL = 16   # one shared output pool per GPU instead of a ring per connection (spans: 32-byte units relative to pool_base)
+FLAG_SPAN_RUNS = 8      # run-length span table (BatchResult.runs): consecutive connections with identical spans
 FLAG_STAGED_SPANS = 2   # force the large-engine span path (table in HBM + D2H) on a small engine
 INGEST_NCCL, INGEST_HOST = 0, 1   # sharded engines: NCCL broadcast over NVLink | every shard copies from host
 RECORD_ALIGN = 32
@@ -86,7 +88,7 @@ class Config(C.Structure):
         ("flags", C.c_uint32),
         ("n_devices", C.c_uint32), ("ingest", C.c_uint32), ("devices", C.POINTER(C.c_int32)),
         ("world_shards", C.c_uint32), ("first_shard", C.c_uint32), ("nccl_unique_id", C.c_void_p),
-        ("global_memory_pool_size", C.c_uint64),
+        ("pool_bytes", C.c_uint64), ("global_memory_pool_size", C.c_uint64),
     ]
 
 
@@ -101,12 +103,18 @@ class Span(C.Structure):
     _fields_ = [("conn", C.c_uint32), ("ring_off", C.c_uint32), ("len", C.c_uint32), ("n_records", C.c_uint32)]
 
 
+class SpanRun(C.Structure):
+    _fields_ = [("conn0", C.c_uint32), ("n_conns", C.c_uint32), ("ring_off", C.c_uint32), ("len", C.c_uint32),
+                ("n_records", C.c_uint32), ("off_stride", C.c_uint32)]
+
+
 class BatchResult(C.Structure):
     _fields_ = [
         ("batch_id", C.c_uint64), ("n_msgs", C.c_uint32), ("n_spans", C.c_uint32), ("spans", C.POINTER(Span)),
         ("n_deliveries", C.c_uint64), ("bytes_out", C.c_uint64), ("n_overflow", C.c_uint32),
         ("overflow_conns", C.POINTER(C.c_uint32)), ("n_direct_dropped", C.c_uint32), ("status", C.c_uint32),
         ("msg_status", C.POINTER(C.c_int8)), ("n_msg_errors", C.c_uint32), ("reserved", C.c_uint32),
+        ("runs", C.POINTER(SpanRun)), ("n_runs", C.c_uint32), ("pool_base", C.c_uint32),
     ]
 
 
@@ -216,6 +224,7 @@ ABI = {
     "pcdn_poll": (_ci, [_vp, _u64, C.POINTER(BatchResult), _ci]),
     "pcdn_read": (_ci, [_vp, _u32, _u32, _u32, _vp]),
     "pcdn_release_batch": (_ci, [_vp, _u64]),
+    "pcdn_retry_batch": (_ci, [_vp, _u64]),
     "pcdn_nccl_unique_id": (_ci, [_vp]),
     "pcdn_num_shards": (_ci, [_vp, C.POINTER(_u32), C.POINTER(_u32)]),
     "pcdn_shard_info": (_ci, [_vp, _u32, C.POINTER(ShardDesc)]),
@@ -539,7 +548,19 @@ class Engine:
     def release_batch(self, batch_id: int) -> None:
         self._chk(self.L.pcdn_release_batch(self.h, batch_id))
 
+    def retry_batch(self, batch_id: int) -> None:
+        """output-pool engines: run a batch again that was refused for space (status PCDN_EAGAIN)"""
+        self._chk(self.L.pcdn_retry_batch(self.h, batch_id))
+
     def spans(self, res: BatchResult) -> List[Tuple[int, int, int, int]]:
+        """(conn, ring_off, len, n_records) per span; a run-length table (FLAG_SPAN_RUNS) is expanded"""
+        if res.runs:
+            out = []
+            for i in range(res.n_runs):
+                r = res.runs[i]
+                out.extend((r.conn0 + k, r.ring_off + k * r.off_stride, r.len, r.n_records) for k in range(r.n_conns))
+            assert len(out) == res.n_spans, (len(out), res.n_spans)
+            return out
         return [(res.spans[i].conn, res.spans[i].ring_off, res.spans[i].len, res.spans[i].n_records)
                 for i in range(res.n_spans)]
 
@@ -552,6 +573,7 @@ class Engine:
         sh = self.shards()
         stride, rbytes = sh[0].shard_stride, sh[0].ring_bytes
         hosts = {d.global_index: d.rings_host for d in sh if d.rings_host}
+        pool = bool(self.cfg.flags & FLAG_OUTPUT_POOL)   # offsets: 32-byte units relative to res.pool_base
         for conn, off, ln, nrec in self.spans(res):
             per.setdefault(conn, []).append((off, ln, nrec))
         out: Dict[int, List[bytes]] = {}
@@ -562,7 +584,11 @@ class Engine:
             for off, ln, nrec in pieces:
                 # host rings: the bytes are read in place, exactly what a socket writer would do
                 hb = hosts.get(conn // stride)
-                data = C.string_at(hb + (conn % stride) * rbytes + off, ln) if hb else self.read(conn, off, ln)
+                if pool:
+                    unit = res.pool_base + off
+                    data = C.string_at(hb + unit * RECORD_ALIGN, ln) if hb else self.read(conn, unit, ln)
+                else:
+                    data = C.string_at(hb + (conn % stride) * rbytes + off, ln) if hb else self.read(conn, off, ln)
                 p = 0
                 for _ in range(nrec):
                     L = int.from_bytes(data[p:p + 4], "big")
@@ -581,6 +607,9 @@ class Engine:
             if not b:
                 return out
             res = self.poll(b)
+            if res.status == 11:      # PCDN_EAGAIN: refused for space in the output pool; everything older is released by now
+                self.retry_batch(b)
+                res = self.poll(b)
             if res.status:
                 self.release_batch(b)
                 raise PcdnError(-int(res.status), "batch rejected on the device")

@@ -68,6 +68,7 @@ struct ShardEgress {
   uint8_t* h_stage[kHostBufs] = {nullptr, nullptr, nullptr};
   GatherDesc* h_desc[kHostBufs] = {nullptr, nullptr, nullptr};
   std::vector<uint64_t> data_off[kHostBufs];
+  std::vector<pcdn_span> expanded;
   cudaStream_t gs = nullptr, cs = nullptr;
   cudaEvent_t ev_gather[kDevBufs] = {nullptr, nullptr};
   cudaEvent_t ev_chunk[kHostBufs] = {nullptr, nullptr, nullptr};  // chunk is in host memory (also: its device buffer is free)
@@ -204,16 +205,30 @@ int drain_shard(pcdn_egress* g, uint64_t batch_id, uint32_t li, pcdn_egress_sink
   ShardEgress& s = g->sh[li];
   const uint64_t ring_bytes = e->cfg.ring_bytes_per_conn;
   const uint32_t base = sh.dev.conn_base;
-  const pcdn_span* sp = res.spans;
-  const uint32_t ns = res.n_spans;
+  // run-length span tables (PCDN_FLAG_SPAN_RUNS) are expanded here: the sink always sees plain spans
+  if (res.runs) {
+    s.expanded.clear();
+    for (uint32_t i = 0; i < res.n_runs; i++) {
+      const pcdn_span_run& r = res.runs[i];
+      for (uint32_t k = 0; k < r.n_conns; k++) s.expanded.push_back(pcdn_span{r.conn0 + k, r.ring_off + k * r.off_stride, r.len, r.n_records});
+    }
+  }
+  const pcdn_span* sp = res.runs ? s.expanded.data() : res.spans;
+  const uint32_t ns = res.runs ? (uint32_t)s.expanded.size() : res.n_spans;
   st->spans += ns;
+  // where a span's records lie inside the shard's ring array / output pool
+  const bool pool = sh.dev.pool != 0;
+  const uint64_t pool_base = res.pool_base;
+  auto src_of = [&](const pcdn_span& x) -> uint64_t {
+    return pool ? (pool_base + x.ring_off) * (uint64_t)PCDN_RECORD_ALIGN : (uint64_t)(x.conn - base) * ring_bytes + x.ring_off;
+  };
   if (sh.h_rings) {
     // egress hand-off mode: one chunk, the records are read where the pack kernel stored them
     std::vector<uint64_t>& off = s.data_off[0];
     off.resize(ns);
     uint64_t bytes = 0;
-    for (uint32_t i = 0; i < ns; i++) { off[i] = (uint64_t)(sp[i].conn - base) * ring_bytes + sp[i].ring_off; bytes += sp[i].len; }
-    pcdn_egress_chunk ch{li, ns, sp, off.data(), sh.h_rings, (uint64_t)e->geo.shard_max_conns * ring_bytes};
+    for (uint32_t i = 0; i < ns; i++) { off[i] = src_of(sp[i]); bytes += sp[i].len; }
+    pcdn_egress_chunk ch{li, ns, sp, off.data(), sh.h_rings, sh.dev.pool ? e->pool_bytes : (uint64_t)e->geo.shard_max_conns * ring_bytes};
     st->bytes += bytes; st->chunks += 1;
     if (ns && sink) {
       std::lock_guard<std::mutex> sl(g->sink_mu);
@@ -231,7 +246,7 @@ int drain_shard(pcdn_egress* g, uint64_t batch_id, uint32_t li, pcdn_egress_sink
     off.resize(r.i1 - r.i0);
     uint64_t at = 0;
     for (uint32_t i = r.i0; i < r.i1; i++) {
-      hd[i - r.i0] = GatherDesc{(unsigned long long)(sp[i].conn - base) * ring_bytes + sp[i].ring_off, at, sp[i].len, 0};
+      hd[i - r.i0] = GatherDesc{(unsigned long long)src_of(sp[i]), at, sp[i].len, 0};
       off[i - r.i0] = at;
       at += sp[i].len;
     }
@@ -407,7 +422,8 @@ int pcdn_egress_create(pcdn_engine* e, const pcdn_egress_config* cfg, pcdn_egres
   g->e = e;
   if (cfg) g->cfg = *cfg;
   if (!g->cfg.chunk_bytes) g->cfg.chunk_bytes = 64ull << 20;
-  g->cfg.chunk_bytes = std::max<uint64_t>(align_up(g->cfg.chunk_bytes, 4096), 2 * e->cfg.ring_bytes_per_conn);
+  if (!(e->cfg.flags & PCDN_FLAG_OUTPUT_POOL)) g->cfg.chunk_bytes = std::max<uint64_t>(g->cfg.chunk_bytes, 2 * e->cfg.ring_bytes_per_conn);
+  g->cfg.chunk_bytes = align_up(g->cfg.chunk_bytes, 4096);
   if (!g->cfg.n_threads) g->cfg.n_threads = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
   g->pool.reset(new Pool(g->cfg.n_threads));
   g->fds.assign(e->geo.N, -1);

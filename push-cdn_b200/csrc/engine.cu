@@ -121,20 +121,29 @@ int acquire_open_slot(pcdn_engine* e) {
 
 // run the kernel pipeline of one shard for slot `si`, whose BatchIn is ready (or will be, once
 // ev_ingest fires) in that shard's memory
-int launch_shard_pipeline(pcdn_engine* e, Shard& sh, uint32_t si, uint32_t n_direct, bool devparse, bool wait_ingest) {
+int launch_shard_pipeline(pcdn_engine* e, Shard& sh, uint32_t si, uint32_t n_direct, bool devparse, bool wait_ingest, bool unblock = false) {
   DeviceGuard dg(sh.device);
   ShardSlot& s = sh.slots[si];
   // Default: the pack runs on the main stream.  A/B switch (pack_variant bit 3): run it on the
   // high-priority pack stream so the next batch's control kernels overlap it — measured SLOWER for
   // the bulk-store pack (profiles/r1_sweep_overlap.txt), so it stays opt-in.
   const bool dp = sh.direct_publish;
-  cudaStream_t st = sh.stream, ps = (!dp && (e->cfg.pack_variant & 8)) ? sh.pack_stream : sh.stream, cs = sh.copy_stream;
+  // Batches of nothing but many direct messages DO take the pack stream: their control kernels are
+  // latency-bound (three dependent random reads per message), their pack is a separate bandwidth-bound
+  // launch, and the two overlap well — C4: 1.98 → 2.10 G msgs/s (profiles/r2_cfg_C4_sweep_v*.json).
+  const bool direct_only = s.in.n_bcast == 0 && n_direct >= kThinSeparateMin;
+  cudaStream_t st = sh.stream, ps = (!dp && ((e->cfg.pack_variant & 8) || direct_only)) ? sh.pack_stream : sh.stream, cs = sh.copy_stream;
   const bool has_direct = n_direct > 0;
   if (wait_ingest) CUDA_TRY(cudaStreamWaitEvent(st, s.ev_ingest, 0));
   s.timed = e->timing;
   s.polled = false;
   s.n_msg_errors = 0;
-  if (++s.w.stamp == 0) s.w.stamp = 1;  // validity stamp of this batch's direct buckets
+  if (++s.w.stamp == 0) s.w.stamp = 1;  // validity stamp of this batch's direct buckets / look-back words
+  if (sh.dev.pool && (s.w.stamp & 0x3FFFFFFFu) == 0) {   // the look-back words carry 30 bits of it
+    s.w.stamp++;
+    CUDA_TRY(cudaMemsetAsync(s.w.lb_state, 0, ((size_t)sh.dev.N / 256 + 1) * 8, st));
+  }
+  s.w.pool_unblock = unblock ? 1u : 0u;
   // latency path of the smallest geometry: match + plan + offsets in one cluster launch that also
   // zeroes / publishes the counters (kernels.cu: k_ctrl_small)
   // (one cluster of 8 CTAs: worth it while the whole match is a few passes — a 128-message batch on a
@@ -522,6 +531,9 @@ int init_shard(pcdn_engine* e, Shard& sh, int ndev, void* user_stream) {
   d.n_valid_topics = c.n_valid_topics;
   d.max_key_len = c.max_key_len;
   d.conn_base = sh.gindex * Ns;
+  d.span_runs = (c.flags & PCDN_FLAG_SPAN_RUNS) ? 1u : 0u;
+  d.pool = (c.flags & PCDN_FLAG_OUTPUT_POOL) ? 1u : 0u;
+  d.pool_units = (uint32_t)(e->pool_bytes / kUnit);
   d.count_drops = sh.gindex == 0 ? 1u : 0u;
   DEV_ALLOC(d.sub, (size_t)g.T * Ws);
   DEV_ALLOC(d.brk, Ws);
@@ -530,11 +542,16 @@ int init_shard(pcdn_engine* e, Shard& sh, int ndev, void* user_stream) {
   DEV_ALLOC(d.keys, (size_t)g.max_keys * g.key_stride);
   DEV_ALLOC(d.ptail, Ns);
   DEV_ALLOC(d.used, Ns);
+  const size_t out_bytes = d.pool ? (size_t)e->pool_bytes : (size_t)g.shard_max_conns * c.ring_bytes_per_conn;
   if (c.flags & PCDN_FLAG_HOST_RINGS) {
     // egress hand-off: the pack stores straight into host memory the socket writers read
-    PIN_ALLOC_MAPPED(sh.h_rings, d.rings, (size_t)g.shard_max_conns * c.ring_bytes_per_conn);
+    PIN_ALLOC_MAPPED(sh.h_rings, d.rings, out_bytes);
   } else {
-    DEV_ALLOC(d.rings, (size_t)g.shard_max_conns * c.ring_bytes_per_conn);
+    DEV_ALLOC(d.rings, out_bytes);
+  }
+  if (d.pool) {
+    DEV_ALLOC(d.pool_state, 1);
+    launch_pool_init(d, sh.stream);
   }
   CUDA_TRY(cudaMemsetAsync(d.sub, 0, (size_t)g.T * Ws * 4, sh.stream));
   CUDA_TRY(cudaMemsetAsync(d.brk, 0, (size_t)Ws * 4, sh.stream));
@@ -588,13 +605,22 @@ int init_shard(pcdn_engine* e, Shard& sh, int ndev, void* user_stream) {
     CUDA_TRY(cudaMemsetAsync(w.dstamp, 0, ((size_t)Ns + 1) * 4, sh.stream));
     w.stamp = 0;
     DEV_ALLOC(w.batch_units, Ns);
-    DEV_ALLOC(s.d_spans_dev, (size_t)2 * Ns);
+    if (d.pool) {
+      DEV_ALLOC(w.cbase, Ns);
+      DEV_ALLOC(w.lb_state, (size_t)Ns / 256 + 1);
+      DEV_ALLOC(w.lb_ticket, 1);
+      CUDA_TRY(cudaMemsetAsync(w.lb_state, 0, ((size_t)Ns / 256 + 1) * 8, sh.stream));
+      CUDA_TRY(cudaMemsetAsync(w.lb_ticket, 0, 4, sh.stream));
+    }
+    w.pool_unblock = 0;
+    const size_t span_entries = (size_t)2 * Ns * (d.span_runs ? 3 : 2) / 2;  // SpanRun = 24 B, Span = 16 B
+    DEV_ALLOC(s.d_spans_dev, span_entries);
     DEV_ALLOC(s.d_ovf_dev, Ns);
     if (sh.direct_publish) {
-      PIN_ALLOC_MAPPED(s.h_spans, s.d_spans_map, (size_t)2 * Ns);
+      PIN_ALLOC_MAPPED(s.h_spans, s.d_spans_map, span_entries);
       PIN_ALLOC_MAPPED(s.h_overflow, s.d_ovf_map, (size_t)Ns);
     } else {
-      PIN_ALLOC(s.h_spans, (size_t)2 * g.shard_max_conns);
+      PIN_ALLOC(s.h_spans, span_entries);
       PIN_ALLOC(s.h_overflow, g.shard_max_conns);
     }
     w.spans = s.d_spans_dev; w.overflow = s.d_ovf_dev;
@@ -758,6 +784,14 @@ int pcdn_create(const pcdn_config* cfg, pcdn_engine** out) {
   g.bucket_mask = nb - 1;
   g.max_owners = 4096;
   g.seed = cfg->hash_seed ? cfg->hash_seed : 0x243F6A8885A308D3ULL;
+  if (cfg->flags & PCDN_FLAG_OUTPUT_POOL) {
+    e->pool_bytes = cfg->pool_bytes ? cfg->pool_bytes : (uint64_t)cfg->max_conns * cfg->ring_bytes_per_conn;
+    e->pool_bytes = e->pool_bytes / PCDN_RECORD_ALIGN * PCDN_RECORD_ALIGN;
+    if (e->pool_bytes < 4096 || e->pool_bytes / PCDN_RECORD_ALIGN >= 0xFFFFFFFFull) {
+      delete e;
+      return fail(PCDN_EINVAL, "pool_bytes must be between 4 KiB and 128 GiB");
+    }
+  }
   e->tables.reset(new HostTables(g));
   e->conns.reset(new Connections(*e->tables, e->identity.c_str()));
   if (!host_only) {
@@ -1406,14 +1440,22 @@ void fill_result(pcdn_engine* e, const Slot& s, const Shard& sh, const ShardSlot
   const uint32_t cap = e->geo.shard_max_conns;
   out->batch_id = batch_id;
   out->n_msgs = s.n_msgs;
-  out->n_spans = std::min<uint32_t>(bs.n_spans, 2 * cap);
-  out->spans = reinterpret_cast<const pcdn_span*>(ss.h_spans);
-  out->n_deliveries = bs.n_deliveries;
-  out->bytes_out = bs.bytes_out;
-  out->n_overflow = std::min<uint32_t>(bs.n_overflow, cap);
+  // a batch the device refused (scatter-list capacity, output pool) wrote nothing: its provisional
+  // counters (the offsets pass counts before the pool says no) are not deliveries
+  const bool refused = bs.status != 0;
+  out->n_spans = refused ? 0 : std::min<uint32_t>(bs.n_spans, 2 * cap);
+  out->spans = sh.dev.span_runs ? nullptr : reinterpret_cast<const pcdn_span*>(ss.h_spans);
+  out->runs = sh.dev.span_runs ? reinterpret_cast<const pcdn_span_run*>(ss.h_spans) : nullptr;
+  out->n_runs = (sh.dev.span_runs && !refused) ? std::min<uint32_t>(bs.n_runs, 2 * e->geo.shard_N) : 0;
+
+  out->n_deliveries = refused ? 0 : bs.n_deliveries;
+  out->bytes_out = refused ? 0 : bs.bytes_out;
+  out->n_overflow = refused ? 0 : std::min<uint32_t>(bs.n_overflow, cap);
   out->overflow_conns = ss.h_overflow;
   out->n_direct_dropped = bs.n_direct_dropped;
-  out->status = bs.status ? (uint32_t)(-PCDN_E2BIG) : 0;
+  // device status: 1 = scatter list capacity, 3 = larger than the whole output pool (E2BIG); 2 = no room in the pool right now (EAGAIN)
+  out->status = bs.status == 0 ? 0 : (bs.status == 2 ? (uint32_t)(-PCDN_EAGAIN) : (uint32_t)(-PCDN_E2BIG));
+  out->pool_base = sh.dev.pool ? bs.pool_base : 0;
   out->msg_status = s.devparse ? ss.h_msg_status : nullptr;
   out->n_msg_errors = ss.n_msg_errors;
   out->reserved = sh.gindex;
@@ -1458,9 +1500,10 @@ int pcdn_detail::poll_one(pcdn_engine* e, uint64_t batch_id, uint32_t li, int bl
     ShardSlot& ss = sh.slots[si];
     devparse = e->slots[si].devparse;
     if (!mapped && !ss.polled) {
-      nsp = std::min<uint32_t>(ss.h_early->n_spans, 2 * e->geo.shard_max_conns);
+      const bool runs = sh.dev.span_runs != 0;
+      nsp = std::min<uint32_t>(runs ? ss.h_early->n_runs : ss.h_early->n_spans, 2 * e->geo.shard_N);
       nov = std::min<uint32_t>(ss.h_early->n_overflow, e->geo.shard_max_conns);
-      if (nsp) CUDA_TRY(cudaMemcpyAsync(ss.h_spans, ss.w.spans, (size_t)nsp * sizeof(Span), cudaMemcpyDeviceToHost, sh.copy_stream));
+      if (nsp) CUDA_TRY(cudaMemcpyAsync(ss.h_spans, ss.w.spans, (size_t)nsp * (runs ? sizeof(SpanRun) : sizeof(Span)), cudaMemcpyDeviceToHost, sh.copy_stream));
       if (nov) CUDA_TRY(cudaMemcpyAsync(ss.h_overflow, ss.w.overflow, (size_t)nov * 4, cudaMemcpyDeviceToHost, sh.copy_stream));
     }
   }
@@ -1477,8 +1520,10 @@ int pcdn_detail::poll_one(pcdn_engine* e, uint64_t batch_id, uint32_t li, int bl
     if (devparse) { ss.n_msg_errors = 0; for (uint32_t i = 0; i < ss.in.n_msgs; i++) ss.n_msg_errors += ss.h_msg_status[i] != 0; }
     const BatchStats& bs = *ss.h_stats;
     ss.polled = true;
-    e->stats.deliveries += bs.n_deliveries;
-    e->stats.bytes_out += bs.bytes_out;
+    if (!bs.status) {
+      e->stats.deliveries += bs.n_deliveries;
+      e->stats.bytes_out += bs.bytes_out;
+    }
     if (ss.timed && li == 0) {  // stage times of the first local shard (shards run the same pipeline side by side)
       float t[4] = {0, 0, 0, 0};
       for (int i = 0; i < 3; i++) cudaEventElapsedTime(&t[i], ss.ev[i], ss.ev[i + 1]);
@@ -1524,19 +1569,29 @@ int pcdn_poll(pcdn_engine* e, uint64_t batch_id, pcdn_batch_result* out, int blo
   Slot& s = e->slots[si];
   if (out) {
     // summed counters + the shards' span tables concatenated (ascending shard = ascending id range)
-    s.merged_spans.clear(); s.merged_overflow.clear();
+    s.merged_spans.clear(); s.merged_overflow.clear(); s.merged_runs.clear();
     pcdn_batch_result tot{};
     for (uint32_t li = 0; li < nl; li++) {
       pcdn_batch_result r{};
       fill_result(e, s, e->shards[li], e->shards[li].slots[si], batch_id, &r);
-      s.merged_spans.insert(s.merged_spans.end(), r.spans, r.spans + r.n_spans);
+      // (output pool: every shard's offsets are relative to ITS region — the merged view carries absolute unit offsets)
+      const size_t s0 = s.merged_spans.size(), r0 = s.merged_runs.size();
+      if (r.spans) s.merged_spans.insert(s.merged_spans.end(), r.spans, r.spans + r.n_spans);
+      if (r.runs) s.merged_runs.insert(s.merged_runs.end(), r.runs, r.runs + r.n_runs);
+      if (r.pool_base) {
+        for (size_t i = s0; i < s.merged_spans.size(); i++) s.merged_spans[i].ring_off += r.pool_base;
+        for (size_t i = r0; i < s.merged_runs.size(); i++) s.merged_runs[i].ring_off += r.pool_base;
+      }
+      tot.n_spans += r.n_spans;
       s.merged_overflow.insert(s.merged_overflow.end(), r.overflow_conns, r.overflow_conns + r.n_overflow);
       tot.n_deliveries += r.n_deliveries; tot.bytes_out += r.bytes_out; tot.n_direct_dropped += r.n_direct_dropped;
-      tot.status |= r.status;
+      if (r.status == (uint32_t)(-PCDN_EAGAIN) || (r.status && !tot.status)) tot.status = r.status;   // "retry" wins over "too big"
       if (li == 0) { tot.msg_status = r.msg_status; tot.n_msg_errors = r.n_msg_errors; }  // identical on every shard
     }
     tot.batch_id = batch_id; tot.n_msgs = s.n_msgs;
-    tot.n_spans = (uint32_t)s.merged_spans.size(); tot.spans = s.merged_spans.data();
+    tot.spans = s.merged_runs.empty() && !(e->cfg.flags & PCDN_FLAG_SPAN_RUNS) ? s.merged_spans.data() : nullptr;
+    tot.runs = (e->cfg.flags & PCDN_FLAG_SPAN_RUNS) ? s.merged_runs.data() : nullptr;
+    tot.n_runs = (uint32_t)s.merged_runs.size();
     tot.n_overflow = (uint32_t)s.merged_overflow.size(); tot.overflow_conns = s.merged_overflow.data();
     *out = tot;
   }
@@ -1551,17 +1606,52 @@ int pcdn_read(pcdn_engine* e, pcdn_conn conn, uint32_t ring_off, uint32_t len, v
   const uint32_t gs = conn / e->geo.shard_N, local = conn % e->geo.shard_N;
   if (gs < e->first_shard || gs >= e->first_shard + e->shards.size())
     return fail(PCDN_ENOENT, "connection lives on a shard of another process");
-  if (local >= e->geo.shard_max_conns || (uint64_t)ring_off + len > e->cfg.ring_bytes_per_conn)
-    return fail(PCDN_EINVAL, "read outside the connection's ring");
   Shard& sh = e->shards[gs - e->first_shard];
+  size_t at;
+  if (sh.dev.pool) {  // ring_off = absolute 32-byte unit inside the shard's output pool (pool_base + span offset)
+    at = (size_t)ring_off * PCDN_RECORD_ALIGN;
+    if (local >= e->geo.shard_max_conns || at + len > e->pool_bytes) return fail(PCDN_EINVAL, "read outside the output pool");
+  } else {
+    if (local >= e->geo.shard_max_conns || (uint64_t)ring_off + len > e->cfg.ring_bytes_per_conn)
+      return fail(PCDN_EINVAL, "read outside the connection's ring");
+    at = (size_t)local * e->cfg.ring_bytes_per_conn + ring_off;
+  }
   if (sh.h_rings) {
-    std::memcpy(dst, sh.h_rings + (size_t)local * e->cfg.ring_bytes_per_conn + ring_off, len);
+    std::memcpy(dst, sh.h_rings + at, len);
     return 0;
   }
   DeviceGuard dg(sh.device);
-  CUDA_TRY(cudaMemcpyAsync(dst, sh.dev.rings + (size_t)local * e->cfg.ring_bytes_per_conn + ring_off, len,
+  CUDA_TRY(cudaMemcpyAsync(dst, sh.dev.rings + at, len,
                            cudaMemcpyDeviceToHost, sh.copy_stream));
   CUDA_TRY(cudaStreamSynchronize(sh.copy_stream));
+  return 0;
+  GUARD_END
+}
+
+int pcdn_retry_batch(pcdn_engine* e, uint64_t batch_id) {
+  GUARD_BEGIN
+  LOCK;
+  if (!e->has_device) return fail(PCDN_ENODEV, "host-only engine");
+  if (!(e->cfg.flags & PCDN_FLAG_OUTPUT_POOL)) return fail(PCDN_EINVAL, "only batches of an output-pool engine can be refused for space");
+  const int si = find_slot_index(e, batch_id);
+  if (si < 0) return fail(PCDN_ENOENT, "unknown batch id");
+  if (e->inflight.empty() || e->inflight.front() != batch_id)
+    return fail(PCDN_EINVAL, "only the oldest unreleased batch can be retried (release the older ones first)");
+  Slot& s = e->slots[si];
+  int rc = flush_journal(e);
+  if (rc) return rc;
+  uint32_t n = 0;
+  for (Shard& sh : e->shards) {
+    ShardSlot& ss = sh.slots[si];
+    {
+      DeviceGuard dg(sh.device);
+      CUDA_TRY(cudaEventSynchronize(ss.ev_done));
+    }
+    if (ss.h_stats->status != 2) continue;   // this shard packed its share (or refused it for good): leave it alone
+    if ((rc = launch_shard_pipeline(e, sh, (uint32_t)si, s.device_input ? s.n_msgs - ss.in.n_bcast : s.n_direct, s.devparse, false, true))) return rc;
+    n++;
+  }
+  if (!n) return fail(PCDN_EINVAL, "the batch was not refused for space");
   return 0;
   GUARD_END
 }
@@ -1629,7 +1719,7 @@ int pcdn_shard_info(pcdn_engine* e, uint32_t local_shard, pcdn_shard_desc* out) 
   if (!out) return fail(PCDN_EINVAL, "null argument");
   std::memset(out, 0, sizeof(*out));
   out->shard_stride = e->geo.shard_N;
-  out->ring_bytes = e->cfg.ring_bytes_per_conn;
+  out->ring_bytes = (e->cfg.flags & PCDN_FLAG_OUTPUT_POOL) ? e->pool_bytes : e->cfg.ring_bytes_per_conn;
   if (!e->has_device) {  // host-only mirror: geometry only
     if (local_shard != 0) return fail(PCDN_EINVAL, "no such local shard");
     out->global_index = e->first_shard; out->device = -1; out->conn_base = e->first_shard * e->geo.shard_N;

@@ -146,6 +146,7 @@ struct Slot {
   bool counted = false;         // counters of this batch have been added to the engine stats
   // merged view of a sharded batch for pcdn_poll (host copy of the shards' span tables)
   std::vector<pcdn_span> merged_spans;
+  std::vector<pcdn_span_run> merged_runs;
   std::vector<pcdn_conn> merged_overflow;
 };
 
@@ -181,6 +182,7 @@ struct pcdn_engine {
   uint64_t next_batch_id = 1;
   std::vector<uint64_t> inflight;  // submit order
   size_t desc_cap = 0, topics_cap = 0, arena_cap = 0;
+  uint64_t pool_bytes = 0;        // PCDN_FLAG_OUTPUT_POOL: bytes of the output pool per shard
   std::vector<UpdSlot> h_slot; std::vector<uint32_t> h_kslot; std::vector<uint8_t> h_kbytes;  // journal parts common to all shards
   bool timing = false;
   pcdn_message_hook hook[2] = {nullptr, nullptr};  // [origin]: MessageHookDef of user / broker connections

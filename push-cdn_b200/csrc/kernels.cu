@@ -595,18 +595,77 @@ __device__ __forceinline__ uint32_t alloc_record(ConnCursor& k, uint32_t u, uint
 // (body shared by k_offsets — 256-thread CTAs, any N — and the fused small-engine control kernel —
 //  eight 1024-thread CTAs of one cluster, N = 8192; NT = threads per CTA, c = this thread's connection)
 // SPARSE_BOUNDS: the fused small-engine kernel's direct segments (rank-sorted, bounds valid iff stamped)
+// Pool mode (DevState::pool): the CTAs of the offsets pass chain their unit totals in connection order
+// with a decoupled look-back (one 64-bit word per CTA: batch stamp | flag | value, so nothing is
+// cleared between batches).  Called by warp 0 of the CTA; returns the units of all CTAs before `vb`.
+__device__ __forceinline__ uint32_t pool_lookback(const Work& w, uint32_t vb, uint32_t ctot) {
+  const uint32_t lane = lane_id();
+  volatile unsigned long long* st = w.lb_state;
+  const unsigned long long tag = (unsigned long long)w.stamp << 34;
+  auto pack = [&](uint32_t flag, uint32_t v) { return tag | ((unsigned long long)flag << 32) | v; };
+  unsigned long long prefix64 = 0;
+  if (vb > 0) {
+    if (lane == 0) st[vb] = pack(1u, ctot);  // AGGREGATE: this CTA's own total
+    int j = (int)vb - 1;
+    for (;;) {
+      const int idx = j - (int)lane;
+      unsigned long long x = 0;
+      if (idx >= 0) { do { x = st[idx]; } while ((x >> 34) != (tag >> 34)); }   // wait until that CTA has published this batch
+      const uint32_t flag = idx >= 0 ? (uint32_t)(x >> 32) & 3u : 2u;             // before CTA 0: inclusive prefix 0
+      const uint32_t val = idx >= 0 ? (uint32_t)x : 0u;
+      const uint32_t pm = __ballot_sync(0xffffffffu, flag == 2u);
+      const int first = pm ? __ffs(pm) - 1 : 32;                                  // nearest predecessor with an inclusive prefix
+      const uint32_t v = (int)lane <= first ? val : 0u;
+      // (32 values of up to 2^32 - 1: summed in two halves; a batch of more than 2^32 units saturates,
+      //  which pool_allocate turns into "larger than the pool")
+      const unsigned long long take = ((unsigned long long)__reduce_add_sync(0xffffffffu, v >> 16) << 16) + __reduce_add_sync(0xffffffffu, v & 0xFFFFu);
+      prefix64 += take;
+      if (pm) break;
+      j -= 32;
+    }
+  }
+  const uint32_t prefix = (uint32_t)(prefix64 > 0xFFFFFFFFull ? 0xFFFFFFFFull : prefix64);
+  const unsigned long long incl = prefix64 + ctot;
+  if (lane == 0) { __threadfence(); st[vb] = pack(2u, incl > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)incl); }  // PREFIX: inclusive
+  return prefix;
+}
+// the CTA that holds the last connections knows the batch total: it takes the region out of the pool
+__device__ __forceinline__ void pool_allocate(const DevState& s, const Work& w, unsigned long long total64) {
+  PoolState* p = s.pool_state;
+  BatchStats* bs = w.stats;
+  if (w.pool_unblock) p->blocked = 0;
+  if (total64 > s.pool_units) { bs->status = 3; return; }   // larger than the whole pool: can never fit (E2BIG)
+  const uint32_t total = (uint32_t)total64;
+  if (p->blocked) { bs->status = 2; return; }                // an older batch is waiting for space: keep the order
+  if (p->used == 0) { p->head = 0; p->tail = 0; }
+  uint32_t base = p->head, skip = 0;
+  bool ok;
+  if (p->head >= p->tail) {      // free: [head, cap) and [0, tail)
+    if ((unsigned long long)p->head + total <= s.pool_units) ok = true;
+    else if (total <= p->tail && p->used) { skip = s.pool_units - p->head; base = 0; ok = true; }
+    else ok = false;
+    if (p->used && p->head == p->tail) ok = false;   // completely full
+  } else {
+    ok = p->head + total <= p->tail;
+  }
+  if (!ok) { bs->status = 2; p->blocked = 1; return; }
+  p->head = base + total;
+  p->used += total + skip;
+  bs->pool_base = base; bs->pool_units = total; bs->pool_skip = skip;
+}
+
 template <bool HAS_DIRECT, int NT, bool SPARSE_BOUNDS>
 __device__ __forceinline__ void offsets_body(const DevState& s, const BatchIn& b, const Work& w, uint32_t max_conns,
-                                             uint32_t c) {
+                                             uint32_t c, uint32_t vb, uint32_t nvb) {
   constexpr int NW = NT / 32;
   __shared__ uint32_t sm[NW + 1];
   __shared__ unsigned long long red[2][NW];
   __shared__ uint32_t span_base;
   if (w.stats->status) return;  // batch rejected (E2BIG): leave all cursors untouched (uniform over the grid)
   const uint32_t wd = c >> 5, lane = c & 31, lt = (1u << lane) - 1u;
-  const uint32_t R = s.ring_units;
+  const uint32_t R = s.pool ? 0x7FFFFFFFu : s.ring_units;   // pool mode: a connection's region just grows
   ConnCursor k;
-  k.pt = s.ptail[c]; k.us = s.used[c]; k.bu = 0;
+  k.pt = s.pool ? 0u : s.ptail[c]; k.us = s.pool ? 0u : s.used[c]; k.bu = 0;
   k.s1_off = 0; k.s1_units = 0; k.s1_rec = 0; k.s2_units = 0; k.s2_rec = 0; k.ovf = 0; k.in2 = 0; k.bytes = 0;
   uint32_t dp = 0, de = 0;
   if (HAS_DIRECT) {
@@ -678,29 +737,84 @@ __device__ __forceinline__ void offsets_body(const DevState& s, const BatchIn& b
   }
   if (HAS_DIRECT) while (dp < de) { emit_direct(dmsg[dp]); dp++; }
 
-  s.ptail[c] = k.pt;
-  s.used[c] = k.us;
+  if (s.pool) {
+    // connection-order prefix of the units: inside the CTA by a scan, across CTAs by the look-back
+    __shared__ uint32_t cta_prefix;
+    uint32_t ctot;
+    const uint32_t cex = cta_excl_scan<NW>(k.bu, &ctot, sm);
+    if (threadIdx.x < 32) {
+      const uint32_t pre = pool_lookback(w, vb, ctot);
+      if (threadIdx.x == 0) {
+        cta_prefix = pre;
+        if (vb == nvb - 1) pool_allocate(s, w, (unsigned long long)pre + ctot);
+      }
+    }
+    __syncthreads();
+    k.s1_off = cta_prefix + cex;   // relative to the batch's region (BatchStats::pool_base)
+    w.cbase[c] = k.s1_off;
+  } else {
+    s.ptail[c] = k.pt;
+    s.used[c] = k.us;
+  }
   w.batch_units[c] = k.bu;
 
   // spans: one per contiguous run (two when the ring wrapped inside the batch)
   const uint32_t nsp = (k.s1_rec ? 1u : 0u) + (k.s2_rec ? 1u : 0u);
-  uint32_t tot, ex = cta_excl_scan<NW>(nsp, &tot, sm);
-  if (threadIdx.x == 0) span_base = tot ? atomicAdd(&w.stats->n_spans, tot) : 0;
+  uint32_t tot, ex;
+  uint32_t run_len = 1, my_runs = nsp, nsp_warp = 0;
+  if (s.span_runs) {
+    // Run-length form: a connection CONTINUES its left neighbour's run when both own exactly one span
+    // with the same (offset, length, records) — the normal case of a dense broadcast batch, where
+    // every connection of the CTA receives the same records at the same ring position.  Runs never
+    // cross a CTA (<= NT connections per run).
+    __shared__ uint32_t r_off[NT], r_len[NT], r_rec[NT], r_brk[NT + 1];
+    const uint32_t t = threadIdx.x;
+    r_off[t] = k.s1_off; r_len[t] = k.s1_units; r_rec[t] = nsp == 1 ? k.s1_rec : 0u;  // 0 = "not exactly one span"
+    __syncthreads();
+    const bool cont = t > 0 && nsp == 1 && r_rec[t - 1] == k.s1_rec && r_len[t - 1] == k.s1_units &&
+                      (s.pool ? r_off[t - 1] + r_len[t - 1] == k.s1_off : r_off[t - 1] == k.s1_off);
+    const uint32_t head = (nsp > 0 && !cont) ? 1u : 0u;
+    my_runs = head ? nsp : 0u;
+    // ONE scan carries both numbers (each <= 2 * NT < 65536): low half = run slots before this thread,
+    // high half = threads before it that do NOT continue a run.  A run ends at the next such thread,
+    // so its length is a subtraction — no counters (a dense batch would hit one counter 255 times).
+    uint32_t ptot;
+    const uint32_t pex = cta_excl_scan<NW>(my_runs | (cont ? 0u : 1u << 16), &ptot, sm);
+    ex = pex & 0xFFFFu; tot = ptot & 0xFFFFu;
+    const uint32_t brk = pex >> 16;                 // rank of this thread among the run breakers
+    if (!cont) r_brk[brk] = t;
+    if (t == 0) r_brk[ptot >> 16] = NT;             // sentinel after the last breaker
+    __syncthreads();
+    if (head) run_len = r_brk[brk + 1] - t;         // followers sit between this breaker and the next
+    if (threadIdx.x == 0) span_base = tot ? atomicAdd(&w.stats->n_runs, tot) : 0;
+    nsp_warp = __reduce_add_sync(0xffffffffu, nsp);                    // n_spans keeps counting expanded spans (added per CTA below)
+  } else {
+    ex = cta_excl_scan<NW>(nsp, &tot, sm);
+    if (threadIdx.x == 0) span_base = tot ? atomicAdd(&w.stats->n_spans, tot) : 0;
+  }
   // block reduction of deliveries / bytes
   // (redux.sync on 32-bit halves: a warp's record count fits 32 bits, its byte count may not)
   const unsigned long long nrec = __reduce_add_sync(0xffffffffu, k.s1_rec + k.s2_rec);
   const unsigned long long by = (unsigned long long)__reduce_add_sync(0xffffffffu, k.bytes & 0xFFFFu) +
                                 ((unsigned long long)__reduce_add_sync(0xffffffffu, k.bytes >> 16) << 16);
-  if (lane == 0) { red[0][threadIdx.x >> 5] = nrec; red[1][threadIdx.x >> 5] = by; }
+  if (lane == 0) { red[0][threadIdx.x >> 5] = nrec | ((unsigned long long)nsp_warp << 48); red[1][threadIdx.x >> 5] = by; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned long long a = 0, bb = 0;
-    for (int i = 0; i < NW; i++) { a += red[0][i]; bb += red[1][i]; }
+    unsigned long long a = 0, bb = 0, sp = 0;
+    for (int i = 0; i < NW; i++) { a += red[0][i] & 0xFFFFFFFFFFFFull; sp += red[0][i] >> 48; bb += red[1][i]; }
     if (a) { atomicAdd(&w.stats->n_deliveries, a); atomicAdd(&w.stats->bytes_out, bb); }
+    if (sp) atomicAdd(&w.stats->n_spans, (uint32_t)sp);
   }
-  if (nsp) {
+  if (s.span_runs) {
+    if (my_runs) {
+      SpanRun* runs = reinterpret_cast<SpanRun*>(w.spans);
+      uint32_t at = span_base + ex;
+      if (k.s1_rec) runs[at++] = SpanRun{s.conn_base + c, run_len, s.pool ? k.s1_off : k.s1_off * kUnit, k.s1_units * kUnit, k.s1_rec, s.pool ? k.s1_units : 0u};
+      if (k.s2_rec) runs[at] = SpanRun{s.conn_base + c, 1, 0, k.s2_units * kUnit, k.s2_rec, 0};
+    }
+  } else if (nsp) {
     uint32_t at = span_base + ex;
-    if (k.s1_rec) w.spans[at++] = Span{s.conn_base + c, k.s1_off * kUnit, k.s1_units * kUnit, k.s1_rec};
+    if (k.s1_rec) w.spans[at++] = Span{s.conn_base + c, s.pool ? k.s1_off : k.s1_off * kUnit, k.s1_units * kUnit, k.s1_rec};
     if (k.s2_rec) w.spans[at] = Span{s.conn_base + c, 0, k.s2_units * kUnit, k.s2_rec};
   }
   if (k.ovf) {
@@ -710,7 +824,19 @@ __device__ __forceinline__ void offsets_body(const DevState& s, const BatchIn& b
 }
 template <bool HAS_DIRECT>
 __global__ void __launch_bounds__(256) k_offsets(DevState s, BatchIn b, Work w, uint32_t max_conns) {
-  offsets_body<HAS_DIRECT, 256, false>(s, b, w, max_conns, blockIdx.x * 256 + threadIdx.x);  // N is a multiple of 8192
+  // Pool mode chains the CTAs in connection order: a CTA takes its position from a ticket, so every
+  // CTA it may wait for in the look-back has already started (blockIdx order is not a promise).
+  __shared__ uint32_t vb_s;
+  uint32_t vb = blockIdx.x;
+  if (s.pool) {
+    if (threadIdx.x == 0) {
+      vb_s = atomicAdd(w.lb_ticket, 1u);
+      if (vb_s == gridDim.x - 1) *w.lb_ticket = 0;   // the last ticket: ready for the next batch
+    }
+    __syncthreads();
+    vb = vb_s;
+  }
+  offsets_body<HAS_DIRECT, 256, false>(s, b, w, max_conns, vb * 256 + threadIdx.x, vb, gridDim.x);  // N is a multiple of 8192
 }
 void launch_offsets(const DevState& s, const Work& w, const BatchIn& b, bool has_direct, cudaStream_t st) {
   if (has_direct) PCDN_COUNT_LAUNCH, k_offsets<true><<<s.N / 256, 256, 0, st>>>(s, b, w, s.N);
@@ -827,7 +953,11 @@ k_ctrl_small(DevState s, BatchIn b, Work w, int zero_stats, BatchStats* publish)
   cluster_sync_all();
 
   // ---- offsets: thread = connection (one pass per 8192 connections)
-  for (uint32_t c0 = 0; c0 < s.N; c0 += 8192) offsets_body<HAS_DIRECT, 1024, true>(s, b, w, s.N, c0 + rank * 1024 + tid);
+  // (pool mode: the CTA's position in connection order is pass * 8 + rank; the eight CTAs of the
+  //  cluster are co-resident and earlier passes are complete, so the look-back never waits on a CTA
+  //  that has not started)
+  for (uint32_t c0 = 0; c0 < s.N; c0 += 8192)
+    offsets_body<HAS_DIRECT, 1024, true>(s, b, w, s.N, c0 + rank * 1024 + tid, c0 / 1024 + rank, s.N / 1024);
 
   // ---- final counters straight into the host's (mapped, pinned) result block
   if (publish) {
@@ -840,6 +970,12 @@ void launch_ctrl_small(const DevState& s, const Work& w, const BatchIn& b, bool 
                        BatchStats* publish, cudaStream_t st) {
   if (has_direct) PCDN_COUNT_LAUNCH, k_ctrl_small<true><<<8, 1024, 0, st>>>(s, b, w, zero_stats ? 1 : 0, publish);
   else PCDN_COUNT_LAUNCH, k_ctrl_small<false><<<8, 1024, 0, st>>>(s, b, w, zero_stats ? 1 : 0, publish);
+}
+
+// where a record goes: `off` units into the connection's own ring, or (pool mode) into the
+// connection's region of this batch's slice of the output pool
+__device__ __forceinline__ uint8_t* conn_out(const DevState& s, const Work& w, uint32_t conn, uint32_t pool_base) {
+  return s.pool ? s.rings + ((size_t)pool_base + w.cbase[conn]) * kUnit : s.rings + (size_t)conn * s.ring_bytes;
 }
 
 // =============================================================================== K2a pack (fat)
@@ -857,6 +993,7 @@ __device__ __forceinline__ void pack_fat_phase(const DevState& s, const BatchIn&
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t ntiles = w.stats->n_fat_tiles;
   if (ntiles == 0) return;
+  const uint32_t pool_base = w.stats->pool_base;
   uint32_t phase = 0;
   uint32_t staged_m = 0xFFFFFFFFu, staged_k = 0xFFFFFFFFu;  // meaningful in thread 0 only
 
@@ -908,7 +1045,7 @@ __device__ __forceinline__ void pack_fat_phase(const DevState& s, const BatchIn&
       for (uint32_t r = r0 + tid; r < r1; r += 256) {
         const uint2 ent = E[r];
         if (ent.y != kOffInvalid)
-          bulk_s2g(s.rings + (size_t)ent.x * s.ring_bytes + (size_t)ent.y * kUnit + chunk_off, buf, nbytes);
+          bulk_s2g(conn_out(s, w, ent.x, pool_base) + (size_t)ent.y * kUnit + chunk_off, buf, nbytes);
       }
       bulk_commit();
     } else if (nvec <= 128) {
@@ -925,7 +1062,7 @@ __device__ __forceinline__ void pack_fat_phase(const DevState& s, const BatchIn&
         for (uint32_t i = 0; i < cnt; i++) {
           const uint32_t conn = __shfl_sync(0xffffffffu, ent.x, i), off = __shfl_sync(0xffffffffu, ent.y, i);
           if (off == kOffInvalid) continue;
-          uint4* dst = reinterpret_cast<uint4*>(s.rings + (size_t)conn * s.ring_bytes + (size_t)off * kUnit + chunk_off);
+          uint4* dst = reinterpret_cast<uint4*>(conn_out(s, w, conn, pool_base) + (size_t)off * kUnit + chunk_off);
           if (lane < nvec) st_stream16(dst + lane, v0);
           if (lane + 32 < nvec) st_stream16(dst + lane + 32, v1);
           if (lane + 64 < nvec) st_stream16(dst + lane + 64, v2);
@@ -940,7 +1077,7 @@ __device__ __forceinline__ void pack_fat_phase(const DevState& s, const BatchIn&
         for (uint32_t i = 0; i < cnt; i++) {
           const uint32_t conn = __shfl_sync(0xffffffffu, ent.x, i), off = __shfl_sync(0xffffffffu, ent.y, i);
           if (off == kOffInvalid) continue;
-          uint4* dst = reinterpret_cast<uint4*>(s.rings + (size_t)conn * s.ring_bytes + (size_t)off * kUnit + chunk_off);
+          uint4* dst = reinterpret_cast<uint4*>(conn_out(s, w, conn, pool_base) + (size_t)off * kUnit + chunk_off);
           for (uint32_t v = lane; v < nvec; v += 32) st_stream16(dst + v, sb[v]);
         }
       }
@@ -972,6 +1109,7 @@ __device__ __forceinline__ void pack_cm_phase(const DevState& s, const BatchIn& 
   if (w.stats->status) return;
   const uint32_t ncm = w.stats->n_cm;
   if (ncm == 0) return;
+  const uint32_t pool_base = w.stats->pool_base;
   const uint32_t ngroups = (ncm + kCmGroup - 1) / kCmGroup;
   const uint32_t tpg = s.W / kCmTileWords;  // tiles per group (W is a multiple of 256)
   const uint32_t ntiles = ngroups * tpg;
@@ -1043,7 +1181,7 @@ __device__ __forceinline__ void pack_cm_phase(const DevState& s, const BatchIn& 
       }
       if (VARIANT == 1) {
         // one lane = one connection: merge adjacent records into runs, one bulk store per run
-        uint8_t* ring = s.rings + (size_t)(wd * 32 + lane) * s.ring_bytes;
+        uint8_t* ring = conn_out(s, w, wd * 32 + lane, pool_base);
         uint32_t run_o = kOffInvalid, run_units = 0, run_s = 0;
 #pragma unroll
         for (int i = 0; i < (int)kCmGroup; i++) {
@@ -1061,7 +1199,7 @@ __device__ __forceinline__ void pack_cm_phase(const DevState& s, const BatchIn& 
         while (rem) {
           const int l = __ffs(rem) - 1;
           rem &= rem - 1;
-          uint8_t* ring = s.rings + (size_t)(wd * 32 + l) * s.ring_bytes;
+          uint8_t* ring = conn_out(s, w, wd * 32 + l, pool_base);
           uint32_t run_o = kOffInvalid, run_units = 0, run_s = 0;
 #pragma unroll
           for (int i = 0; i <= (int)kCmGroup; i++) {
@@ -1121,13 +1259,14 @@ __device__ __forceinline__ void copy_record(const uint4* __restrict__ src, uint4
 // Warp per scatter-list entry (broadcasts with < kFatMin recipients).
 __device__ __forceinline__ void pack_thin_phase(const DevState& s, const BatchIn& b, const Work& w) {
   const uint32_t n = w.stats->n_thin_entries;
+  const uint32_t pool_base = w.stats->pool_base;
   const uint32_t lane = lane_id();
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t e = gw; e < n; e += nw) {
     const uint4 ent = w.ethin[e];
     if (ent.y == kOffInvalid) continue;
     copy_record(reinterpret_cast<const uint4*>(b.arena + (size_t)ent.z * 16),
-                reinterpret_cast<uint4*>(s.rings + (size_t)ent.x * s.ring_bytes + (size_t)ent.y * kUnit), ent.w, lane);
+                reinterpret_cast<uint4*>(conn_out(s, w, ent.x, pool_base) + (size_t)ent.y * kUnit), ent.w, lane);
   }
 }
 // Direct messages: warp per MESSAGE — entry m of the direct list, the frame slot and the length are
@@ -1137,6 +1276,7 @@ __device__ __forceinline__ void pack_thin_phase(const DevState& s, const BatchIn
 // scattered sub-KB writes, not by load latency — profiles/r1_cfg_C4*.json)
 __device__ __forceinline__ void pack_direct_phase(const DevState& s, const BatchIn& b, const Work& w) {
   const uint32_t n = b.n_msgs;
+  const uint32_t pool_base = w.stats->pool_base;
   const uint32_t lane = lane_id();
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   // The three per-message words (list entry, slot, length) of the NEXT message are fetched while the
@@ -1151,7 +1291,7 @@ __device__ __forceinline__ void pack_direct_phase(const DevState& s, const Batch
     if (nx < n) { ent = w.edir[nx]; so = b.slot_off16[nx]; len = b.raw_len[nx]; }
     if (cur.y == kOffInvalid) continue;
     copy_record(reinterpret_cast<const uint4*>(b.arena + (size_t)cso * 16),
-                reinterpret_cast<uint4*>(s.rings + (size_t)cur.x * s.ring_bytes + (size_t)cur.y * kUnit), clen, lane);
+                reinterpret_cast<uint4*>(conn_out(s, w, cur.x, pool_base) + (size_t)cur.y * kUnit), clen, lane);
   }
 }
 
@@ -1190,14 +1330,16 @@ void launch_pack(const DevState& s, const Work& w, const BatchIn& b, uint32_t n_
   // A/B switches for profiling: bit 2 = st.global.cs.v4 stores instead of bulk stores; bit 1 = no
   // connection-major class (DevState::cm_enable, read by k_plan_a); bits 4-7 = log2 multiplier of
   // the 128 KB message-major tile (DevState::fat_tile_bytes); bits 8+ = CTAs per SM.
-  const uint32_t ctas_per_sm = (variant >> 8) ? (variant >> 8) : 3;
+  const uint32_t ctas_per_sm = ((variant >> 8) & 15u) ? ((variant >> 8) & 15u) : 3;
   const uint32_t grid = (uint32_t)n_sms * ctas_per_sm;
   const int do_direct = (n_direct && !direct_separate) ? 1 : 0;
   if (b.n_bcast || do_direct) {  // (a batch of nothing but many direct messages has no work for this kernel)
     if (variant & 4) PCDN_COUNT_LAUNCH, k_pack<0><<<grid, 256, 0, st>>>(s, b, w, do_direct);
     else PCDN_COUNT_LAUNCH, k_pack<1><<<grid, 256, 0, st>>>(s, b, w, do_direct);
   }
-  if (direct_separate) PCDN_COUNT_LAUNCH, k_pack_direct<<<(uint32_t)n_sms * 8, 256, 0, st>>>(s, b, w);
+  // (A/B: bits 12-15 = CTAs per SM of the separate direct pack, default 8 = full occupancy)
+  const uint32_t dctas = ((variant >> 12) & 15u) ? ((variant >> 12) & 15u) : 8u;
+  if (direct_separate) PCDN_COUNT_LAUNCH, k_pack_direct<<<(uint32_t)n_sms * dctas, 256, 0, st>>>(s, b, w);
 }
 
 // =============================================================================== release
@@ -1217,7 +1359,19 @@ __global__ void __launch_bounds__(256) k_release(DevState s, const uint32_t* __r
     }
   }
 }
+// pool mode: the region of the oldest batch goes back (batches are released in order)
+__global__ void k_pool_release(PoolState* p, const BatchStats* __restrict__ stats) {
+  if (stats->status) return;  // a refused batch holds nothing
+  p->used -= stats->pool_units + stats->pool_skip;
+  p->tail = stats->pool_base + stats->pool_units;
+  if (p->used == 0) { p->head = 0; p->tail = 0; }
+}
+__global__ void k_pool_init(PoolState* p) { p->head = 0; p->tail = 0; p->used = 0; p->blocked = 0; }
+void launch_pool_init(const DevState& s, cudaStream_t st) {
+  if (s.pool) PCDN_COUNT_LAUNCH, k_pool_init<<<1, 1, 0, st>>>(s.pool_state);
+}
 void launch_release(const DevState& s, const uint32_t* batch_units, const BatchStats* stats, cudaStream_t st) {
+  if (s.pool) { PCDN_COUNT_LAUNCH, k_pool_release<<<1, 1, 0, st>>>(s.pool_state, stats); return; }
   PCDN_COUNT_LAUNCH, k_release<<<(s.N / 4 + 255) / 256, 256, 0, st>>>(s, batch_units, stats);
 }
 

@@ -79,7 +79,16 @@ struct DevState {
   // bitmap / broker-mask words here are this shard's slice (local word index); the direct map and
   // owner_conn[] are replicated on every shard and name connections by GLOBAL id, so a direct
   // message resolves identically everywhere and is packed by the shard that owns the target.
+  // PCDN_FLAG_OUTPUT_POOL: instead of one fixed ring per connection, `rings` is ONE output pool of
+  // pool_units x 32 B shared by all connections of the shard.  Every batch gets a contiguous region,
+  // laid out connection by connection (a connection's records back to back, in batch order); the
+  // region is freed as a whole when the batch is released.  No connection can overflow; a batch
+  // that does not fit is refused as a whole (status 2) and retried after older ones are released.
+  uint32_t pool;
+  uint32_t pool_units;       // capacity of the pool in 32-byte units
+  struct PoolState* pool_state;
   uint32_t conn_base;
+  uint32_t span_runs;    // PCDN_FLAG_SPAN_RUNS: the span table is run-length encoded (SpanRun entries)
   uint32_t count_drops;  // 1 on exactly one shard of the broker (global shard 0): it counts the unroutable directs
   uint64_t ring_bytes;
   uint64_t seed;
@@ -113,10 +122,23 @@ struct BatchStats {
   uint32_t n_cm;            // messages on the connection-major path
   uint32_t cm_cursor;
   uint32_t n_hot;           // connections with more than kHotMin direct hits in this batch
+  uint32_t n_runs;          // run-length entries written to the span table (span_runs engines)
+  uint32_t pool_base;       // pool mode: first unit of this batch's region (span offsets are relative to it)
+  uint32_t pool_units;      // pool mode: units of the region
+  uint32_t pool_skip;       // pool mode: units skipped at the end of the pool to keep the region contiguous
   uint32_t reserved;
 };
 
+// ring buffer of batch regions inside the output pool (units of 32 B); batches are released in order
+struct PoolState { uint32_t head, tail, used, blocked; };
+
 struct Span { uint32_t conn, ring_off, len, n_records; };
+// n_conns consecutive connection ids that each own an identical span (same offset, length, records):
+// a dense broadcast batch is 1 run per 256 connections instead of one 16-byte span per connection
+// (off_stride: units added to ring_off per connection — 0 with per-connection rings, where every
+//  connection of the run has the records at the same offset of its own ring; len / 32 in pool mode,
+//  where the connections' regions follow each other)
+struct SpanRun { uint32_t conn0, n_conns, ring_off, len, n_records, off_stride; };
 
 // per-slot scratch
 struct Work {
@@ -159,9 +181,15 @@ struct Work {
   uint32_t* dend;        // [N+1]
   uint32_t* dstamp;      // [N+1]
   uint32_t stamp;        // per-slot batch counter (never 0)
+  // pool mode: connection c's region starts at pool_base + cbase[c]; the CTAs of k_offsets chain their
+  // totals with a decoupled look-back (lb_state: stamp | flag | value per CTA, no clearing)
+  uint32_t* cbase;       // [N]
+  unsigned long long* lb_state;  // [N / 256 + 1]
+  uint32_t* lb_ticket;   // [1] dispatch-order CTA numbers of k_offsets (zero between batches)
+  uint32_t pool_unblock; // this launch is the retry of the oldest refused batch: clear PoolState::blocked
   // outputs
   uint32_t* batch_units; // [N] units consumed by this batch per connection (for release)
-  Span* spans;           // [2*max_conns]
+  Span* spans;           // [2*N] spans, or (span_runs) [2*N] SpanRun entries in the same buffer (sized for the larger)
   uint32_t* overflow;    // [max_conns]
   int8_t* msg_status;    // [max_msgs] device-parse outcome per message
   BatchStats* stats;
@@ -186,6 +214,7 @@ void launch_ctrl_small(const DevState& s, const Work& w, const BatchIn& b, bool 
                        BatchStats* publish, cudaStream_t st);
 void launch_pack(const DevState& s, const Work& w, const BatchIn& b, uint32_t n_direct, uint32_t variant, int n_sms, cudaStream_t st);
 void launch_release(const DevState& s, const uint32_t* batch_units, const BatchStats* stats, cudaStream_t st);
+void launch_pool_init(const DevState& s, cudaStream_t st);
 unsigned long long kernel_launches();   // launches issued by this library in this process so far
 void count_kernel_launch();
 

@@ -136,7 +136,8 @@ def shard_cfg(pcdn, variant):
     return dict(devices=list(range(min(n, 4))), ingest=pcdn.INGEST_NCCL)
 
 
-@pytest.mark.parametrize("variant", [0, 4, 2, "staged", "host", "host-st", "shards-host", "shards-nccl"])
+@pytest.mark.parametrize("variant", [0, 4, 2, 8 + 65536, "staged", "runs", "runs-staged", "pool", "pool-st", "pool-staged-runs", "pool-host", "pool-shards",
+                                     "host", "host-st", "shards-host", "shards-nccl"])
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_random_mixed_batches(pcdn, seed, variant):
     """users + peer brokers, multi-topic broadcasts (fat and thin recipient sets), directs to local,
@@ -148,6 +149,23 @@ def test_random_mixed_batches(pcdn, seed, variant):
     rng = random.Random(seed)
     if variant == "staged":
         w = World(pcdn, flags=pcdn.FLAG_STAGED_SPANS, ring_bytes_per_conn=1 << 20)
+    elif variant.startswith("pool") if isinstance(variant, str) else False:
+        # PCDN_FLAG_OUTPUT_POOL: one shared output pool (1 GiB; a batch here delivers a few hundred MB)
+        # instead of per-connection rings
+        fl = pcdn.FLAG_OUTPUT_POOL
+        kw = {}
+        if variant == "pool-st":
+            kw["pack_variant"] = 4
+        if variant == "pool-staged-runs":
+            fl |= pcdn.FLAG_STAGED_SPANS | pcdn.FLAG_SPAN_RUNS
+        if variant == "pool-host":
+            fl |= pcdn.FLAG_HOST_RINGS
+        if variant == "pool-shards":
+            kw.update(shard_cfg(pcdn, "shards-host"), max_conns=1024)
+        w = World(pcdn, flags=fl, pool_bytes=1 << 30, **kw)
+    elif variant in ("runs", "runs-staged"):
+        # run-length span table (PCDN_FLAG_SPAN_RUNS): same streams, the table just arrives compressed
+        w = World(pcdn, flags=pcdn.FLAG_SPAN_RUNS | (pcdn.FLAG_STAGED_SPANS if variant == "runs-staged" else 0), ring_bytes_per_conn=1 << 20)
     elif variant in ("host", "host-st"):
         # egress hand-off mode: rings in mapped pinned host memory, frames read in place by the host
         # (TMA bulk stores / st.global.cs over PCIe)
@@ -157,6 +175,10 @@ def test_random_mixed_batches(pcdn, seed, variant):
     elif isinstance(variant, str):
         w = World(pcdn, ring_bytes_per_conn=1 << 20, max_conns=1024, **shard_cfg(pcdn, variant))
         assert w.e.num_shards()[0] >= 2
+    elif variant == 8 + 65536:
+        # the pack on its own stream (overlaps the next batch's control kernels), forced onto the
+        # large-engine path where that stream is used
+        w = World(pcdn, pack_variant=8, flags=pcdn.FLAG_STAGED_SPANS, ring_bytes_per_conn=1 << 20)
     else:
         w = World(pcdn, pack_variant=variant, ring_bytes_per_conn=1 << 20)
     keys = []
