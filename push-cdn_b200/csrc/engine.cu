@@ -155,6 +155,7 @@ int launch_shard_pipeline(pcdn_engine* e, Shard& sh, uint32_t si, uint32_t n_dir
   // without broadcasts and with few messages (at most one span per message).  Otherwise they are staged in HBM and copied
   // out with one DMA of the exact size while the pack runs.
   s.spans_mapped = dp && (sh.dev.N <= 8192 || (s.in.n_bcast == 0 && s.in.n_msgs <= 4096));
+  if (sh.dev.pool && !fused) s.spans_mapped = false;   // k_pool_finish patches the table: keep it in HBM until it is final
   s.w.spans = s.spans_mapped ? s.d_spans_map : s.d_spans_dev;
   s.w.overflow = s.spans_mapped ? s.d_ovf_map : s.d_ovf_dev;
   const bool zero_in_kernel = fused && !devparse;  // (k_parse counts into the batch counters before the fused kernel)
@@ -528,6 +529,7 @@ int init_shard(pcdn_engine* e, Shard& sh, int ndev, void* user_stream) {
   d.ring_bytes = c.ring_bytes_per_conn; d.ring_units = (uint32_t)(c.ring_bytes_per_conn / kUnit);
   d.cm_enable = (c.pack_variant & 2) ? 0 : 1;
   d.fat_tile_bytes = (128u << 10) << ((c.pack_variant >> 4) & 15u);  // A/B: bits 4-7 double the tile
+  d.fat_grab = 1u << ((c.pack_variant >> 16) & 7u);                   // A/B: bits 16-18 = log2 tiles per cursor update
   d.n_valid_topics = c.n_valid_topics;
   d.max_key_len = c.max_key_len;
   d.conn_base = sh.gindex * Ns;
@@ -608,9 +610,8 @@ int init_shard(pcdn_engine* e, Shard& sh, int ndev, void* user_stream) {
     if (d.pool) {
       DEV_ALLOC(w.cbase, Ns);
       DEV_ALLOC(w.lb_state, (size_t)Ns / 256 + 1);
-      DEV_ALLOC(w.lb_ticket, 1);
+      DEV_ALLOC(w.lb_tot, (size_t)Ns / 256 + 1);
       CUDA_TRY(cudaMemsetAsync(w.lb_state, 0, ((size_t)Ns / 256 + 1) * 8, sh.stream));
-      CUDA_TRY(cudaMemsetAsync(w.lb_ticket, 0, 4, sh.stream));
     }
     w.pool_unblock = 0;
     const size_t span_entries = (size_t)2 * Ns * (d.span_runs ? 3 : 2) / 2;  // SpanRun = 24 B, Span = 16 B

@@ -654,7 +654,11 @@ __device__ __forceinline__ void pool_allocate(const DevState& s, const Work& w, 
   bs->pool_base = base; bs->pool_units = total; bs->pool_skip = skip;
 }
 
-template <bool HAS_DIRECT, int NT, bool SPARSE_BOUNDS>
+// Pool mode, two ways to chain the CTAs' unit totals: LOOKBACK (the fused small-engine kernel: its CTAs
+// are co-resident, the chain is at most 64 long) or, in the regular kernel, CTA-local offsets + the
+// CTA total in lb_tot[], finished by k_pool_finish (one more launch instead of 4096 CTAs polling each
+// other: the look-back cost 40 us at 2^20 connections, the finish kernel 5).
+template <bool HAS_DIRECT, int NT, bool SPARSE_BOUNDS, bool LOOKBACK>
 __device__ __forceinline__ void offsets_body(const DevState& s, const BatchIn& b, const Work& w, uint32_t max_conns,
                                              uint32_t c, uint32_t vb, uint32_t nvb) {
   constexpr int NW = NT / 32;
@@ -742,12 +746,17 @@ __device__ __forceinline__ void offsets_body(const DevState& s, const BatchIn& b
     __shared__ uint32_t cta_prefix;
     uint32_t ctot;
     const uint32_t cex = cta_excl_scan<NW>(k.bu, &ctot, sm);
-    if (threadIdx.x < 32) {
-      const uint32_t pre = pool_lookback(w, vb, ctot);
-      if (threadIdx.x == 0) {
-        cta_prefix = pre;
-        if (vb == nvb - 1) pool_allocate(s, w, (unsigned long long)pre + ctot);
+    if (LOOKBACK) {
+      if (threadIdx.x < 32) {
+        const uint32_t pre = pool_lookback(w, vb, ctot);
+        if (threadIdx.x == 0) {
+          cta_prefix = pre;
+          if (vb == nvb - 1) pool_allocate(s, w, (unsigned long long)pre + ctot);
+        }
       }
+    } else if (threadIdx.x == 0) {
+      cta_prefix = 0;            // CTA-local: k_pool_finish adds the CTA's base to cbase[] and to the span table
+      w.lb_tot[vb] = ctot;
     }
     __syncthreads();
     k.s1_off = cta_prefix + cex;   // relative to the batch's region (BatchStats::pool_base)
@@ -824,23 +833,49 @@ __device__ __forceinline__ void offsets_body(const DevState& s, const BatchIn& b
 }
 template <bool HAS_DIRECT>
 __global__ void __launch_bounds__(256) k_offsets(DevState s, BatchIn b, Work w, uint32_t max_conns) {
-  // Pool mode chains the CTAs in connection order: a CTA takes its position from a ticket, so every
-  // CTA it may wait for in the look-back has already started (blockIdx order is not a promise).
-  __shared__ uint32_t vb_s;
-  uint32_t vb = blockIdx.x;
-  if (s.pool) {
-    if (threadIdx.x == 0) {
-      vb_s = atomicAdd(w.lb_ticket, 1u);
-      if (vb_s == gridDim.x - 1) *w.lb_ticket = 0;   // the last ticket: ready for the next batch
-    }
-    __syncthreads();
-    vb = vb_s;
-  }
-  offsets_body<HAS_DIRECT, 256, false>(s, b, w, max_conns, vb * 256 + threadIdx.x, vb, gridDim.x);  // N is a multiple of 8192
+  offsets_body<HAS_DIRECT, 256, false, false>(s, b, w, max_conns, blockIdx.x * 256 + threadIdx.x, blockIdx.x, gridDim.x);  // N is a multiple of 8192
 }
+// Pool mode, after k_offsets: every CTA scans the (at most a few thousand) CTA totals in shared memory
+// — redundantly, 16 KB of reads each, cheaper than a second dependent launch — then the grid adds each
+// connection's CTA base to cbase[] and to the span / run table (entries name their connection, hence
+// their CTA); CTA 0 takes the region out of the pool.
+__global__ void __launch_bounds__(1024) k_pool_finish(DevState s, Work w, uint32_t nblk) {
+  extern __shared__ uint32_t tb[];   // [nblk] exclusive CTA bases
+  __shared__ uint32_t sm[33];
+  __shared__ unsigned long long total_s;
+  if (w.stats->status) return;
+  unsigned long long carry = 0;
+  for (uint32_t b0 = 0; b0 < nblk; b0 += 1024) {
+    const uint32_t i = b0 + threadIdx.x;
+    const uint32_t v = i < nblk ? w.lb_tot[i] : 0;
+    uint32_t tot, ex = cta_excl_scan<32>(v, &tot, sm);
+    const unsigned long long at = carry + ex;
+    if (i < nblk) tb[i] = at > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)at;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) total_s = carry;
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) pool_allocate(s, w, total_s);
+  const uint32_t gt = blockIdx.x * 1024 + threadIdx.x, gn = gridDim.x * 1024;
+  for (uint32_t c = gt; c < s.N; c += gn) w.cbase[c] += tb[c >> 8];
+  if (s.span_runs) {
+    SpanRun* r = reinterpret_cast<SpanRun*>(w.spans);
+    const uint32_t n = w.stats->n_runs;
+    for (uint32_t i = gt; i < n; i += gn) r[i].ring_off += tb[(r[i].conn0 - s.conn_base) >> 8];
+  } else {
+    const uint32_t n = w.stats->n_spans;
+    for (uint32_t i = gt; i < n; i += gn) w.spans[i].ring_off += tb[(w.spans[i].conn - s.conn_base) >> 8];
+  }
+}
+
 void launch_offsets(const DevState& s, const Work& w, const BatchIn& b, bool has_direct, cudaStream_t st) {
   if (has_direct) PCDN_COUNT_LAUNCH, k_offsets<true><<<s.N / 256, 256, 0, st>>>(s, b, w, s.N);
   else PCDN_COUNT_LAUNCH, k_offsets<false><<<s.N / 256, 256, 0, st>>>(s, b, w, s.N);
+  if (s.pool) {
+    const uint32_t nblk = s.N / 256;
+    if (nblk * 4 > 48u * 1024) cudaFuncSetAttribute(k_pool_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(nblk * 4));  // > 3 M connections per shard
+    PCDN_COUNT_LAUNCH, k_pool_finish<<<std::min<uint32_t>(148u, (s.N + 8191) / 8192), 1024, nblk * 4, st>>>(s, w, nblk);
+  }
 }
 
 // =============================================================================== fused control (small engines)
@@ -957,7 +992,7 @@ k_ctrl_small(DevState s, BatchIn b, Work w, int zero_stats, BatchStats* publish)
   //  cluster are co-resident and earlier passes are complete, so the look-back never waits on a CTA
   //  that has not started)
   for (uint32_t c0 = 0; c0 < s.N; c0 += 8192)
-    offsets_body<HAS_DIRECT, 1024, true>(s, b, w, s.N, c0 + rank * 1024 + tid, c0 / 1024 + rank, s.N / 1024);
+    offsets_body<HAS_DIRECT, 1024, true, true>(s, b, w, s.N, c0 + rank * 1024 + tid, c0 / 1024 + rank, s.N / 1024);
 
   // ---- final counters straight into the host's (mapped, pinned) result block
   if (publish) {
@@ -997,9 +1032,12 @@ __device__ __forceinline__ void pack_fat_phase(const DevState& s, const BatchIn&
   uint32_t phase = 0;
   uint32_t staged_m = 0xFFFFFFFFu, staged_k = 0xFFFFFFFFu;  // meaningful in thread 0 only
 
+  uint32_t grab_next = 0, grab_left = 0;  // thread 0: consecutive tiles taken with one cursor update (s.fat_grab of them)
   for (;;) {
     if (tid == 0) {
-      const uint32_t t = atomicAdd(&w.stats->tile_cursor, 1u);
+      if (grab_left == 0) { grab_next = atomicAdd(&w.stats->tile_cursor, s.fat_grab); grab_left = s.fat_grab; }
+      const uint32_t t = grab_next++;
+      grab_left--;
       t_info[0] = t;
       if (t < ntiles) {
         uint32_t lo = 0, hi = b.n_msgs;  // largest m with tbase[m] <= t

@@ -72,6 +72,7 @@ struct DevState {
   uint32_t bucket_mask, key_stride;
   uint32_t ring_units;   // ring_bytes / 32
   uint32_t fat_tile_bytes;  // bytes of stores per message-major pack tile
+  uint32_t fat_grab;        // consecutive message-major tiles a CTA takes per cursor update (A/B knob; 1 = default)
   uint32_t cm_enable;    // connection-major pack class on (default) / off (A/B profiling)
   uint32_t n_valid_topics;  // Topic::prune validity bound (0 = all)
   uint32_t max_key_len;
@@ -184,8 +185,8 @@ struct Work {
   // pool mode: connection c's region starts at pool_base + cbase[c]; the CTAs of k_offsets chain their
   // totals with a decoupled look-back (lb_state: stamp | flag | value per CTA, no clearing)
   uint32_t* cbase;       // [N]
-  unsigned long long* lb_state;  // [N / 256 + 1]
-  uint32_t* lb_ticket;   // [1] dispatch-order CTA numbers of k_offsets (zero between batches)
+  unsigned long long* lb_state;  // [N / 256 + 1] look-back words (fused small-engine kernel)
+  uint32_t* lb_tot;      // [N / 256 + 1] units per k_offsets CTA (regular kernel; finished by k_pool_finish)
   uint32_t pool_unblock; // this launch is the retry of the oldest refused batch: clear PoolState::blocked
   // outputs
   uint32_t* batch_units; // [N] units consumed by this batch per connection (for release)

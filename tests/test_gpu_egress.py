@@ -46,11 +46,15 @@ def traffic(w, rng, keys, n):
             w.direct(k, orc.direct_frame(k, payload(rng, size)))
 
 
-@pytest.mark.parametrize("mode", ["hbm", "hbm-small-chunks", "host-rings", "shards-host"])
+@pytest.mark.parametrize("mode", ["hbm", "hbm-small-chunks", "host-rings", "shards-host", "pool", "pool-runs-host"])
 def test_drain_to_host_memory_matches_oracle(pcdn, mode):
     cfg = dict(max_conns=2048, ring_bytes_per_conn=1 << 18)
     if mode == "host-rings":
         cfg["flags"] = pcdn.FLAG_HOST_RINGS
+    if mode == "pool":        # shared output pool: spans are unit offsets relative to the batch's region
+        cfg.update(flags=pcdn.FLAG_OUTPUT_POOL, pool_bytes=512 << 20)
+    if mode == "pool-runs-host":
+        cfg.update(flags=pcdn.FLAG_OUTPUT_POOL | pcdn.FLAG_SPAN_RUNS | pcdn.FLAG_HOST_RINGS, pool_bytes=512 << 20)
     if mode == "shards-host":
         cfg.update(shard_cfg(pcdn, mode), max_conns=1024)
     w = World(pcdn, **cfg)
@@ -77,7 +81,7 @@ def test_drain_to_host_memory_matches_oracle(pcdn, mode):
     w.e.close()
 
 
-@pytest.mark.parametrize("mode", ["hbm", "host-rings", "shards-host"])
+@pytest.mark.parametrize("mode", ["hbm", "host-rings", "shards-host", "pool-runs"])
 def test_writer_to_file_descriptors(pcdn, mode):
     """>= 1 K sinks: every attached connection's memfd must hold exactly the oracle's stream for that
     connection over several batches; connections without a descriptor are counted, not written."""
@@ -86,6 +90,8 @@ def test_writer_to_file_descriptors(pcdn, mode):
         cfg["flags"] = pcdn.FLAG_HOST_RINGS
     if mode == "shards-host":
         cfg.update(shard_cfg(pcdn, mode), max_conns=1024)
+    if mode == "pool-runs":
+        cfg.update(flags=pcdn.FLAG_OUTPUT_POOL | pcdn.FLAG_SPAN_RUNS, pool_bytes=512 << 20)
     w = World(pcdn, **cfg)
     eg = pcdn.Egress(w.e, n_threads=8)
     rng = random.Random(8)

@@ -136,7 +136,7 @@ def shard_cfg(pcdn, variant):
     return dict(devices=list(range(min(n, 4))), ingest=pcdn.INGEST_NCCL)
 
 
-@pytest.mark.parametrize("variant", [0, 4, 2, 8 + 65536, "staged", "runs", "runs-staged", "pool", "pool-st", "pool-staged-runs", "pool-host", "pool-shards",
+@pytest.mark.parametrize("variant", [0, 4, 2, 8 + 65536, "staged", "runs", "runs-staged", "pool", "pool-st", "pool-staged-runs", "pool-host", "pool-shards", "pool-shards-nccl",
                                      "host", "host-st", "shards-host", "shards-nccl"])
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_random_mixed_batches(pcdn, seed, variant):
@@ -162,6 +162,9 @@ def test_random_mixed_batches(pcdn, seed, variant):
             fl |= pcdn.FLAG_HOST_RINGS
         if variant == "pool-shards":
             kw.update(shard_cfg(pcdn, "shards-host"), max_conns=1024)
+        if variant == "pool-shards-nccl":   # every GPU its own pool, batches replicated by the library's ncclBroadcast
+            kw.update(shard_cfg(pcdn, "shards-nccl"), max_conns=1024)
+            fl |= pcdn.FLAG_SPAN_RUNS
         w = World(pcdn, flags=fl, pool_bytes=1 << 30, **kw)
     elif variant in ("runs", "runs-staged"):
         # run-length span table (PCDN_FLAG_SPAN_RUNS): same streams, the table just arrives compressed
