@@ -293,6 +293,9 @@ def main():
     dbs = [db, pkg.DeviceBatch(M, M, d_arenas[1].data_ptr(), d_arenas[1].numel(), d_kind.data_ptr(), d_flags.data_ptr(),
                                d_slot.data_ptr(), d_len.data_ptr(), d_aoff.data_ptr(), d_alen.data_ptr(),
                                d_topics.data_ptr(), M, d_bidx.data_ptr())]
+    for d_ in dbs:
+        d_.hints = pkg.BATCH_READY      # the batch buffers are static and complete: the library may broadcast batch n+1 while batch n is packed
+    db.hints = pkg.BATCH_READY
     state = {"i": 0}
 
     def step_device():

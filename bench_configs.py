@@ -77,6 +77,7 @@ class DeviceBatch:
         self.db = pkg.DeviceBatch(n, nb, self.arena.data_ptr(), self.arena.numel(), self.kind.data_ptr(), self.flags.data_ptr(),
                                   self.slot.data_ptr(), self.len.data_ptr(), self.aoff.data_ptr(), self.alen.data_ptr(),
                                   self.topics.data_ptr(), len(topics), self.bidx.data_ptr())
+        self.db.hints = pkg.BATCH_READY   # complete in device memory before the first submit
 
 
 def zipf_p(n, s=0.99):

@@ -247,7 +247,17 @@ typedef struct pcdn_device_batch {
   const uint16_t* topics;        /* device: concatenated topic lists                           */
   uint32_t n_topics_total;
   const uint32_t* bcast_index;   /* device [n_bcast]: batch index of the j-th broadcast, ascending */
+  uint32_t hints;                /* PCDN_BATCH_*                                               */
+  uint32_t reserved;
 } pcdn_device_batch;
+/* pcdn_device_batch.hints */
+enum {
+  /* The arrays are already complete in device memory (produced and synchronised earlier).  Without
+   * this hint the engine orders the batch after everything queued on its (root shard's) main stream,
+   * so that a caller sharing that stream can produce the batch with its own kernels; with it a sharded
+   * engine may broadcast batch n+1 while batch n is still being packed. */
+  PCDN_BATCH_READY = 1
+};
 
 typedef struct pcdn_stats {
   uint64_t batches, msgs, deliveries, bytes_out;

@@ -38,6 +38,7 @@ FLAG_HOST_RINGS = 4     # rings in mapped pinned host memory: spans are readable
 FLAG_OUTPUT_POOL = 16   # one shared output pool per GPU instead of a ring per connection (spans: 32-byte units relative to pool_base)
 FLAG_SPAN_RUNS = 8      # run-length span table (BatchResult.runs): consecutive connections with identical spans
 FLAG_STAGED_SPANS = 2   # force the large-engine span path (table in HBM + D2H) on a small engine
+BATCH_READY = 1         # DeviceBatch.hints: the arrays are already complete in device memory
 INGEST_NCCL, INGEST_HOST = 0, 1   # sharded engines: NCCL broadcast over NVLink | every shard copies from host
 RECORD_ALIGN = 32
 CONN_NONE = 0xFFFFFFFF
@@ -123,7 +124,7 @@ class DeviceBatch(C.Structure):
         ("n_msgs", C.c_uint32), ("n_bcast", C.c_uint32), ("arena", C.c_void_p), ("arena_bytes", C.c_uint64),
         ("kind", C.c_void_p), ("flags", C.c_void_p), ("slot_off16", C.c_void_p), ("raw_len", C.c_void_p),
         ("aux_off", C.c_void_p), ("aux_len", C.c_void_p), ("topics", C.c_void_p), ("n_topics_total", C.c_uint32),
-        ("bcast_index", C.c_void_p),
+        ("bcast_index", C.c_void_p), ("hints", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 

@@ -321,3 +321,22 @@ def test_message_hook_seam_on_state_messages(pcdn):
     e.set_message_hook(0, None)
     assert e.user_receive(b"alice", orc.serialize(pcdn.KIND_UNSUBSCRIBE, bytes([2]))) == 0    # hook removed: processed
     assert e.debug_interested([2]) == []
+
+
+def test_config_validation_of_round2_fields(pcdn):
+    """shard layout, ingest mode and output-pool size are checked before anything is allocated"""
+    def bad(**kw):
+        with pytest.raises(pcdn.PcdnError) as ei:
+            pcdn.Engine(**dict(dict(device=-1, max_conns=64), **kw))
+        assert ei.value.code == -1, kw
+
+    bad(world_shards=2, first_shard=2)                       # first_shard + n_devices > world_shards
+    bad(ingest=7)
+    bad(flags=pcdn.FLAG_OUTPUT_POOL, pool_bytes=100)         # smaller than 4 KiB
+    bad(flags=pcdn.FLAG_OUTPUT_POOL, pool_bytes=200 << 30)   # 2^32 units of 32 B = 128 GiB is the limit
+    bad(max_conns=1 << 31, world_shards=4)                   # id space beyond 32 bits
+    e = pcdn.Engine(device=-1, max_conns=64, flags=pcdn.FLAG_OUTPUT_POOL, world_shards=3, first_shard=1)
+    assert e.num_shards() == (0, 3) and e.shard_info(0).conn_base == 8192
+    with pytest.raises(pcdn.PcdnError) as ei:
+        e.retry_batch(1)
+    assert ei.value.code == -3                               # host-only engine: no data path
