@@ -200,6 +200,8 @@ int drain_shard(pcdn_egress* g, uint64_t batch_id, uint32_t li, pcdn_egress_sink
   pcdn_batch_result res{};
   int rc = pcdn_poll_shard(e, batch_id, li, &res, 1);
   if (rc) return rc;
+  if (res.status == (uint32_t)(-PCDN_EAGAIN))
+    return fail(PCDN_EAGAIN, "the batch was refused for space in the output pool: release older batches, pcdn_retry_batch, drain again");
   if (res.status) return fail(PCDN_E2BIG, "batch was rejected on the device: nothing to drain");
   Shard& sh = e->shards[li];
   ShardEgress& s = g->sh[li];
@@ -497,7 +499,12 @@ int pcdn_egress_soft_close(pcdn_egress* g, pcdn_conn conn, int* fd_out) {
     uint64_t b = 0;
     if ((rc = pcdn_next_batch(g->e, &b))) return rc;
     if (!b) break;
-    if ((rc = drain_locked(g, b, fd_sink, g, nullptr))) return rc;
+    rc = drain_locked(g, b, fd_sink, g, nullptr);
+    if (rc == PCDN_EAGAIN) {   // output pool: everything older is released by now, so the refused batch fits
+      if ((rc = pcdn_retry_batch(g->e, b))) return rc;
+      rc = drain_locked(g, b, fd_sink, g, nullptr);
+    }
+    if (rc) return rc;
     if ((rc = pcdn_release_batch(g->e, b))) return rc;
   }
   if (fd_out) *fd_out = g->fds[conn];
