@@ -207,15 +207,11 @@ __device__ __forceinline__ void direct_lookup_body(const DevState& s, const Batc
   uint32_t target = kConnNone;
   const uint32_t klen = is_direct ? b.aux_len[m] : 0;
   const uint8_t* kp = b.arena + (is_direct ? b.aux_off[m] : 0);
-  // hash: lane gl of the group takes the 64-bit words gl, gl + 8, ... of the key.  The first two are kept
-  // (keys up to 128 bytes = the production BLS key fit entirely): the compare below reuses them instead
-  // of reading the frame a second time.
+  // hash
   const uint32_t nw = (klen + 7) >> 3;
-  uint64_t acc = 0, kw0 = 0, kw1 = 0;
-  for (uint32_t i = gl, it = 0; i < nw; i += 8, it++) {
+  uint64_t acc = 0;
+  for (uint32_t i = gl; i < nw; i += 8) {
     uint64_t wd = (uint64_t)key_word32(kp, 2 * i, klen) | ((uint64_t)key_word32(kp, 2 * i + 1, klen) << 32);
-    if (it == 0) kw0 = wd;
-    if (it == 1) kw1 = wd;
     acc += key_word_mix(wd, i, s.seed);
   }
 #pragma unroll
@@ -231,6 +227,7 @@ __device__ __forceinline__ void direct_lookup_body(const DevState& s, const Batc
   if (b1 == b2 && gl >= 4) cand = false;
   uint32_t gmask = (__ballot_sync(0xffffffffu, cand) >> gshift) & 0xFFu;  // this group's candidates
   uint32_t route = ROUTE_NONE;
+  const uint32_t nw32 = (klen + 3) >> 2;
   while (__any_sync(0xffffffffu, gmask != 0)) {  // groups advance through their own candidates in lockstep
     const bool active = gmask != 0;
     const int src = active ? (int)(gshift + __ffs(gmask) - 1) : (int)lane;
@@ -239,14 +236,8 @@ __device__ __forceinline__ void direct_lookup_body(const DevState& s, const Batc
     const uint32_t rt = __shfl_sync(0xffffffffu, e.route, src);
     bool eq = true;
     if (active) {
-      // the stored key (zero padded to key_stride, 16-byte aligned) is compared 64 bits at a time against
-      // the words this lane already holds; longer keys read the rest of the frame again
-      const uint64_t* ak = reinterpret_cast<const uint64_t*>(s.keys + (size_t)kslot * s.key_stride);
-      for (uint32_t i = gl, it = 0; i < nw; i += 8, it++) {
-        const uint64_t mine = it == 0 ? kw0 : it == 1 ? kw1
-                            : ((uint64_t)key_word32(kp, 2 * i, klen) | ((uint64_t)key_word32(kp, 2 * i + 1, klen) << 32));
-        eq = eq && (ak[i] == mine);
-      }
+      const uint32_t* ak = reinterpret_cast<const uint32_t*>(s.keys + (size_t)kslot * s.key_stride);
+      for (uint32_t i = gl; i < nw32; i += 8) eq = eq && (ak[i] == key_word32(kp, i, klen));
     }
     const bool all_eq = ((__ballot_sync(0xffffffffu, eq) >> gshift) & 0xFFu) == 0xFFu;
     if (active && all_eq) { route = rt; gmask = 0; }
