@@ -511,10 +511,14 @@ def main():
 
             def check(ch):
                 n = ch.n_spans
-                a = np.ctypeslib.as_array(C.cast(ch.data, C.POINTER(C.c_uint8)), shape=(ch.bytes,)).reshape(n, M * rec)
+                flat = np.ctypeslib.as_array(C.cast(ch.data, C.POINTER(C.c_uint8)), shape=(ch.bytes,))
                 offs = np.ctypeslib.as_array(ch.data_off, shape=(n,))
+                # the spans of a chunk lie at a constant stride: back to back in a staged chunk, one ring apart when
+                # the sink reads host rings in place
+                st = int(offs[1] - offs[0]) if n > 1 else M * rec
+                a = np.lib.stride_tricks.as_strided(flat[int(offs[0]):], shape=(n, M * rec), strides=(st, 1), writeable=False)
                 sp = np.ctypeslib.as_array(C.cast(ch.spans, C.POINTER(C.c_uint32)), shape=(n, 4))
-                ok = bool((a[:, keep] == image[keep]).all()) and bool((offs == np.arange(n, dtype=np.uint64) * (M * rec)).all()) \
+                ok = bool((a[:, keep] == image[keep]).all()) and bool((offs == offs[0] + np.arange(n, dtype=np.uint64) * np.uint64(st)).all()) \
                     and bool((sp[:, 2] == M * rec).all()) and bool((sp[:, 3] == M).all())
                 seen["spans"] += n
                 seen["bad"] += 0 if ok else 1
