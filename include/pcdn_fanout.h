@@ -195,7 +195,7 @@ typedef struct pcdn_msg {
  * L = BE32(p), write the 4+L bytes to the socket, advance p by round_up(4+L, 32). */
 typedef struct pcdn_span {
   pcdn_conn conn;
-  uint32_t ring_off;  /* byte offset of the first record inside the connection's ring          */
+  uint32_t ring_off;  /* byte offset of the first record inside the connection's ring; PCDN_FLAG_OUTPUT_POOL: offset in 32-byte units relative to pcdn_batch_result.pool_base */
   uint32_t len;       /* bytes covered (multiple of 32), padding included                      */
   uint32_t n_records; /* deliveries in this run                                                */
 } pcdn_span;
@@ -221,10 +221,10 @@ typedef struct pcdn_batch_result {
   uint32_t n_overflow;             /* connections whose ring was full: their deliveries from the overflow point on were dropped; the host must remove them (R13 analogue) */
   const pcdn_conn* overflow_conns; /* engine-owned                                              */
   uint32_t n_direct_dropped;       /* direct messages with no route (handler.rs:210,224)        */
-  uint32_t status;                 /* 0 or PCDN_E2BIG (as positive number)                      */
+  uint32_t status;                 /* 0, PCDN_E2BIG (scatter-list capacity, or larger than the whole output pool) or PCDN_EAGAIN (output pool full: release older batches, pcdn_retry_batch) — as positive numbers; a refused batch wrote nothing and reports zero counters */
   const int8_t* msg_status;        /* device-parse batches: per message 0 or PCDN_EPARSE / PCDN_EPRUNE (the reference would have ended that sender's receive loop); NULL otherwise */
   uint32_t n_msg_errors;           /* number of non-zero entries in msg_status                  */
-  uint32_t reserved;
+  uint32_t reserved;               /* pcdn_poll_shard: global index of the shard                */
   const pcdn_span_run* runs;       /* PCDN_FLAG_SPAN_RUNS: the span table in run-length form (then spans == NULL) */
   uint32_t n_runs;
   uint32_t pool_base;              /* PCDN_FLAG_OUTPUT_POOL: first 32-byte unit of this batch's region; span offsets are relative to it (0 otherwise) */
