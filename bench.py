@@ -515,10 +515,15 @@ def main():
                 offs = np.ctypeslib.as_array(ch.data_off, shape=(n,))
                 # the spans of a chunk lie at a constant stride: back to back in a staged chunk, one ring apart when
                 # the sink reads host rings in place
-                st = int(offs[1] - offs[0]) if n > 1 else M * rec
-                a = np.lib.stride_tricks.as_strided(flat[int(offs[0]):], shape=(n, M * rec), strides=(st, 1), writeable=False)
+                so = np.sort(offs.astype(np.int64))          # (in-place host rings: the span table is in CTA order, not address order)
+                st = int(so[1] - so[0]) if n > 1 else M * rec
+                ap = st >= M * rec and bool((so == so[0] + np.arange(n, dtype=np.int64) * st).all()) and int(so[-1]) + M * rec <= ch.bytes
+                if not ap:
+                    seen["bad"] += 1
+                    return
+                a = np.lib.stride_tricks.as_strided(flat[int(so[0]):], shape=(n, M * rec), strides=(st, 1), writeable=False)
                 sp = np.ctypeslib.as_array(C.cast(ch.spans, C.POINTER(C.c_uint32)), shape=(n, 4))
-                ok = bool((a[:, keep] == image[keep]).all()) and bool((offs == offs[0] + np.arange(n, dtype=np.uint64) * np.uint64(st)).all()) \
+                ok = bool((a[:, keep] == image[keep]).all()) \
                     and bool((sp[:, 2] == M * rec).all()) and bool((sp[:, 3] == M).all())
                 seen["spans"] += n
                 seen["bad"] += 0 if ok else 1

@@ -87,7 +87,7 @@ def zipf_p(n, s=0.99):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", required=True, choices=["C1", "C3", "C4", "C5dense", "C5sparse", "latency", "churn"])
+    ap.add_argument("--workload", required=True, choices=["C1", "C3", "C4", "C5dense", "C5sparse", "latency", "churn", "writer"])
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--variant", type=int, default=0)
@@ -158,6 +158,58 @@ def main():
                 out["cases"].append({"case": name, "p50_us": ts[len(ts) // 2], "p99_us": ts[int(len(ts) * 0.99)], "min_us": ts[0],
                                      "submit_call_p50_us": tsub[len(tsub) // 2], "deliveries": int(r.n_deliveries)})
             eng.close()
+        print(json.dumps(out), flush=True)
+        return
+
+    if wl == "writer":
+        # f-2 egress writer: 8192 subscribers, each with its own memfd as "socket"; batches of 8 x 1 KiB broadcasts;
+        # pcdn_egress_write_batch = poll + gather + DMA + one writev per connection and batch on the writer threads
+        import resource
+        soft, hard = resource.getrlimit(resource.RLIMIT_NOFILE)
+        resource.setrlimit(resource.RLIMIT_NOFILE, (hard, hard))
+        n, M = min(8192, hard - 256), 8
+        rng = np.random.default_rng(12)
+        keys = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        keys[:, :8] = np.arange(n, dtype=np.uint64).view(np.uint8).reshape(n, 8)
+        frames = [B.broadcast_frame(0, bytes(((i * 131 + m) & 0xFF) for i in range(1024))) for m in range(M)]
+        L = len(frames[0]); rec = (4 + L + 31) // 32 * 32
+        out = {"metric": "egress writer: pcdn_submit (host buffers) -> pcdn_egress_write_batch to one memfd per connection (wall clock)", "cases": []}
+        for host_rings in (False, True):
+            eng = pkg.Engine(device=0, stream=stream.cuda_stream, max_conns=n, max_topics=16, max_keys=n, max_key_len=32,
+                             ring_bytes_per_conn=4 * M * rec, max_batch_msgs=64, max_batch_bcast=16, max_batch_bytes=1 << 20,
+                             max_batch_deliveries=M * n + 1024, batch_slots=2, flags=pkg.FLAG_SPAN_RUNS | (pkg.FLAG_HOST_RINGS if host_rings else 0))
+            conns = eng.add_users_bulk(keys, 32, np.zeros(n, dtype=np.uint16), np.arange(n + 1, dtype=np.uint32))
+            eg = pkg.Egress(eng, n_threads=16)
+            fds = [os.memfd_create("c%d" % c) for c in conns]
+            for c, fd in zip(conns, fds):
+                eg.attach(int(c), fd)
+            msgs = [("b", [0], fr, False) for fr in frames]
+            ts, nbytes = [], 0
+            for it in range(8):
+                t0 = time.perf_counter()
+                b = eng.submit(msgs)
+                st = eg.write_batch(b)
+                eng.release_batch(b)
+                t1 = time.perf_counter()
+                assert st.fd_bytes == n * M * (4 + L) and st.unattached_spans == 0 and eg.failed() == []
+                if it >= 2:
+                    ts.append(t1 - t0); nbytes = st.fd_bytes
+                if it == 7:   # what is in the "sockets" is the framed stream
+                    want = b"".join(L.to_bytes(4, "big") + fr for fr in frames)
+                    for fd in fds[:: max(1, n // 64)]:
+                        sz = os.lseek(fd, 0, os.SEEK_END)
+                        os.lseek(fd, sz - len(want), os.SEEK_SET)
+                        assert os.read(fd, len(want)) == want
+                for fd in fds:
+                    os.ftruncate(fd, 0); os.lseek(fd, 0, os.SEEK_SET)
+            ts.sort()
+            p50 = ts[len(ts) // 2]
+            out["cases"].append({"rings": "mapped pinned host memory (read in place)" if host_rings else "HBM (gather + DMA)", "connections": n,
+                                 "bytes_per_batch": int(nbytes), "p50_ms_per_batch": p50 * 1e3, "GBps_to_file_descriptors": nbytes / p50 / 1e9,
+                                 "writev_calls_per_batch": int(st.fd_writes), "writer_threads": 16})
+            for fd in fds:
+                os.close(fd)
+            eg.close(); eng.close()
         print(json.dumps(out), flush=True)
         return
 
