@@ -119,6 +119,9 @@ int acquire_open_slot(pcdn_engine* e) {
   return fail(PCDN_EAGAIN, "all batch slots are in flight: poll and release a batch first");
 }
 
+// the adaptive pack-stream overlap applies to batches whose previous output was at most this many bytes
+static constexpr unsigned long long kOverlapMaxBytes = 2ull << 30;
+
 // run the kernel pipeline of one shard for slot `si`, whose BatchIn is ready (or will be, once
 // ev_ingest fires) in that shard's memory
 int launch_shard_pipeline(pcdn_engine* e, Shard& sh, uint32_t si, uint32_t n_direct, bool devparse, bool wait_ingest, bool unblock = false) {
@@ -132,7 +135,26 @@ int launch_shard_pipeline(pcdn_engine* e, Shard& sh, uint32_t si, uint32_t n_dir
   // latency-bound (three dependent random reads per message), their pack is a separate bandwidth-bound
   // launch, and the two overlap well — C4: 1.98 → 2.10 G msgs/s (profiles/r2_cfg_C4_sweep_v*.json).
   const bool direct_only = s.in.n_bcast == 0 && n_direct >= kThinSeparateMin;
-  cudaStream_t st = sh.stream, ps = (!dp && ((e->cfg.pack_variant & 8) || direct_only)) ? sh.pack_stream : sh.stream, cs = sh.copy_stream;
+  // Broadcast batches: running the next batch's control stage beside this batch's pack helps when the pack is
+  // short and message-major (sparse fan-out, config 5: 0.293 -> 0.282 ms) and hurts a long pack, which then shares
+  // SMs and HBM with it (config 5 dense: 5.29 -> 6.70 ms; C2 likewise) - profiles/r2_overlap_adaptive.txt.  Which
+  // one this batch will be is decided on the device, so the class mix and size of the most recent COMPLETED batch
+  // of this shard predict it (a workload changes its mix rarely; a wrong guess costs one batch a few percent).
+  if (!dp && s.in.n_bcast > 0) {
+    for (int k = 0; k < 2; k++) {
+      const int pv = sh.prev_slot[k];
+      if (pv < 0 || pv == (int)si) continue;
+      const ShardSlot& o = sh.slots[pv];
+      if (cudaEventQuery(o.ev_done) != cudaSuccess) { cudaGetLastError(); continue; }
+      const BatchStats& ps_ = *o.h_stats;
+      sh.fat_only = ps_.status == 0 && ps_.n_cm == 0 && ps_.n_fat_tiles > 0 && ps_.bytes_out <= kOverlapMaxBytes;
+      break;
+    }
+  }
+  const bool fat_overlap = s.in.n_bcast > 0 && sh.fat_only && !(e->cfg.pack_variant & 32);   // (bit 5: A/B switch, never overlap broadcast batches)
+  sh.prev_slot[1] = sh.prev_slot[0];
+  sh.prev_slot[0] = (int)si;
+  cudaStream_t st = sh.stream, ps = (!dp && ((e->cfg.pack_variant & 8) || direct_only || fat_overlap)) ? sh.pack_stream : sh.stream, cs = sh.copy_stream;
   const bool has_direct = n_direct > 0;
   if (wait_ingest) CUDA_TRY(cudaStreamWaitEvent(st, s.ev_ingest, 0));
   s.timed = e->timing;

@@ -122,6 +122,8 @@ struct Shard {
   std::vector<Upd32> h_u32;
   NcclComm comm = nullptr;
   int nccl_ranks = 0;
+  int prev_slot[2] = {-1, -1};      // the two most recently launched slots (newest first)
+  bool fat_only = false;            // the last completed batch packed message-major tiles only (no connection-major message)
   cudaEvent_t ev_submit = nullptr;  // device-input batches: "everything queued on the main stream so far"
   std::vector<void*> dev_allocs, pin_allocs;
 };
