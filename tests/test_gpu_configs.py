@@ -174,3 +174,52 @@ def test_output_pool_backpressure_and_wrap(pcdn, staged):
     w.bcast([1], orc.broadcast_frame([1], b"still alive"))
     assert w.check() == 500
     w.e.close()
+
+
+@pytest.mark.parametrize("pool", [False, True])
+def test_alternating_batch_classes_in_flight(pcdn, pool):
+    """The engine moves the pack of short message-major-only batches to its pack stream (so the next
+    batch's control kernels run beside it) and decides that from the last COMPLETED batch
+    (engine.cu launch_shard_pipeline).  Several batches are in flight here and their classes alternate
+    — sparse 4 KiB broadcasts (message-major only), dense 1 KiB broadcasts (connection-major), direct
+    only — so successive packs land on different streams in every order; per-connection order and bytes
+    must still be the oracle's."""
+    rng = random.Random(77)
+    cfg = dict(max_conns=8192, ring_bytes_per_conn=1 << 18, max_batch_deliveries=1 << 18, batch_slots=4,
+               max_batch_bytes=8 << 20)
+    if pool:
+        cfg.update(flags=pcdn.FLAG_OUTPUT_POOL, pool_bytes=1 << 30)
+    w = World(pcdn, **cfg)
+    keys = [i.to_bytes(8, "little") for i in range(6000)]
+    for i, k in enumerate(keys):
+        w.add_user(k, [0] + rng.sample(range(1, 64), 3))
+    kinds = ["sparse", "sparse", "dense", "sparse", "direct", "sparse", "sparse", "dense", "dense", "sparse", "direct", "sparse"]
+    got, total = {}, 0
+    for rnd in range(3):
+        ids = []
+        for bi, kind in enumerate(kinds):
+            tag = rnd * 16 + bi
+            if kind == "sparse":
+                for m in range(6):
+                    t = rng.randrange(1, 64)
+                    w.bcast([t], orc.broadcast_frame([t], bytes([tag, m]) * 2100))
+            elif kind == "dense":
+                for m in range(3):
+                    w.bcast([0], orc.broadcast_frame([0], bytes([tag, m]) * 400))
+            else:
+                for m in range(3000):
+                    k = rng.choice(keys)
+                    w.direct(k, orc.direct_frame(k, bytes([tag, m & 0xFF]) * 40))
+            ids.append(w.e.flush())
+            if len(ids) == 4 or bi == len(kinds) - 1:      # four in flight, then consume them oldest first
+                for b in ids:
+                    r = w.e.poll(b)
+                    assert r.status == 0 and r.n_overflow == 0
+                    total += r.n_deliveries
+                    for c, fr in w.e.collect_frames(r).items():
+                        got.setdefault(c, []).extend(fr)
+                    w.e.release_batch(b)
+                ids = []
+    assert got == w.expect()
+    assert total > 3 * (3 * 6000 * 3 + 2 * 3000)
+    w.e.close()
