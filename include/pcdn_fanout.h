@@ -513,6 +513,11 @@ int pcdn_egress_soft_close(pcdn_egress* g, pcdn_conn conn, int* fd_out);
 
 /* ---- introspection (tests, metrics: cdn-proto/src/connection/metrics.rs:12-28) ------------- */
 int pcdn_get_stats(pcdn_engine* e, pcdn_stats* out);
+/* the per-stage device times of the stats struct (ms_direct .. ms_pack) are accumulated while this is on.
+ * Diagnostic, environment only: PCDN_TIMELINE=<file> appends one line per batch with the device
+ * timestamps of its stage events (written when the batch is released, which then blocks until its
+ * pack is done; with PCDN_TIMELINE_ASYNC=1 nothing blocks and the last 64 batches are written when
+ * the engine is destroyed). */
 int pcdn_set_timing(pcdn_engine* e, int on);
 /* device pointer + geometry of the rings (zero-copy verification / GPUDirect hand-off) */
 int pcdn_ring_info(pcdn_engine* e, void** dev_base, uint64_t* ring_bytes, uint32_t* max_conns);

@@ -121,6 +121,7 @@ int acquire_open_slot(pcdn_engine* e) {
 
 // the adaptive pack-stream overlap applies to batches whose previous output was at most this many bytes
 static constexpr unsigned long long kOverlapMaxBytes = 2ull << 30;
+static constexpr uint32_t kTimelineBatches = 64;
 
 // run the kernel pipeline of one shard for slot `si`, whose BatchIn is ready (or will be, once
 // ev_ingest fires) in that shard's memory
@@ -157,7 +158,15 @@ int launch_shard_pipeline(pcdn_engine* e, Shard& sh, uint32_t si, uint32_t n_dir
   cudaStream_t st = sh.stream, ps = (!dp && ((e->cfg.pack_variant & 8) || direct_only || fat_overlap)) ? sh.pack_stream : sh.stream, cs = sh.copy_stream;
   const bool has_direct = n_direct > 0;
   if (wait_ingest) CUDA_TRY(cudaStreamWaitEvent(st, s.ev_ingest, 0));
-  s.timed = e->timing;
+  s.timed = e->timing && !e->timeline_async;
+  cudaEvent_t* tev = s.ev;
+  bool timed = s.timed;
+  if (e->timeline_async) {   // diagnostic: stage events from a ring of kTimelineBatches sets, read back when the engine goes away
+    const uint32_t k = sh.tl_n++ % kTimelineBatches;
+    tev = &sh.tl_ev[(size_t)k * 6];
+    sh.tl_batch[k] = e->next_batch_id;
+    timed = true;
+  }
   s.polled = false;
   s.n_msg_errors = 0;
   if (++s.w.stamp == 0) s.w.stamp = 1;  // validity stamp of this batch's direct buckets / look-back words
@@ -181,20 +190,20 @@ int launch_shard_pipeline(pcdn_engine* e, Shard& sh, uint32_t si, uint32_t n_dir
   s.w.spans = s.spans_mapped ? s.d_spans_map : s.d_spans_dev;
   s.w.overflow = s.spans_mapped ? s.d_ovf_map : s.d_ovf_dev;
   const bool zero_in_kernel = fused && !devparse;  // (k_parse counts into the batch counters before the fused kernel)
-  if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[0], st));
+  if (timed) CUDA_TRY(cudaEventRecord(tev[0], st));
   if (!zero_in_kernel) launch_batch_begin(sh.dev, s.w, s.in, has_direct, st);
   if (devparse) launch_parse(sh.dev, s.w, s.in, st);
   if (has_direct && !fused) launch_direct(sh.dev, s.w, s.in, n_direct, st);  // fused: lookup + sort inside k_ctrl_small
-  if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[1], st));
+  if (timed) CUDA_TRY(cudaEventRecord(tev[1], st));
   if (fused) {
     launch_ctrl_small(sh.dev, s.w, s.in, has_direct, zero_in_kernel, s.d_stats_pub, st);
-    if (s.timed) { CUDA_TRY(cudaEventRecord(s.ev[2], st)); CUDA_TRY(cudaEventRecord(s.ev[3], st)); }
+    if (timed) { CUDA_TRY(cudaEventRecord(tev[2], st)); CUDA_TRY(cudaEventRecord(tev[3], st)); }
   } else {
     launch_match(sh.dev, s.w, s.in, st);
-    if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[2], st));
+    if (timed) CUDA_TRY(cudaEventRecord(tev[2], st));
     launch_plan(sh.dev, s.w, s.in, st);
     launch_offsets(sh.dev, s.w, s.in, has_direct, st);
-    if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[3], st));
+    if (timed) CUDA_TRY(cudaEventRecord(tev[3], st));
   }
   if (!s.spans_mapped) {
     CUDA_TRY(cudaEventRecord(s.ev_ctrl, st));
@@ -207,9 +216,11 @@ int launch_shard_pipeline(pcdn_engine* e, Shard& sh, uint32_t si, uint32_t n_dir
   }
   // (mapped spans: k_offsets wrote spans / overflow into host memory; everything stays on one
   //  stream and the host waits for ev_done only)
-  if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[4], ps));
+  s.on_pack_stream = ps != st;
+  if (e->timeline_async) sh.tl_ps[(sh.tl_n - 1) % kTimelineBatches] = (int)s.on_pack_stream;
+  if (timed) CUDA_TRY(cudaEventRecord(tev[4], ps));
   launch_pack(sh.dev, s.w, s.in, n_direct, e->cfg.pack_variant, sh.n_sms, ps);
-  if (s.timed) CUDA_TRY(cudaEventRecord(s.ev[5], ps));
+  if (timed) CUDA_TRY(cudaEventRecord(tev[5], ps));
   CUDA_TRY(cudaGetLastError());
   if (!fused) CUDA_TRY(cudaMemcpyAsync(s.h_stats, s.w.stats, sizeof(BatchStats), cudaMemcpyDeviceToHost, ps));
   CUDA_TRY(cudaEventRecord(s.ev_done, ps));
@@ -502,6 +513,18 @@ void destroy_shard(pcdn_engine* e, Shard& sh) {
   if (sh.copy_stream) cudaStreamSynchronize(sh.copy_stream);
   if (sh.ingest_stream) cudaStreamSynchronize(sh.ingest_stream);
   if (sh.comm && e->nccl) { e->nccl->CommDestroy(sh.comm); sh.comm = nullptr; }
+  if (e->timeline && e->timeline_async && sh.ev_base) {
+    const uint32_t n = std::min(sh.tl_n, kTimelineBatches), first = sh.tl_n - n;
+    for (uint32_t j = first; j < sh.tl_n; j++) {
+      const uint32_t k = j % kTimelineBatches;
+      float t[6];
+      for (int q = 0; q < 6; q++) if (cudaEventElapsedTime(&t[q], sh.ev_base, sh.tl_ev[(size_t)k * 6 + q]) != cudaSuccess) { t[q] = -1.f; cudaGetLastError(); }
+      std::fprintf(e->timeline, "shard %u batch %llu pack_stream %d ctrl_begin %.4f direct_end %.4f match_end %.4f offsets_end %.4f pack_begin %.4f pack_end %.4f\n",
+                   sh.gindex, (unsigned long long)sh.tl_batch[k], sh.tl_ps[k], t[0], t[1], t[2], t[3], t[4], t[5]);
+    }
+    std::fflush(e->timeline);
+  }
+  for (auto& ev : sh.tl_ev) if (ev) cudaEventDestroy(ev);
   for (auto& s : sh.slots) {
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     if (s.ev_ctrl) cudaEventDestroy(s.ev_ctrl);
@@ -515,6 +538,7 @@ void destroy_shard(pcdn_engine* e, Shard& sh) {
   if (sh.jstage_d) cudaFree(sh.jstage_d);
   if (sh.ev_journal) cudaEventDestroy(sh.ev_journal);
   if (sh.ev_submit) cudaEventDestroy(sh.ev_submit);
+  if (sh.ev_base) cudaEventDestroy(sh.ev_base);
   if (sh.copy_stream) cudaStreamDestroy(sh.copy_stream);
   if (sh.pack_stream) cudaStreamDestroy(sh.pack_stream);
   if (sh.ingest_stream) cudaStreamDestroy(sh.ingest_stream);
@@ -533,6 +557,7 @@ void destroy_engine(pcdn_engine* e) {
     if (prev >= 0) cudaSetDevice(prev);
     cudaGetLastError();  // a failed create must not leave its error behind for the next engine's launches
   }
+  if (e->timeline) std::fclose(e->timeline);
   delete e;
 }
 
@@ -569,6 +594,12 @@ int init_shard(pcdn_engine* e, Shard& sh, int ndev, void* user_stream) {
   CUDA_TRY(cudaStreamCreateWithFlags(&sh.copy_stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&sh.ev_journal, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&sh.ev_submit, cudaEventDisableTiming));
+  if (e->timeline) { CUDA_TRY(cudaEventCreate(&sh.ev_base)); CUDA_TRY(cudaEventRecord(sh.ev_base, sh.stream)); }
+  if (e->timeline_async) {
+    sh.tl_ev.assign((size_t)kTimelineBatches * 6, nullptr);
+    sh.tl_batch.assign(kTimelineBatches, 0); sh.tl_ps.assign(kTimelineBatches, 0);
+    for (auto& ev : sh.tl_ev) CUDA_TRY(cudaEventCreate(&ev));
+  }
   {
     // highest priority: when a pack and the (small) control kernels of the next batch become
     // runnable together, the pack's persistent CTAs must be placed first and evenly over the SMs
@@ -814,6 +845,12 @@ int pcdn_create(const pcdn_config* cfg, pcdn_engine** out) {
         if (cfg->devices[i] == cfg->devices[j])
           return fail(PCDN_EINVAL, "PCDN_INGEST_NCCL needs one GPU per shard (use PCDN_INGEST_HOST for shards that share a device)");
   pcdn_engine* e = new pcdn_engine();
+  if (const char* tl = std::getenv("PCDN_TIMELINE")) {
+    e->timeline = std::fopen(tl, "a");
+    e->timing = e->timeline != nullptr;
+    const char* as = std::getenv("PCDN_TIMELINE_ASYNC");
+    e->timeline_async = e->timeline && as && as[0] == '1';
+  }
   e->cfg = *cfg;
   e->identity = cfg->identity ? cfg->identity : "/";
   e->cfg.identity = e->identity.c_str();
@@ -1732,6 +1769,14 @@ int pcdn_release_batch(pcdn_engine* e, uint64_t batch_id) {
     // its pinned staging buffers must not be refilled before that copy ran (device-input batches have
     // no host staging and stay fully asynchronous — the pipelined submit_device/release loop).
     if (!ss.polled && !s.device_input) CUDA_TRY(cudaEventSynchronize(e->sharded ? ss.ev_ingest : ss.ev_done));
+    if (e->timeline && ss.timed && !e->timeline_async) {   // diagnostic: where this batch's stages ran on the shard's clock (blocks until the pack is done)
+      CUDA_TRY(cudaEventSynchronize(ss.ev_done));
+      float t[6];
+      for (int k = 0; k < 6; k++) if (cudaEventElapsedTime(&t[k], sh.ev_base, ss.ev[k]) != cudaSuccess) { t[k] = -1.f; cudaGetLastError(); }
+      std::fprintf(e->timeline, "shard %u batch %llu pack_stream %d ctrl_begin %.4f direct_end %.4f match_end %.4f offsets_end %.4f pack_begin %.4f pack_end %.4f\n",
+                   sh.gindex, (unsigned long long)batch_id, (int)ss.on_pack_stream, t[0], t[1], t[2], t[3], t[4], t[5]);
+      std::fflush(e->timeline);
+    }
     // ring space may be reused only after the pack that filled it has finished
     CUDA_TRY(cudaStreamWaitEvent(sh.stream, ss.ev_done, 0));
     launch_release(sh.dev, ss.w.batch_units, ss.w.stats, sh.stream);
@@ -1810,7 +1855,7 @@ int pcdn_get_stats(pcdn_engine* e, pcdn_stats* out) {
 }
 int pcdn_set_timing(pcdn_engine* e, int on) {
   LOCK;
-  e->timing = on != 0;
+  e->timing = on != 0 || e->timeline != nullptr;
   return 0;
 }
 int pcdn_ring_info(pcdn_engine* e, void** dev_base, uint64_t* ring_bytes, uint32_t* max_conns) {

@@ -98,6 +98,7 @@ struct ShardSlot {
   cudaEvent_t ev_early = nullptr;  // early counters are in h_early (copy stream)
   cudaEvent_t ev_ingest = nullptr; // the batch has arrived in d_arena (ingest stream)
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool on_pack_stream = false;     // this batch's pack was launched on the pack stream
   bool timed = false;
   bool polled = false;             // results of this shard have been fetched
 };
@@ -124,6 +125,9 @@ struct Shard {
   int nccl_ranks = 0;
   int prev_slot[2] = {-1, -1};      // the two most recently launched slots (newest first)
   bool fat_only = false;            // the last completed batch packed message-major tiles only (no connection-major message)
+  cudaEvent_t ev_base = nullptr;    // PCDN_TIMELINE: time zero of this shard's timeline dump
+  std::vector<cudaEvent_t> tl_ev;   // PCDN_TIMELINE_ASYNC: 6 stage events for each of the last kTimelineBatches launches
+  std::vector<uint64_t> tl_batch; std::vector<int> tl_ps; uint32_t tl_n = 0;
   cudaEvent_t ev_submit = nullptr;  // device-input batches: "everything queued on the main stream so far"
   std::vector<void*> dev_allocs, pin_allocs;
 };
@@ -187,6 +191,8 @@ struct pcdn_engine {
   uint64_t pool_bytes = 0;        // PCDN_FLAG_OUTPUT_POOL: bytes of the output pool per shard
   std::vector<UpdSlot> h_slot; std::vector<uint32_t> h_kslot; std::vector<uint8_t> h_kbytes;  // journal parts common to all shards
   bool timing = false;
+  bool timeline_async = false;      // PCDN_TIMELINE_ASYNC=1: never block; the timeline is written when the engine is destroyed
+  FILE* timeline = nullptr;         // PCDN_TIMELINE=<file>: per-batch device timestamps of the stage events (diagnostic)
   pcdn_message_hook hook[2] = {nullptr, nullptr};  // [origin]: MessageHookDef of user / broker connections
   void* hook_user[2] = {nullptr, nullptr};
   uint64_t inflight_bytes = 0;  // Limiter analogue: accepted frame bytes whose batch is not released yet
