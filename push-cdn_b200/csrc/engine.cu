@@ -119,8 +119,11 @@ int acquire_open_slot(pcdn_engine* e) {
   return fail(PCDN_EAGAIN, "all batch slots are in flight: poll and release a batch first");
 }
 
-// the adaptive pack-stream overlap applies to batches whose previous output was at most this many bytes
-static constexpr unsigned long long kOverlapMaxBytes = 2ull << 30;
+// The adaptive pack-stream overlap applies to batches whose previous output was at most this many bytes.
+// With every step queued ahead, about half of the overlapped packs lose the launch race against the next
+// control stage and run ~40 % longer (profiles/r2_timeline_overlap.txt); the overlap hides at most the
+// ~0.08 ms control stage, so it stops paying once a pack takes more than ~0.25 ms (1.5 GB of stores).
+static constexpr unsigned long long kOverlapMaxBytes = 3ull << 29;
 static constexpr uint32_t kTimelineBatches = 64;
 
 // run the kernel pipeline of one shard for slot `si`, whose BatchIn is ready (or will be, once
